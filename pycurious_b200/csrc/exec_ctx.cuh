@@ -1,0 +1,88 @@
+// Execution-context policy: every kernel body in this directory is a template
+//     template <class Ctx> __host__ __device__ void xxx_body(Ctx &cx, const Params &p)
+// that only talks to the machine through `cx`.  DevCtx maps 1:1 onto CUDA
+// intrinsics (zero overhead, everything inlines).  HostCtx (tests/emu only, built
+// when CB_EMU is defined) runs the very same body on CPU threads with barriers so
+// that kernel LOGIC can be checked in a container without a GPU.  HostCtx is test
+// infrastructure; the product library never contains or calls it.
+#pragma once
+#include "common.cuh"
+
+#ifdef __CUDACC__
+struct DevCtx {
+    char *smem_base;
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ int bid() const { return blockIdx.x; }
+    __device__ __forceinline__ int nblocks() const { return gridDim.x; }
+    __device__ __forceinline__ char *smem() const { return smem_base; }
+    __device__ __forceinline__ void sync_block() const { __syncthreads(); }
+    __device__ __forceinline__ void sync_warp() const { __syncwarp(); }
+    __device__ __forceinline__ double shfl_xor(double v, int o) const { return __shfl_xor_sync(0xffffffffu, v, o); }
+    __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ int shfl_i(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ bool any(bool pred) const { return __any_sync(0xffffffffu, pred); }
+    __device__ __forceinline__ bool all(bool pred) const { return __all_sync(0xffffffffu, pred); }
+    template <class T> __device__ __forceinline__ static T ldg(const T *p) { return __ldg(p); }
+    template <class T> __device__ __forceinline__ static T ldcg(const T *p) { return __ldcg(p); }
+    template <class T> __device__ __forceinline__ static void stcg(T *p, T v) { __stcg(p, v); }
+};
+#endif
+
+#ifdef CB_EMU
+#include <pthread.h>
+#include <vector>
+struct EmuBlock {
+    int nthreads, nblocks, bid;
+    pthread_barrier_t block_bar;
+    std::vector<pthread_barrier_t> warp_bar;
+    std::vector<double> shfl_buf;      // one slot per thread
+    std::vector<int> vote_buf;
+    std::vector<char> smem;
+};
+struct HostCtx {
+    EmuBlock *blk;
+    int tid_;
+    int tid() const { return tid_; }
+    int nthreads() const { return blk->nthreads; }
+    int bid() const { return blk->bid; }
+    int nblocks() const { return blk->nblocks; }
+    char *smem() const { return blk->smem.data(); }
+    void sync_block() const { pthread_barrier_wait(&blk->block_bar); }
+    void sync_warp() const { pthread_barrier_wait(&blk->warp_bar[tid_ >> 5]); }
+    double shfl_xor(double v, int o) const {
+        blk->shfl_buf[tid_] = v;
+        sync_warp();
+        double r = blk->shfl_buf[tid_ ^ o];
+        sync_warp();
+        return r;
+    }
+    double shfl(double v, int src) const {
+        blk->shfl_buf[tid_] = v;
+        sync_warp();
+        double r = blk->shfl_buf[(tid_ & ~31) | src];
+        sync_warp();
+        return r;
+    }
+    int shfl_i(int v, int src) const { return (int)shfl((double)v, src); }
+    bool any(bool pred) const {
+        blk->vote_buf[tid_] = pred;
+        sync_warp();
+        bool r = false;
+        for (int i = 0; i < 32; ++i) r = r || blk->vote_buf[(tid_ & ~31) | i];
+        sync_warp();
+        return r;
+    }
+    bool all(bool pred) const { return !any(!pred); }
+    template <class T> static T ldg(const T *p) { return *p; }
+    template <class T> static T ldcg(const T *p) { return *p; }
+    template <class T> static void stcg(T *p, T v) { *p = v; }
+};
+#endif
+
+template <class Ctx>
+CB_HD double ctx_warp_sum(const Ctx &cx, double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += cx.shfl_xor(v, o);
+    return v;
+}

@@ -1,0 +1,228 @@
+// Mixed-radix in-place FFT engine for one warp ("team") working on one
+// shared-memory line of N complex doubles, plus the Bluestein chirp-z core.
+//
+// Replaces numpy.fft.fft2 (pocketfft) behind pycurious/grid.py:270.
+//
+// Layout of the algorithm
+//   forward  = decimation-in-frequency, natural order in, digit-reversed out
+//   backward = decimation-in-time with the pass list reversed, digit-reversed in,
+//              natural order out
+// Both run in place: a radix-R butterfly reads and writes the same R slots, so the
+// only synchronisation is one __syncwarp() between passes.  Bluestein's circular
+// convolution never needs natural order in the frequency domain (the filter is
+// stored digit-reversed), so no reordering pass exists anywhere; the last forward
+// pass, the filter multiply and the first backward pass touch the same R
+// consecutive slots and are fused in registers (bluestein_mid_pass).
+//
+// Twiddles: per-pass compact tables T_p[(s-1)*sub + j] = exp(-2 pi i j s / L_p), so
+// that consecutive lanes (consecutive j) read consecutive 16-byte words.
+//
+// Every function is __host__ __device__ and takes (lane, nlanes) so that
+// tests can drive the identical code on the CPU, one emulated lane at a time.
+#pragma once
+#include "common.cuh"
+
+#define CB_MAX_PASS CB_MAX_RADIX_PASSES
+
+// Shared-memory lines are padded by one complex slot per 8 (16 B per 128 B): the unit-stride
+// last pass makes lane b touch slots b*R+t, which for R = 8 is a 128-byte lane stride, an
+// 8-way bank conflict on LDS.128 without the pad.
+#define CB_PAD(i) ((i) + ((i) >> 3))
+CB_HD int fft_line_slots(int n) { return CB_PAD(n) + 1; }
+
+struct FftPass {
+    int32_t radix;     // R
+    int32_t len;       // L: length of the sub-transform this pass splits (DIF) / builds (DIT)
+    int32_t sub;       // L / R
+    uint32_t magic;    // ceil(2^32 / sub) for b / sub via __umulhi (unused when sub == 1)
+    int32_t tw_off;    // offset of this pass' twiddle table (double2 units); -1 when sub == 1
+};
+
+struct FftPlan {
+    int32_t n;         // transform length N
+    int32_t npass;
+    int32_t tw_count;  // total twiddles (double2)
+    FftPass pass[CB_MAX_PASS];
+};
+
+CB_HD uint32_t fastdiv(uint32_t b, uint32_t magic) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(b, magic);
+#else
+    return (uint32_t)(((uint64_t)b * (uint64_t)magic) >> 32);
+#endif
+}
+
+// ---- radix-R forward DFT kernels: y_s = sum_t v_t exp(-2 pi i s t / R) ----
+template <int R> struct Dft;
+
+template <> struct Dft<2> {
+    CB_HD static void run(double2 *v) {
+        double2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <> struct Dft<3> {
+    CB_HD static void run(double2 *v) {
+        const double S = 0.86602540378443864676;   // sin(2 pi / 3)
+        double2 t = cadd(v[1], v[2]);
+        double2 m = cplx(fma(-0.5, t.x, v[0].x), fma(-0.5, t.y, v[0].y));
+        double2 d = cscale(csub(v[1], v[2]), S);
+        v[0] = cadd(v[0], t);
+        v[1] = cadd(m, cmul_mi(d));
+        v[2] = cadd(m, cmul_pi(d));
+    }
+};
+
+template <> struct Dft<4> {
+    CB_HD static void run(double2 *v) {
+        double2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+        double2 c = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+        v[0] = cadd(a, c);
+        v[2] = csub(a, c);
+        v[1] = cadd(b, cmul_mi(d));
+        v[3] = cadd(b, cmul_pi(d));
+    }
+};
+
+template <> struct Dft<5> {
+    CB_HD static void run(double2 *v) {
+        const double C1 = 0.30901699437494742410, C2 = -0.80901699437494742410;
+        const double S1 = 0.95105651629515357212, S2 = 0.58778525229247312917;
+        double2 a1 = cadd(v[1], v[4]), a2 = cadd(v[2], v[3]);
+        double2 b1 = csub(v[1], v[4]), b2 = csub(v[2], v[3]);
+        double2 r1 = cplx(fma(C1, a1.x, fma(C2, a2.x, v[0].x)), fma(C1, a1.y, fma(C2, a2.y, v[0].y)));
+        double2 r2 = cplx(fma(C2, a1.x, fma(C1, a2.x, v[0].x)), fma(C2, a1.y, fma(C1, a2.y, v[0].y)));
+        double2 q1 = cplx(fma(S1, b1.x, S2 * b2.x), fma(S1, b1.y, S2 * b2.y));
+        double2 q2 = cplx(fma(S2, b1.x, -S1 * b2.x), fma(S2, b1.y, -S1 * b2.y));
+        v[0] = cadd(v[0], cadd(a1, a2));
+        v[1] = cadd(r1, cmul_mi(q1));
+        v[4] = cadd(r1, cmul_pi(q1));
+        v[2] = cadd(r2, cmul_mi(q2));
+        v[3] = cadd(r2, cmul_pi(q2));
+    }
+};
+
+template <> struct Dft<8> {
+    CB_HD static void run(double2 *v) {
+        const double H = 0.70710678118654752440;   // sqrt(1/2)
+        double2 e[4] = {v[0], v[2], v[4], v[6]};
+        double2 o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<4>::run(e);
+        Dft<4>::run(o);
+        // o_k *= exp(-i pi k / 4)
+        double2 o1 = cplx(H * (o[1].x + o[1].y), H * (o[1].y - o[1].x));
+        double2 o2 = cmul_mi(o[2]);
+        double2 o3 = cplx(H * (o[3].y - o[3].x), -H * (o[3].x + o[3].y));
+        v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+        v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+        v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+    }
+};
+
+// ---- one DIF pass: butterfly then twiddle ------------------------------------
+template <int R>
+CB_HD void dif_pass(double2 *buf, const double2 *tw, const FftPass &ps, int n, int lane, int nlanes) {
+    const int sub = ps.sub;
+    const int nb = n / R;
+    for (int b = lane; b < nb; b += nlanes) {
+        int blk = (sub == 1) ? b : (int)fastdiv((uint32_t)b, ps.magic);
+        int j = b - blk * sub;
+        const int i0 = blk * ps.len + j;
+        double2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = buf[CB_PAD(i0 + t * sub)];
+        Dft<R>::run(v);
+        if (sub > 1) {
+            const double2 *w = tw + ps.tw_off + j;
+#pragma unroll
+            for (int s = 1; s < R; ++s) v[s] = cmul(v[s], w[(s - 1) * sub]);
+        }
+#pragma unroll
+        for (int s = 0; s < R; ++s) buf[CB_PAD(i0 + s * sub)] = v[s];
+    }
+}
+
+// ---- one DIT pass: twiddle then butterfly ------------------------------------
+template <int R>
+CB_HD void dit_pass(double2 *buf, const double2 *tw, const FftPass &ps, int n, int lane, int nlanes) {
+    const int sub = ps.sub;
+    const int nb = n / R;
+    for (int b = lane; b < nb; b += nlanes) {
+        int blk = (sub == 1) ? b : (int)fastdiv((uint32_t)b, ps.magic);
+        int j = b - blk * sub;
+        const int i0 = blk * ps.len + j;
+        double2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = buf[CB_PAD(i0 + t * sub)];
+        if (sub > 1) {
+            const double2 *w = tw + ps.tw_off + j;
+#pragma unroll
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], w[(t - 1) * sub]);
+        }
+        Dft<R>::run(v);
+#pragma unroll
+        for (int s = 0; s < R; ++s) buf[CB_PAD(i0 + s * sub)] = v[s];
+    }
+}
+
+// ---- fused: last DIF pass (sub == 1) -> * filter -> conj -> first DIT pass ----
+// After it, buf holds conj(Y*H) advanced by one backward pass.
+template <int R>
+CB_HD void bluestein_mid_pass(double2 *buf, const double2 *filt, int n, int lane, int nlanes) {
+    const int nb = n / R;
+    for (int b = lane; b < nb; b += nlanes) {
+        const int i0 = b * R;
+        double2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = buf[CB_PAD(i0 + t)];
+        Dft<R>::run(v);
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = cconj(cmul(v[t], filt[CB_PAD(i0 + t)]));
+        Dft<R>::run(v);
+#pragma unroll
+        for (int t = 0; t < R; ++t) buf[CB_PAD(i0 + t)] = v[t];
+    }
+}
+
+#define CB_RADIX_SWITCH(R, CALL)                   \
+    switch (R) {                                   \
+    case 2: { constexpr int RR = 2; CALL; } break; \
+    case 3: { constexpr int RR = 3; CALL; } break; \
+    case 4: { constexpr int RR = 4; CALL; } break; \
+    case 5: { constexpr int RR = 5; CALL; } break; \
+    default: { constexpr int RR = 8; CALL; } break; \
+    }
+
+// ---- team (= one warp) drivers; `cx` supplies the warp barrier ---------------------
+// natural order in -> digit-reversed out
+template <class Ctx>
+CB_BODY void fft_forward_dif(const Ctx &cx, double2 *buf, const double2 *tw, const FftPlan &pl, int lane) {
+    for (int p = 0; p < pl.npass; ++p) {
+        cx.sync_warp();
+        CB_RADIX_SWITCH(pl.pass[p].radix, dif_pass<RR>(buf, tw, pl.pass[p], pl.n, lane, CB_WARP));
+    }
+    cx.sync_warp();
+}
+
+// buf = a (zero padded to pl.n).  On return buf[k] = conj((a (*) b)[k]) in natural order, where
+// `filt` = DIF(b)/N stored digit-reversed (and padded like buf).
+template <class Ctx>
+CB_BODY void bluestein_convolve(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt,
+                                const FftPlan &pl, int lane) {
+    const int last = pl.npass - 1;
+    for (int p = 0; p < last; ++p) {
+        cx.sync_warp();
+        CB_RADIX_SWITCH(pl.pass[p].radix, dif_pass<RR>(buf, tw, pl.pass[p], pl.n, lane, CB_WARP));
+    }
+    cx.sync_warp();
+    CB_RADIX_SWITCH(pl.pass[last].radix, bluestein_mid_pass<RR>(buf, filt, pl.n, lane, CB_WARP));
+    for (int p = last - 1; p >= 0; --p) {
+        cx.sync_warp();
+        CB_RADIX_SWITCH(pl.pass[p].radix, dit_pass<RR>(buf, tw, pl.pass[p], pl.n, lane, CB_WARP));
+    }
+    cx.sync_warp();
+}

@@ -1,0 +1,167 @@
+// Spectrum stage: plan objects, launches and C-ABI entry points (include/curie_b200.h).
+// Kernel body: spectrum_body.cuh.  Replaces pycurious/grid.py:112-157, :199-216, :218-288.
+#include <cstring>
+#include <new>
+#include "spectrum_plan.h"
+
+struct cb_spectrum_plan {
+    SpectrumHostPlan hp;
+    int device = 0, sm_count = 0, occupancy = 1, grid_max = 0;
+    double2 *d_tw = nullptr, *d_chirp = nullptr, *d_filt = nullptr;
+    int32_t *d_slot = nullptr, *d_bin_ptr = nullptr, *d_bin_idx = nullptr;
+    double *d_taper_r = nullptr, *d_taper_c = nullptr;
+};
+
+extern __shared__ double2 cb_dyn_smem[];
+
+__global__ void __launch_bounds__(CB_SPEC_MAX_TEAMS * CB_WARP, 1)
+spectrum_kernel(const __grid_constant__ SpectrumParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem)};
+    spectrum_body(cx, P);
+}
+
+__global__ void __launch_bounds__(256) detrend_kernel(const __grid_constant__ DetrendParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem)};
+    detrend_body(cx, P);
+}
+
+template <class T>
+static int upload(T **dst, const std::vector<T> &src) {
+    *dst = nullptr;
+    if (src.empty()) return CB_OK;
+    CB_CUDA_TRY(cudaMalloc((void **)dst, src.size() * sizeof(T)));
+    CB_CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return CB_OK;
+}
+
+extern "C" {
+
+int cb_spectrum_plan_destroy(cb_spectrum_plan *plan) {
+    if (!plan) return CB_OK;
+    cudaFree(plan->d_tw); cudaFree(plan->d_chirp); cudaFree(plan->d_filt); cudaFree(plan->d_slot);
+    cudaFree(plan->d_bin_ptr); cudaFree(plan->d_bin_idx); cudaFree(plan->d_taper_r); cudaFree(plan->d_taper_c);
+    delete plan;
+    return CB_OK;
+}
+
+int cb_spectrum_plan_create(int nw, int nbins, const double *taper_r, const double *taper_c,
+                            const int32_t *bin_ptr, const int32_t *bin_idx, cb_spectrum_plan **out) {
+    CB_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    CB_REQUIRE(bin_ptr && bin_idx, "bin CSR is NULL");
+    CB_REQUIRE((taper_r == nullptr) == (taper_c == nullptr), "give both tapers or none");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    cb_spectrum_plan *pl = new (std::nothrow) cb_spectrum_plan();
+    if (!pl) return CB_ERR_NOMEM;
+    CB_CUDA_TRY(cudaGetDevice(&pl->device));
+    cudaDeviceProp prop;
+    CB_CUDA_TRY(cudaGetDeviceProperties(&prop, pl->device));
+    pl->sm_count = prop.multiProcessorCount;
+    if (!spectrum_plan_build_host(pl->hp, nw, nbins, taper_r, taper_c, bin_ptr, bin_idx,
+                                  (int64_t)prop.sharedMemPerBlockOptin)) {
+        cb_set_error("spectrum plan for nw=%d: %s", nw, pl->hp.error.c_str());
+        delete pl;
+        return CB_ERR_UNSUPPORTED;
+    }
+    SpectrumHostPlan &hp = pl->hp;
+#define UP(dst, src) if ((rc = upload(&pl->dst, hp.src)) != CB_OK) { cb_spectrum_plan_destroy(pl); return rc; }
+    UP(d_tw, tw) UP(d_chirp, chirp) UP(d_filt, filt) UP(d_slot, slot)
+    UP(d_bin_ptr, bin_ptr) UP(d_bin_idx, bin_idx) UP(d_taper_r, taper_r) UP(d_taper_c, taper_c)
+#undef UP
+    cudaError_t e = cudaFuncSetAttribute(spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)hp.smem_bytes);
+    if (e != cudaSuccess) {
+        cb_set_error("cudaFuncSetAttribute(smem=%lld): %s", (long long)hp.smem_bytes, cudaGetErrorString(e));
+        cb_spectrum_plan_destroy(pl);
+        return CB_ERR_CUDA;
+    }
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spectrum_kernel, hp.threads, (size_t)hp.smem_bytes);
+    if (e != cudaSuccess || occ < 1) {
+        cb_set_error("spectrum kernel does not fit an SM (threads=%d smem=%lld): %s", hp.threads,
+                     (long long)hp.smem_bytes, cudaGetErrorString(e));
+        cb_spectrum_plan_destroy(pl);
+        return CB_ERR_UNSUPPORTED;
+    }
+    pl->occupancy = occ;
+    pl->grid_max = pl->sm_count * occ;
+    *out = pl;
+    return CB_OK;
+}
+
+int cb_spectrum_plan_get_info(const cb_spectrum_plan *plan, cb_spectrum_plan_info *info) {
+    CB_REQUIRE(plan && info, "NULL argument");
+    const SpectrumHostPlan &hp = plan->hp;
+    memset(info, 0, sizeof(*info));
+    info->nw = hp.n; info->nbins = hp.nbins; info->nvh = hp.nvh; info->bluestein = hp.bluestein;
+    info->fft_len = hp.fft.n; info->npass = hp.fft.npass;
+    for (int p = 0; p < hp.fft.npass; ++p) info->radix[p] = hp.fft.pass[p].radix;
+    info->nnz_full = hp.nnz_full; info->nnz_folded = (int32_t)hp.bin_idx.size();
+    info->teams = hp.teams; info->threads = hp.threads; info->grid_max = plan->grid_max;
+    info->smem_bytes = hp.smem_bytes; info->workspace_bytes_per_cta = hp.ws_per_cta;
+    return CB_OK;
+}
+
+int cb_spectrum_plan_get_bins(const cb_spectrum_plan *plan, int32_t *bin_ptr_host, int32_t *bin_idx_host) {
+    CB_REQUIRE(plan && bin_ptr_host && bin_idx_host, "NULL argument");
+    const SpectrumHostPlan &hp = plan->hp;
+    // read back what the kernel actually uses
+    CB_CUDA_TRY(cudaMemcpy(bin_ptr_host, plan->d_bin_ptr, hp.bin_ptr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (!hp.bin_idx.empty())
+        CB_CUDA_TRY(cudaMemcpy(bin_idx_host, plan->d_bin_idx, hp.bin_idx.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return CB_OK;
+}
+
+int64_t cb_spectrum_workspace_bytes(const cb_spectrum_plan *plan) {
+    if (!plan) return 0;
+    return (int64_t)plan->grid_max * plan->hp.ws_per_cta + 256;
+}
+
+int cb_spectrum_batch(const cb_spectrum_plan *plan, const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
+                      const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin, int detrend, double power,
+                      double *phi_dev, double *sigma_dev, void *workspace_dev, int64_t workspace_bytes,
+                      void *stream) {
+    CB_REQUIRE(plan != nullptr, "plan is NULL");
+    CB_REQUIRE(nwin >= 0, "nwin < 0");
+    if (nwin == 0) return CB_OK;
+    CB_REQUIRE(grid_dev && iy0_dev && ix0_dev && phi_dev && sigma_dev && workspace_dev, "NULL buffer");
+    const SpectrumHostPlan &hp = plan->hp;
+    CB_REQUIRE(ny >= hp.n && nx >= hp.n && ld >= nx, "grid smaller than the window");
+    const int grid = (int)std::min<int64_t>(nwin, plan->grid_max);
+    uintptr_t base = ((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255;
+    CB_REQUIRE((int64_t)(base - (uintptr_t)workspace_dev) + (int64_t)grid * hp.ws_per_cta <= workspace_bytes,
+               "workspace too small (see cb_spectrum_workspace_bytes)");
+    SpectrumParams P;
+    memset(&P, 0, sizeof(P));
+    spectrum_fill_params(hp, P, plan->d_tw, plan->d_chirp, plan->d_filt, plan->d_slot, plan->d_taper_r,
+                         plan->d_taper_c, plan->d_bin_ptr, plan->d_bin_idx);
+    P.grid = grid_dev; P.ld = ld; P.iy0 = iy0_dev; P.ix0 = ix0_dev; P.nwin = nwin;
+    P.detrend = detrend ? 1 : 0; P.power = power;
+    P.phi = phi_dev; P.sigma = sigma_dev;
+    P.gt = reinterpret_cast<double2 *>(base);
+    P.lh = reinterpret_cast<double *>(base + (uintptr_t)grid * (uintptr_t)hp.gt_stride * 16);
+    spectrum_kernel<<<grid, hp.threads, (size_t)hp.smem_bytes, (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_detrend_batch(const double *grid_dev, int64_t ny, int64_t nx, int64_t ld, int nw,
+                     const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin, double *out_dev, void *stream) {
+    CB_REQUIRE(nwin >= 0 && nw >= 2, "bad sizes");
+    if (nwin == 0) return CB_OK;
+    CB_REQUIRE(grid_dev && iy0_dev && ix0_dev && out_dev, "NULL buffer");
+    CB_REQUIRE(ny >= nw && nx >= nw && ld >= nx, "grid smaller than the window");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    int dev = 0, sms = 0;
+    CB_CUDA_TRY(cudaGetDevice(&dev));
+    CB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DetrendParams P{grid_dev, ld, iy0_dev, ix0_dev, nwin, nw, out_dev};
+    const int grid = (int)std::min<int64_t>(nwin, (int64_t)sms * 8);
+    detrend_kernel<<<grid, 256, 96 * sizeof(double), (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+// Host-side plan of the spectrum stage: FFT schedule, Bluestein tables, taper, folded bin CSR,
+// shared-memory carve-up.  Pure host code (no CUDA calls) so tests/emu can reuse it.
+#pragma once
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "fft_plan.h"
+#include "spectrum_body.cuh"
+
+struct SpectrumHostPlan {
+    int n = 0, nbins = 0, nvh = 0, npad = 0, bluestein = 0;
+    FftPlan fft;
+    std::vector<double2> tw, chirp, filt;
+    std::vector<int32_t> slot;
+    std::vector<double> taper_r, taper_c;
+    bool has_taper = false;
+    std::vector<int32_t> bin_ptr, bin_idx;
+    int nnz_full = 0;
+    // shared memory layout (double2 slots) and launch shape
+    int sm_tw = 0, sm_filt = 0, sm_chirp = 0, sm_buf = 0, line_slots = 0;
+    int teams = 0, threads = 0;
+    int64_t smem_bytes = 0;
+    int64_t gt_stride = 0, lh_stride = 0, ws_per_cta = 0;
+    std::string error;
+};
+
+static const int CB_SPEC_MAX_TEAMS = 16;
+static const int CB_SPEC_RED_SLOTS = 48;      // 96 doubles of block-reduction scratch
+
+// Folds the reference-built CSR (flat ids a*n+b of the fftSHIFTED plane) onto the Hermitian
+// half plane v <= n/2 that the kernel computes: |F[u,v]| = |F[-u,-v]| for real input.
+static inline void fold_bins(int n, int nbins, const int32_t *ptr, const int32_t *idx,
+                             std::vector<int32_t> &optr, std::vector<int32_t> &oidx) {
+    const int half = n / 2;
+    optr.assign(nbins + 1, 0);
+    oidx.clear();
+    std::vector<int32_t> ids;
+    for (int b = 0; b < nbins; ++b) {
+        ids.clear();
+        for (int e = ptr[b]; e < ptr[b + 1]; ++e) {
+            int a = idx[e] / n, c = idx[e] % n;
+            int u = (a + (n + 1) / 2) % n;      // np.fft.fftshift: shifted[a] = orig[(a + ceil(n/2)) % n]
+            int v = (c + (n + 1) / 2) % n;
+            if (v > half) { u = (n - u) % n; v = n - v; }
+            ids.push_back(v * n + u);
+        }
+        std::sort(ids.begin(), ids.end());
+        // mean and population std are unchanged when every member appears the same number of
+        // times (for odd n every half-plane point of a bin is hit exactly twice): keep one copy.
+        size_t i = 0;
+        int mult = 0;
+        bool uniform = !ids.empty();
+        while (i < ids.size()) {
+            size_t j = i;
+            while (j < ids.size() && ids[j] == ids[i]) ++j;
+            int m = (int)(j - i);
+            if (!mult) mult = m;
+            else if (m != mult) { uniform = false; break; }
+            i = j;
+        }
+        if (uniform && mult > 1) ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        oidx.insert(oidx.end(), ids.begin(), ids.end());
+        optr[b + 1] = (int32_t)oidx.size();
+    }
+}
+
+static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nbins, const double *taper_r,
+                                            const double *taper_c, const int32_t *bin_ptr,
+                                            const int32_t *bin_idx, int64_t smem_limit_bytes) {
+    if (nw < 4 || nw > 16384) { hp.error = "window edge must be in [4, 16384]"; return false; }
+    if (nbins < 1) { hp.error = "nbins must be >= 1"; return false; }
+    hp.n = nw;
+    hp.nbins = nbins;
+    hp.nvh = nw / 2 + 1;
+    hp.npad = (nw + 1) & ~1;
+    // direct mixed radix when nw is 2/3/5-smooth, else Bluestein on a padded smooth length
+    if (cbplan::build_fft_plan(nw, hp.fft, hp.tw)) {
+        hp.bluestein = 0;
+        hp.slot = cbplan::digit_reversed_slots(hp.fft);
+    } else {
+        int M = cbplan::bluestein_length(nw);
+        if (!M || !cbplan::build_fft_plan(M, hp.fft, hp.tw)) { hp.error = "no FFT plan"; return false; }
+        hp.bluestein = 1;
+        cbplan::build_bluestein_tables(nw, hp.fft, hp.chirp, hp.filt);
+    }
+    hp.has_taper = taper_r && taper_c;
+    if (hp.has_taper) {
+        hp.taper_r.assign(taper_r, taper_r + nw);
+        hp.taper_c.assign(taper_c, taper_c + nw);
+    }
+    for (int b = 0; b < nbins; ++b)
+        if (bin_ptr[b + 1] < bin_ptr[b]) { hp.error = "bin_ptr not monotone"; return false; }
+    hp.nnz_full = bin_ptr[nbins] - bin_ptr[0];
+    for (int e = bin_ptr[0]; e < bin_ptr[nbins]; ++e)
+        if (bin_idx[e] < 0 || bin_idx[e] >= nw * nw) { hp.error = "bin_idx out of range"; return false; }
+    fold_bins(nw, nbins, bin_ptr, bin_idx, hp.bin_ptr, hp.bin_idx);
+
+    hp.line_slots = (fft_line_slots(hp.fft.n) + 1) & ~1;
+    hp.sm_tw = CB_SPEC_RED_SLOTS;
+    hp.sm_filt = hp.sm_tw + hp.fft.tw_count;
+    hp.sm_chirp = hp.sm_filt + (hp.bluestein ? hp.line_slots : 0);
+    hp.sm_buf = hp.sm_chirp + (hp.bluestein ? nw : 0);
+    int64_t slots_avail = smem_limit_bytes / 16 - hp.sm_buf;
+    int teams = (int)std::min<int64_t>(CB_SPEC_MAX_TEAMS, slots_avail / hp.line_slots);
+    if (teams < 1) { hp.error = "window too large for the shared-memory FFT line"; return false; }
+    teams = std::min(teams, std::max(1, hp.nvh));
+    hp.teams = teams;
+    hp.threads = teams * CB_WARP;
+    hp.smem_bytes = 16 * ((int64_t)hp.sm_buf + (int64_t)teams * hp.line_slots);
+    hp.gt_stride = (((int64_t)hp.nvh * hp.npad) + 15) & ~15LL;
+    hp.lh_stride = (((int64_t)hp.nvh * nw) + 31) & ~31LL;
+    hp.ws_per_cta = hp.gt_stride * 16 + hp.lh_stride * 8;
+    return true;
+}
+
+// Fills the plan-dependent part of the kernel parameters from pointers that live where the
+// kernel will run (device pointers for the product, host pointers for tests/emu).
+static inline void spectrum_fill_params(const SpectrumHostPlan &hp, SpectrumParams &P, const double2 *tw,
+                                        const double2 *chirp, const double2 *filt, const int32_t *slot,
+                                        const double *taper_r, const double *taper_c,
+                                        const int32_t *bin_ptr, const int32_t *bin_idx) {
+    P.n = hp.n; P.nvh = hp.nvh; P.npad = hp.npad; P.bluestein = hp.bluestein; P.fft = hp.fft;
+    P.tw = tw; P.chirp = chirp; P.filt = filt; P.slot = slot;
+    P.taper_r = hp.has_taper ? taper_r : nullptr;
+    P.taper_c = hp.has_taper ? taper_c : nullptr;
+    P.bin_ptr = bin_ptr; P.bin_idx = bin_idx; P.nbins = hp.nbins;
+    P.gt_stride = hp.gt_stride; P.lh_stride = hp.lh_stride;
+    P.sm_tw = hp.sm_tw; P.sm_filt = hp.sm_filt; P.sm_chirp = hp.sm_chirp; P.sm_buf = hp.sm_buf;
+    P.line_slots = hp.line_slots;
+}

@@ -1,0 +1,122 @@
+// CPU emulation harness for the kernel bodies (TEST INFRASTRUCTURE ONLY).
+// Compiles pycurious_b200/csrc/*_body.cuh with CB_EMU so that the same templates that the
+// CUDA kernels instantiate with DevCtx run here with HostCtx: one pthread per CUDA thread,
+// pthread barriers for __syncthreads/__syncwarp, a scratch array for shuffles.  It exists to
+// check kernel LOGIC in a container without a GPU; nothing in pycurious_b200/ loads it.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include "spectrum_plan.h"
+
+void cb_set_error(const char *fmt, ...) { (void)fmt; }
+int cb_check_device() { return CB_ERR_NO_DEVICE; }
+
+template <class F>
+static void emu_launch(int nblocks, int nthreads, size_t smem_bytes, F body) {
+    for (int b = 0; b < nblocks; ++b) {
+        EmuBlock blk;
+        blk.nthreads = nthreads; blk.nblocks = nblocks; blk.bid = b;
+        pthread_barrier_init(&blk.block_bar, nullptr, nthreads);
+        int nw = (nthreads + 31) / 32;
+        blk.warp_bar.resize(nw);
+        for (int w = 0; w < nw; ++w) {
+            int cnt = std::min(32, nthreads - 32 * w);
+            pthread_barrier_init(&blk.warp_bar[w], nullptr, cnt);
+        }
+        blk.shfl_buf.assign(nthreads, 0.0);
+        blk.vote_buf.assign(nthreads, 0);
+        blk.smem.assign(smem_bytes + 64, 0);
+        std::vector<std::thread> th;
+        th.reserve(nthreads);
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&blk, t, &body]() { HostCtx cx{&blk, t}; body(cx); });
+        for (auto &x : th) x.join();
+        pthread_barrier_destroy(&blk.block_bar);
+        for (auto &wb : blk.warp_bar) pthread_barrier_destroy(&wb);
+    }
+}
+
+extern "C" {
+
+// plan introspection without a device: FFT length, radices, folded CSR size
+int emu_spectrum_plan_info(int nw, int nbins, const int32_t *bin_ptr, const int32_t *bin_idx,
+                           int32_t *out /* bluestein, fft_len, npass, radix[12], nnz_full, nnz_folded, teams */) {
+    SpectrumHostPlan hp;
+    if (!spectrum_plan_build_host(hp, nw, nbins, nullptr, nullptr, bin_ptr, bin_idx, 232448)) return -1;
+    out[0] = hp.bluestein; out[1] = hp.fft.n; out[2] = hp.fft.npass;
+    for (int p = 0; p < CB_MAX_PASS; ++p) out[3 + p] = hp.fft.pass[p].radix;
+    out[15] = hp.nnz_full; out[16] = (int32_t)hp.bin_idx.size(); out[17] = hp.teams;
+    return 0;
+}
+
+// 1-D DFT of length n through the device FFT engine (one emulated warp), Bluestein or direct.
+int emu_dft(int n, const double *in_re_im, double *out_re_im) {
+    FftPlan fft;
+    std::vector<double2> tw, chirp, filt;
+    std::vector<int32_t> slot;
+    bool direct = cbplan::build_fft_plan(n, fft, tw);
+    if (direct) slot = cbplan::digit_reversed_slots(fft);
+    else {
+        int M = cbplan::bluestein_length(n);
+        if (!M || !cbplan::build_fft_plan(M, fft, tw)) return -1;
+        cbplan::build_bluestein_tables(n, fft, chirp, filt);
+    }
+    std::vector<double2> line(fft_line_slots(fft.n) + 2, cplx(0, 0));
+    emu_launch(1, 32, 0, [&](const HostCtx &cx) {
+        const int lane = cx.tid();
+        for (int x = lane; x < fft.n; x += 32) {
+            double2 z = cplx(0, 0);
+            if (x < n) {
+                z = cplx(in_re_im[2 * x], in_re_im[2 * x + 1]);
+                if (!direct) z = cmul(z, chirp[x]);
+            }
+            line[CB_PAD(x)] = z;
+        }
+        if (direct) fft_forward_dif(cx, line.data(), tw.data(), fft, lane);
+        else bluestein_convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
+        for (int k = lane; k < n; k += 32) {
+            double2 z = direct ? line[CB_PAD(slot[k])] : bluestein_out(line.data(), chirp.data(), k);
+            out_re_im[2 * k] = z.x;
+            out_re_im[2 * k + 1] = z.y;
+        }
+    });
+    return direct ? 0 : fft.n;
+}
+
+int emu_spectrum(int nw, int nbins, const double *taper_r, const double *taper_c, const int32_t *bin_ptr,
+                 const int32_t *bin_idx, const double *grid, int64_t ld, const int32_t *iy0,
+                 const int32_t *ix0, int64_t nwin, int detrend, double power, double *phi, double *sigma,
+                 int nblocks, int max_teams) {
+    SpectrumHostPlan hp;
+    if (!spectrum_plan_build_host(hp, nw, nbins, taper_r, taper_c, bin_ptr, bin_idx, 232448)) {
+        fprintf(stderr, "emu_spectrum: %s\n", hp.error.c_str());
+        return -1;
+    }
+    if (max_teams > 0 && hp.teams > max_teams) {
+        hp.teams = max_teams;
+        hp.threads = 32 * max_teams;
+        hp.smem_bytes = 16 * ((int64_t)hp.sm_buf + (int64_t)hp.teams * hp.line_slots);
+    }
+    SpectrumParams P;
+    memset(&P, 0, sizeof(P));
+    spectrum_fill_params(hp, P, hp.tw.data(), hp.chirp.data(), hp.filt.data(), hp.slot.data(),
+                         hp.taper_r.data(), hp.taper_c.data(), hp.bin_ptr.data(), hp.bin_idx.data());
+    P.grid = grid; P.ld = ld; P.iy0 = iy0; P.ix0 = ix0; P.nwin = nwin;
+    P.detrend = detrend; P.power = power; P.phi = phi; P.sigma = sigma;
+    std::vector<double2> gt((size_t)nblocks * hp.gt_stride);
+    std::vector<double> lh((size_t)nblocks * hp.lh_stride);
+    P.gt = gt.data(); P.lh = lh.data();
+    emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body(cx, P); });
+    return 0;
+}
+
+int emu_detrend(const double *grid, int64_t ld, int nw, const int32_t *iy0, const int32_t *ix0,
+                int64_t nwin, double *out) {
+    DetrendParams P{grid, ld, iy0, ix0, nwin, nw, out};
+    emu_launch(1, 128, 96 * sizeof(double), [&](const HostCtx &cx) { detrend_body(cx, P); });
+    return 0;
+}
+
+}  // extern "C"
