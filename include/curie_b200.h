@@ -148,6 +148,7 @@ int cb_fit_batch(const double *kh_dev, int nk,
                  const double *x0_dev /* [nwin,4] or NULL */,
                  double *x_out_dev /* [nwin,4] */, double *f_out_dev /* [nwin] or NULL */,
                  int32_t *niter_dev /* [nwin] or NULL */, int32_t *status_dev /* [nwin] or NULL */,
+                 int32_t *nfev_dev /* [nwin] or NULL: model evaluations of nk points each */,
                  void *stream);
 
 /* ------------------------------------------------------------------------

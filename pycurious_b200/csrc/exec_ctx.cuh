@@ -21,6 +21,12 @@ struct DevCtx {
     __device__ __forceinline__ double shfl_xor(double v, int o) const { return __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
     __device__ __forceinline__ int shfl_i(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ int team_lanes() const { return CB_WARP; }
+    __device__ __forceinline__ double warp_sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
     __device__ __forceinline__ bool any(bool pred) const { return __any_sync(0xffffffffu, pred); }
     __device__ __forceinline__ bool all(bool pred) const { return __all_sync(0xffffffffu, pred); }
     template <class T> __device__ __forceinline__ static T ldg(const T *p) { return __ldg(p); }
@@ -65,6 +71,11 @@ struct HostCtx {
         return r;
     }
     int shfl_i(int v, int src) const { return (int)shfl((double)v, src); }
+    int team_lanes() const { return CB_WARP; }
+    double warp_sum(double v) const {
+        for (int o = 16; o > 0; o >>= 1) v += shfl_xor(v, o);
+        return v;
+    }
     bool any(bool pred) const {
         blk->vote_buf[tid_] = pred;
         sync_warp();
@@ -78,11 +89,28 @@ struct HostCtx {
     template <class T> static T ldcg(const T *p) { return *p; }
     template <class T> static void stcg(T *p, T v) { *p = v; }
 };
-#endif
 
-template <class Ctx>
-CB_HD double ctx_warp_sum(const Ctx &cx, double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += cx.shfl_xor(v, o);
-    return v;
-}
+// One "warp" = one lane: the per-warp kernels (fit, MCMC) run serially, which is the fast way to
+// check their arithmetic on the CPU.  nthreads is the number of emulated warps per block.
+struct SerialCtx {
+    int warp_, nwarps_, bid_, nblocks_;
+    char *smem_;
+    int tid() const { return warp_ * CB_WARP; }          // lane 0 of warp `warp_`
+    int nthreads() const { return nwarps_ * CB_WARP; }
+    int bid() const { return bid_; }
+    int nblocks() const { return nblocks_; }
+    char *smem() const { return smem_; }
+    void sync_block() const {}
+    void sync_warp() const {}
+    double shfl_xor(double v, int) const { return v; }
+    double shfl(double v, int) const { return v; }
+    int shfl_i(int v, int) const { return v; }
+    int team_lanes() const { return 1; }
+    double warp_sum(double v) const { return v; }
+    bool any(bool pred) const { return pred; }
+    bool all(bool pred) const { return pred; }
+    template <class T> static T ldg(const T *p) { return *p; }
+    template <class T> static T ldcg(const T *p) { return *p; }
+    template <class T> static void stcg(T *p, T v) { *p = v; }
+};
+#endif

@@ -1,0 +1,177 @@
+// Batched Metropolis-Hastings sampler, one chain (= one window) per warp.
+// Replaces CurieOptimise.metropolis_hastings (pycurious/optimise.py:585-633) literally:
+//   burn-in  : greedy tempered climb, P = exp(-misfit/1000), accept iff P1 > P0, no uniform drawn
+//   sampling : P = exp(-misfit) with the 1e-99 floor on P0, accept iff u <= min(P1/P0, 1)
+//   bounds are NOT applied (the reference does not apply them either)
+// Random numbers: counter-based Philox4x32-10 (Salmon et al. 2011), key = seed ^ chain id,
+// counter = (step, block, phase); the stream is replicated on the host by
+// oracle/curie_oracle.py:PhiloxStream so that chains are step-comparable.
+#pragma once
+#include "bouligand.cuh"
+
+struct MhParams {
+    const double *kh;
+    int32_t nk;
+    const double *phi;      // [nwin, nk]
+    int64_t nwin;
+    cb_mh_options opt;
+    const double *x0_dev;   // [nwin,4] or NULL
+    double *out;            // mode 0: [nwin,4,nsim]; mode 1: [nwin,10]
+    int64_t *accepted;      // [nwin] or NULL
+    int32_t warps_per_block;
+};
+
+struct U32x4 { uint32_t v[4]; };
+
+CB_HD void mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+    const uint64_t p = (uint64_t)a * (uint64_t)b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+}
+
+CB_HD U32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo(0xD2511F53u, c0, hi0, lo0);
+        mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    U32x4 o;
+    o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+    return o;
+}
+
+// 52 random bits -> open interval (0,1): (n + 0.5) * 2^-52, exactly representable
+CB_HD double u52(uint32_t hi, uint32_t lo) {
+    const uint64_t n = ((uint64_t)hi << 20) ^ (uint64_t)(lo >> 12);
+    return ((double)n + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+CB_HD void cb_sincos_2pi(double u, double &s, double &c) {
+#ifdef __CUDA_ARCH__
+    sincospi(2.0 * u, &s, &c);
+#else
+    s = sin(2.0 * CB_PI * u);
+    c = cos(2.0 * CB_PI * u);
+#endif
+}
+
+// Four standard normals (two Box-Muller pairs) for step t of phase ph.
+CB_HD void philox_normal4(uint64_t t, uint32_t ph, uint32_t k0, uint32_t k1, double *z) {
+    const uint32_t tl = (uint32_t)t, th = (uint32_t)(t >> 32);
+    const U32x4 a = philox4x32_10(tl, th, 0u, ph, k0, k1);
+    const U32x4 b = philox4x32_10(tl, th, 1u, ph, k0, k1);
+    const double u[4] = {u52(a.v[0], a.v[1]), u52(a.v[2], a.v[3]), u52(b.v[0], b.v[1]), u52(b.v[2], b.v[3])};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const double r = sqrt(-2.0 * log(u[2 * p]));
+        double s, c;
+        cb_sincos_2pi(u[2 * p + 1], s, c);
+        z[2 * p] = r * c;
+        z[2 * p + 1] = r * s;
+    }
+}
+
+CB_HD double philox_uniform(uint64_t t, uint32_t ph, uint32_t k0, uint32_t k1) {
+    const U32x4 c = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 2u, ph, k0, k1);
+    return u52(c.v[0], c.v[1]);
+}
+
+template <class Ctx>
+CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
+    const int tid = cx.tid();
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nk = P.nk;
+    const int64_t w = (int64_t)cx.bid() * P.warps_per_block + warp;
+    if (w >= P.nwin) return;
+
+    double *s_k = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * 3 * nk;
+    double *s_lk = s_k + nk, *s_phi = s_lk + nk;
+    for (int i = lane; i < nk; i += cx.team_lanes()) {
+        const double k = P.kh[i];
+        s_k[i] = k;
+        s_lk[i] = log(k);
+        s_phi[i] = P.phi[w * nk + i];
+    }
+    cx.sync_warp();
+
+    const cb_mh_options &o = P.opt;
+    Priors pr;
+    double x[4], scale[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        pr.mu[j] = o.prior_mu[j];
+        pr.sigma[j] = o.prior_sigma[j];
+        scale[j] = o.x_scale[j];
+        x[j] = P.x0_dev ? P.x0_dev[w * 4 + j] : o.x0[j];
+    }
+    const uint64_t chain = o.chain_offset + (uint64_t)w;
+    const uint32_t k0 = (uint32_t)(o.seed ^ chain), k1 = (uint32_t)((o.seed >> 32) ^ (chain >> 32));
+
+    // ---- burn-in (optimise.py:598-611) ----
+    double P0 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x, pr, lane) / 1000.0);
+    for (int64_t t = 0; t < o.burnin; ++t) {
+        double z[4], x1[4];
+        philox_normal4((uint64_t)t, 0u, k0, k1, z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
+        const double P1 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x1, pr, lane) / 1000.0);
+        if (P1 > P0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = x1[j];
+            P0 = P1;
+        }
+    }
+
+    // ---- sampling (optimise.py:613-631) ----
+    P0 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x, pr, lane));
+    int64_t nacc = 0;
+    double mean[5] = {0, 0, 0, 0, 0}, m2[5] = {0, 0, 0, 0, 0};   // Welford accumulators (mode 1)
+    double *chain_out = P.out + w * 4 * o.nsim;
+    for (int64_t t = 0; t < o.nsim; ++t) {
+        double z[4], x1[4];
+        philox_normal4((uint64_t)t, 1u, k0, k1, z);
+        const double u = philox_uniform((uint64_t)t, 1u, k0, k1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
+        P0 = fmax(P0, 1e-99);
+        const double P1 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x1, pr, lane));
+        const double ratio = fmin(P1 / P0, 1.0);
+        if (u <= ratio) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = x1[j];
+            P0 = P1;
+            ++nacc;
+        }
+        if (o.reduce_mode == 0) {
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) chain_out[j * o.nsim + t] = x[j];
+            }
+        } else {
+            const double v[5] = {x[0], x[1], x[2], x[3], x[1] + x[2]};
+            const double inv = 1.0 / (double)(t + 1);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const double dlt = v[j] - mean[j];
+                mean[j] += dlt * inv;
+                m2[j] = fma(dlt, v[j] - mean[j], m2[j]);
+            }
+        }
+    }
+    if (lane == 0) {
+        if (o.reduce_mode != 0) {
+            double *mo = P.out + w * 10;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                mo[j] = mean[j];
+                mo[5 + j] = o.nsim > 0 ? sqrt(m2[j] / (double)o.nsim) : NAN;
+            }
+        }
+        if (P.accepted) P.accepted[w] = nacc;
+    }
+}

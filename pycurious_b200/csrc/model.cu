@@ -1,0 +1,178 @@
+// Forward model hooks, batched MAP fit and Metropolis-Hastings: kernels + C-ABI entry points.
+// Bodies: besselk.cuh, bouligand.cuh, fit_body.cuh, mh_body.cuh.
+#include <cstring>
+#include "fit_body.cuh"
+#include "mh_body.cuh"
+
+extern __shared__ double cb_dyn_smem_d[];
+
+#define CB_FIT_WARPS 4      // warps (= windows) per CTA in the per-warp kernels
+
+__global__ void __launch_bounds__(256) besselk_kernel(const double *nu, const double *x, int64_t n, double *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = cb_kv(nu[i], x[i]);
+}
+
+__global__ void __launch_bounds__(256)
+bouligand_kernel(const double *kh, int nk, const double *params, int64_t m, double *out) {
+    const int64_t total = m * (int64_t)nk;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / nk;
+        const int j = (int)(i - row * nk);
+        const double *p = params + 4 * row;
+        const ModelCoef mc = model_coef(p[0], p[1], p[2], p[3]);
+        const double k = kh[j];
+        out[i] = bouligand_point(mc, k, log(k));
+    }
+}
+
+struct MisfitParams {
+    const double *kh;
+    int32_t nk;
+    const double *phi;
+    int64_t phi_stride;
+    const double *params;
+    int64_t m;
+    Priors pr;
+    double *out;
+};
+
+__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) misfit_kernel(const __grid_constant__ MisfitParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * CB_FIT_WARPS + warp;
+    if (row >= P.m) return;
+    double *s_k = cb_dyn_smem_d + (int64_t)warp * 3 * P.nk, *s_lk = s_k + P.nk, *s_phi = s_lk + P.nk;
+    for (int i = lane; i < P.nk; i += CB_WARP) {
+        s_k[i] = P.kh[i];
+        s_lk[i] = log(P.kh[i]);
+        s_phi[i] = P.phi[row * P.phi_stride + i];
+    }
+    __syncwarp();
+    double x[4];
+    for (int j = 0; j < 4; ++j) x[j] = P.params[row * 4 + j];
+    const double f = misfit_warp(cx, s_k, s_lk, s_phi, P.nk, x, P.pr, lane);
+    if (lane == 0) P.out[row] = f;
+}
+
+__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) fit_kernel(const __grid_constant__ FitParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
+    fit_body(cx, P);
+}
+
+__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) mh_kernel(const __grid_constant__ MhParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
+    mh_body(cx, P);
+}
+
+static int elementwise_grid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+extern "C" {
+
+int cb_besselk(const double *nu_dev, const double *x_dev, int64_t n, double *out_dev, void *stream) {
+    CB_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(nu_dev && x_dev && out_dev, "NULL buffer");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    besselk_kernel<<<elementwise_grid(n), 256, 0, (cudaStream_t)stream>>>(nu_dev, x_dev, n, out_dev);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_bouligand_forward(const double *kh_dev, int nk, const double *params_dev, int64_t m, double *out_dev,
+                         void *stream) {
+    CB_REQUIRE(nk > 0 && m >= 0, "bad sizes");
+    if (m == 0) return CB_OK;
+    CB_REQUIRE(kh_dev && params_dev && out_dev, "NULL buffer");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    bouligand_kernel<<<elementwise_grid(m * nk), 256, 0, (cudaStream_t)stream>>>(kh_dev, nk, params_dev, m, out_dev);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+static int per_warp_launch_shape(int nk, int64_t nwin, int *grid, size_t *smem) {
+    CB_REQUIRE(nk > 0 && nk <= 4096, "nk must be in [1, 4096]");
+    *smem = (size_t)CB_FIT_WARPS * 3 * (size_t)nk * sizeof(double);
+    int64_t g = (nwin + CB_FIT_WARPS - 1) / CB_FIT_WARPS;
+    CB_REQUIRE(g <= 2147483647LL, "too many windows for one launch");
+    *grid = (int)g;
+    return CB_OK;
+}
+
+int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_stride, const double *params_dev,
+              int64_t m, const double *prior_mu_host, const double *prior_sigma_host, double *out_dev,
+              void *stream) {
+    CB_REQUIRE(m >= 0, "m < 0");
+    if (m == 0) return CB_OK;
+    CB_REQUIRE(kh_dev && phi_dev && params_dev && out_dev, "NULL buffer");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    int grid;
+    size_t smem;
+    if ((rc = per_warp_launch_shape(nk, m, &grid, &smem)) != CB_OK) return rc;
+    MisfitParams P;
+    P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.phi_stride = phi_stride; P.params = params_dev; P.m = m; P.out = out_dev;
+    for (int j = 0; j < 4; ++j) {
+        P.pr.mu[j] = prior_mu_host ? prior_mu_host[j] : NAN;
+        P.pr.sigma[j] = prior_sigma_host ? prior_sigma_host[j] : NAN;
+    }
+    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    misfit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_fit_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwin, const cb_fit_options *opt_host,
+                 const double *x0_dev, double *x_out_dev, double *f_out_dev, int32_t *niter_dev,
+                 int32_t *status_dev, int32_t *nfev_dev, void *stream) {
+    CB_REQUIRE(nwin >= 0, "nwin < 0");
+    if (nwin == 0) return CB_OK;
+    CB_REQUIRE(kh_dev && phi_dev && opt_host && x_out_dev, "NULL buffer");
+    for (int j = 0; j < 4; ++j) {
+        CB_REQUIRE(!(opt_host->lb[j] > opt_host->ub[j]), "lower bound above upper bound");
+        CB_REQUIRE(isnan(opt_host->prior_mu[j]) || opt_host->prior_sigma[j] > 0.0, "prior sigma must be > 0");
+    }
+    int rc = cb_check_device();
+    if (rc) return rc;
+    int grid;
+    size_t smem;
+    if ((rc = per_warp_launch_shape(nk, nwin, &grid, &smem)) != CB_OK) return rc;
+    FitParams P;
+    memset(&P, 0, sizeof(P));
+    P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
+    P.x_out = x_out_dev; P.f_out = f_out_dev; P.niter = niter_dev; P.status = status_dev; P.nfev = nfev_dev;
+    P.warps_per_block = CB_FIT_WARPS;
+    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_mh_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwin, const cb_mh_options *opt_host,
+                const double *x0_dev, double *out_dev, int64_t *accepted_dev, void *stream) {
+    CB_REQUIRE(nwin >= 0, "nwin < 0");
+    if (nwin == 0) return CB_OK;
+    CB_REQUIRE(kh_dev && phi_dev && opt_host && out_dev, "NULL buffer");
+    CB_REQUIRE(opt_host->nsim >= 0 && opt_host->burnin >= 0, "negative chain length");
+    CB_REQUIRE(opt_host->reduce_mode == 0 || opt_host->reduce_mode == 1, "reduce_mode must be 0 or 1");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    int grid;
+    size_t smem;
+    if ((rc = per_warp_launch_shape(nk, nwin, &grid, &smem)) != CB_OK) return rc;
+    MhParams P;
+    memset(&P, 0, sizeof(P));
+    P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
+    P.out = out_dev; P.accepted = accepted_dev; P.warps_per_block = CB_FIT_WARPS;
+    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mh_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+}  // extern "C"

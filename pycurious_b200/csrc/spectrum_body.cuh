@@ -96,9 +96,9 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                 sx += rx;
                 sy = fma((double)y - ctr, r0, sy);
             }
-            s0 = ctx_warp_sum(cx, s0);
-            sx = ctx_warp_sum(cx, sx);
-            sy = ctx_warp_sum(cx, sy);
+            s0 = cx.warp_sum(s0);
+            sx = cx.warp_sum(sx);
+            sy = cx.warp_sum(sy);
             if (lane == 0) { s_red[warp] = s0; s_red[32 + warp] = sx; s_red[64 + warp] = sy; }
             cx.sync_block();
             s0 = sx = sy = 0.0;
@@ -188,7 +188,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
             const int lo = Ctx::ldg(P.bin_ptr + b), hi = Ctx::ldg(P.bin_ptr + b + 1);
             double s = 0.0;
             for (int e = lo + lane; e < hi; e += CB_WARP) s += Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e));
-            s = ctx_warp_sum(cx, s);
+            s = cx.warp_sum(s);
             const double cnt = (double)(hi - lo);
             const double mean = s / cnt;
             double q = 0.0;
@@ -196,7 +196,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                 const double d = Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e)) - mean;
                 q = fma(d, d, q);
             }
-            q = ctx_warp_sum(cx, q);
+            q = cx.warp_sum(q);
             if (lane == 0) {
                 P.phi[w * P.nbins + b] = P.power * mean;
                 P.sigma[w * P.nbins + b] = fabs(P.power) * sqrt(q / cnt);
@@ -239,9 +239,9 @@ CB_BODY void detrend_body(const Ctx &cx, const DetrendParams &P) {
             sx += rx;
             sy = fma((double)y - ctr, r0, sy);
         }
-        s0 = ctx_warp_sum(cx, s0);
-        sx = ctx_warp_sum(cx, sx);
-        sy = ctx_warp_sum(cx, sy);
+        s0 = cx.warp_sum(s0);
+        sx = cx.warp_sum(sx);
+        sy = cx.warp_sum(sy);
         if (lane == 0) { s_red[warp] = s0; s_red[32 + warp] = sx; s_red[64 + warp] = sy; }
         cx.sync_block();
         s0 = sx = sy = 0.0;

@@ -9,6 +9,8 @@
 #include <functional>
 #include <thread>
 #include "spectrum_plan.h"
+#include "fit_body.cuh"
+#include "mh_body.cuh"
 
 void cb_set_error(const char *fmt, ...) { (void)fmt; }
 int cb_check_device() { return CB_ERR_NO_DEVICE; }
@@ -117,6 +119,85 @@ int emu_detrend(const double *grid, int64_t ld, int nw, const int32_t *iy0, cons
     DetrendParams P{grid, ld, iy0, ix0, nwin, nw, out};
     emu_launch(1, 128, 96 * sizeof(double), [&](const HostCtx &cx) { detrend_body(cx, P); });
     return 0;
+}
+
+// ---- forward model hooks ---------------------------------------------------------------------
+void emu_besselk(const double *nu, const double *x, int64_t n, double *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = cb_kv(nu[i], x[i]);
+}
+
+void emu_gamma(const double *z, int64_t n, double *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = cb_gamma(z[i]);
+}
+
+void emu_bouligand(const double *kh, int nk, const double *params, int64_t m, double *out) {
+    for (int64_t r = 0; r < m; ++r) {
+        const double *p = params + 4 * r;
+        ModelCoef mc = model_coef(p[0], p[1], p[2], p[3]);
+        for (int j = 0; j < nk; ++j) out[r * nk + j] = bouligand_point(mc, kh[j], log(kh[j]));
+    }
+}
+
+// analytic dPhi/ddz (used by the fit) for finite-difference checks
+void emu_bouligand_ddz(const double *kh, int nk, const double *p, double *phi, double *dphi) {
+    ModelCoef mc = model_coef(p[0], p[1], p[2], p[3]);
+    for (int j = 0; j < nk; ++j) phi[j] = bouligand_point_ddz(mc, kh[j], log(kh[j]), dphi[j]);
+}
+
+void emu_misfit(const double *kh, int nk, const double *phi, int64_t phi_stride, const double *params, int64_t m,
+                const double *prior_mu, const double *prior_sigma, double *out) {
+    Priors pr;
+    for (int j = 0; j < 4; ++j) { pr.mu[j] = prior_mu ? prior_mu[j] : NAN; pr.sigma[j] = prior_sigma ? prior_sigma[j] : NAN; }
+    std::vector<double> lk(nk);
+    for (int j = 0; j < nk; ++j) lk[j] = log(kh[j]);
+    SerialCtx cx{0, 1, 0, 1, nullptr};
+    for (int64_t r = 0; r < m; ++r)
+        out[r] = misfit_warp(cx, kh, lk.data(), phi + r * phi_stride, nk, params + 4 * r, pr, 0);
+}
+
+// mode 0: SerialCtx (one lane per warp, fast); mode 1: HostCtx (32 pthreads per warp, checks the shuffles)
+int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_fit_options *opt, const double *x0,
+            double *x_out, double *f_out, int32_t *niter, int32_t *status, int32_t *nfev, int mode) {
+    FitParams P;
+    memset(&P, 0, sizeof(P));
+    P.kh = kh; P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0;
+    P.x_out = x_out; P.f_out = f_out; P.niter = niter; P.status = status; P.nfev = nfev;
+    if (mode == 0) {
+        P.warps_per_block = 1;
+        std::vector<double> sm(3 * nk);
+        for (int64_t w = 0; w < nwin; ++w) {
+            SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
+            fit_body(cx, P);
+        }
+    } else {
+        P.warps_per_block = 2;
+        emu_launch((int)((nwin + 1) / 2), 64, 2 * 3 * nk * sizeof(double), [&](const HostCtx &cx) { fit_body(cx, P); });
+    }
+    return 0;
+}
+
+int emu_mh(const double *kh, int nk, const double *phi, int64_t nwin, const cb_mh_options *opt, const double *x0,
+           double *out, int64_t *accepted, int mode) {
+    MhParams P;
+    memset(&P, 0, sizeof(P));
+    P.kh = kh; P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0; P.out = out; P.accepted = accepted;
+    if (mode == 0) {
+        P.warps_per_block = 1;
+        std::vector<double> sm(3 * nk);
+        for (int64_t w = 0; w < nwin; ++w) {
+            SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
+            mh_body(cx, P);
+        }
+    } else {
+        P.warps_per_block = 2;
+        emu_launch((int)((nwin + 1) / 2), 64, 2 * 3 * nk * sizeof(double), [&](const HostCtx &cx) { mh_body(cx, P); });
+    }
+    return 0;
+}
+
+void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {
+    U32x4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    for (int i = 0; i < 4; ++i) out[i] = r.v[i];
 }
 
 }  // extern "C"
