@@ -47,6 +47,11 @@ const char *cb_last_error(void);
 /* SM count, compute capability and opt-in shared memory of the current device. */
 int cb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_optin_bytes);
 
+/* Measures the FP64 FMA rate of the current device with a register-resident DFMA chain kernel
+ * (roofline denominator for the Bessel / fit / MCMC kernels; MEASURED_PEAKS.json has no FP64 entry).
+ * Synchronous; *tflops_out = 2 * DFMA/s / 1e12. */
+int cb_fp64_fma_peak(double *tflops_out);
+
 /* ------------------------------------------------------------------------
  * Spectrum stage:  CurieGrid.subgrid -> [remove_trend_linear] -> radial_spectrum
  * replaces pycurious/grid.py:112-157 (window gather), :199-216 (plane detrend),
@@ -120,6 +125,8 @@ int cb_besselk(const double *nu_dev, const double *x_dev, int64_t n, double *out
 /* out[m, j] = bouligand2009(kh[j], params[m,0..3]); params rows are (beta, zt, dz, C). */
 int cb_bouligand_forward(const double *kh_dev, int nk, const double *params_dev, int64_t m,
                          double *out_dev, void *stream);
+/* out[i] = bouligand2009(kh[i], params[i,0..3]): fully element-wise (the caller broadcasts). */
+int cb_bouligand_points(const double *kh_dev, const double *params_dev, int64_t n, double *out_dev, void *stream);
 /* out[m] = CurieOptimise.min_func(params[m], kh, phi[m or 0]) incl. priors (optimise.py:196-230);
  * phi_stride = 0 shares one spectrum between all rows.  prior_mu[i] = NaN means no prior. */
 int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_stride,

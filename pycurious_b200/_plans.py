@@ -1,0 +1,272 @@
+"""Host-side planning for the device kernels.
+
+Everything here is O(window) work done once per (window size, grid spacing, taper)
+and cached: centroid -> node index rule, taper vectors, the radial-bin membership
+CSR and wavenumber axis, Radon ray end points.  The membership and the end
+points are computed with the reference's own numpy expressions so that the
+integers the kernels consume are bit-identical to what pycurious would use
+(pycurious/grid.py:135-139, :242-245, :277-282; src/radon.pyx:30-96).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+import weakref
+
+import numpy as np
+
+from . import _lib
+
+
+# ----------------------------------------------------------------------------
+# centroid -> window origin  (CurieGrid.subgrid, pycurious/grid.py:130-155)
+# ----------------------------------------------------------------------------
+def nearest_node(coords, q):
+    """Vectorised `np.abs(coords - q).argmin()` for increasing `coords`: the distance profile
+    is V-shaped, so the argmin is one of the two bracketing nodes and ties go to the lower
+    index, exactly like argmin's first-minimum rule."""
+    q = np.asarray(q, dtype=np.float64)
+    hi = np.clip(np.searchsorted(coords, q, side="left"), 0, coords.size - 1)
+    lo = np.clip(hi - 1, 0, coords.size - 1)
+    pick_lo = np.abs(coords[lo] - q) <= np.abs(coords[hi] - q)
+    return np.where(pick_lo, lo, hi).astype(np.int64)
+
+
+def window_nodes(window, dx):
+    nw = int(round(window / dx))
+    return nw, nw // 2
+
+
+def window_origins(g, window, xc, yc):
+    """Top-left nodes (iy0, ix0) and edge n of the windows CurieGrid.subgrid would cut around each
+    centroid; raises the reference's ValueErrors for the first offending centroid."""
+    xc = np.atleast_1d(np.asarray(xc, dtype=np.float64))
+    yc = np.atleast_1d(np.asarray(yc, dtype=np.float64))
+    outside = (xc < g.xmin) | (xc > g.xmax) | (yc < g.ymin) | (yc > g.ymax)
+    if outside.any():
+        i = int(np.flatnonzero(outside)[0])
+        raise ValueError("Point {} outside data range".format((xc[i], yc[i])))
+    _, half = window_nodes(window, g.dx)
+    ix = nearest_node(g.xcoords, xc)
+    iy = nearest_node(g.ycoords, yc)
+    bad = (ix - half < 0) | (ix + half + 1 > g.nx) | (iy - half < 0) | (iy + half + 1 > g.ny)
+    if bad.any():
+        i = int(np.flatnonzero(bad)[0])
+        raise ValueError("Window size {} at centroid {} exceeds the data range".format(window, (xc[i], yc[i])))
+    return (iy - half).astype(np.int32), (ix - half).astype(np.int32), 2 * half + 1
+
+
+# ----------------------------------------------------------------------------
+# radial bins  (CurieGrid._taper_spectrum / _FFT_spectrum, grid.py:242-245, :277-286)
+# ----------------------------------------------------------------------------
+_bin_cache = {}
+
+
+def radial_bins(nr, dx, scale=0.001):
+    """(kbins, k, bin_ptr, bin_idx): bin edges, mean wavenumber per bin, and the CSR of member
+    indices a*nr+b in the fftshifted plane.  Same numpy expressions as the reference, so membership
+    (decided by floating-point rounding of hypot/arange) is bit-identical."""
+    key = (int(nr), float(dx), float(scale))
+    hit = _bin_cache.get(key)
+    if hit is not None:
+        return hit
+    dk = 2.0 * np.pi / (nr - 1) / (dx * scale)
+    kbins = np.arange(dk, dk * nr / 2, dk)
+    nbins = kbins.size - 1
+    c = int((nr - 1) // 2)
+    a, b = np.mgrid[0:nr, 0:nr]
+    kk = np.hypot((a - c) * dk, (b - c) * dk)
+    flat = kk.ravel()
+    k = np.empty(max(nbins, 0))
+    ptr = np.zeros(max(nbins, 0) + 1, dtype=np.int32)
+    members = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(nbins):
+            m = np.flatnonzero(np.logical_and(flat >= kbins[i], flat <= kbins[i + 1])).astype(np.int32)
+            members.append(m)
+            ptr[i + 1] = ptr[i] + m.size
+            k[i] = flat[m].mean() if m.size else np.nan
+    idx = np.concatenate(members) if members else np.zeros(0, dtype=np.int32)
+    out = (kbins, k, ptr, np.ascontiguousarray(idx, dtype=np.int32))
+    _bin_cache[key] = out
+    return out
+
+
+# ----------------------------------------------------------------------------
+# spectrum plans
+# ----------------------------------------------------------------------------
+class SpectrumPlan:
+    """Owns a cb_spectrum_plan plus its scratch slab on the current device."""
+
+    def __init__(self, nw, dx, taper_vec):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        self.nw = int(nw)
+        self.kbins, self.k, ptr, idx = radial_bins(nw, dx)
+        self.nbins = int(self.k.size)
+        if self.nbins < 1:
+            raise ValueError("window of {} nodes is too small for a radial spectrum".format(nw))
+        self._taper = None if taper_vec is None else np.ascontiguousarray(taper_vec, dtype=np.float64)
+        tp = None if self._taper is None else self._taper.ctypes.data
+        handle = C.c_void_p()
+        _lib.check(lib.cb_spectrum_plan_create(self.nw, self.nbins, tp, tp, ptr.ctypes.data, idx.ctypes.data,
+                                               C.byref(handle)))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, lib.cb_spectrum_plan_destroy, handle)
+        nbytes = int(lib.cb_spectrum_workspace_bytes(handle))
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        self.device = torch.cuda.current_device()
+
+    def info(self):
+        info = _lib.SpectrumPlanInfo()
+        _lib.check(_lib.load().cb_spectrum_plan_get_info(self.handle, C.byref(info)))
+        return info
+
+    def folded_bins(self):
+        info = self.info()
+        ptr = np.empty(self.nbins + 1, dtype=np.int32)
+        idx = np.empty(info.nnz_folded, dtype=np.int32)
+        _lib.check(_lib.load().cb_spectrum_plan_get_bins(self.handle, ptr.ctypes.data, idx.ctypes.data))
+        return ptr, idx
+
+    def run(self, grid_t, iy0_t, ix0_t, detrend, power):
+        """grid_t: 2-D float64 cuda tensor; iy0_t/ix0_t: int32 cuda tensors -> (Phi, sigma) cuda [n, nbins]."""
+        torch = _lib.require_cuda()
+        n = int(iy0_t.numel())
+        phi = torch.empty((n, self.nbins), dtype=torch.float64, device="cuda")
+        sig = torch.empty((n, self.nbins), dtype=torch.float64, device="cuda")
+        ny, nx = grid_t.shape
+        _lib.check(_lib.load().cb_spectrum_batch(
+            self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0), iy0_t.data_ptr(), ix0_t.data_ptr(), n,
+            1 if detrend else 0, float(power), phi.data_ptr(), sig.data_ptr(),
+            self.workspace.data_ptr(), self.workspace.numel(), _lib.stream_ptr(torch)))
+        return phi, sig
+
+
+_plan_cache = {}
+
+
+def taper_vector(taper, n, **kwargs):
+    """The 1-D taper the reference would build (grid.py:233-237); None stays None."""
+    if taper is None:
+        return None
+    return np.asarray(taper(n, **kwargs), dtype=np.float64)
+
+
+def spectrum_plan(nw, dx, taper_vec):
+    torch = _lib.require_cuda()
+    key = (int(nw), float(dx), None if taper_vec is None else taper_vec.tobytes(), torch.cuda.current_device())
+    plan = _plan_cache.get(key)
+    if plan is None:
+        if len(_plan_cache) > 32:
+            _plan_cache.clear()
+        plan = SpectrumPlan(nw, dx, taper_vec)
+        _plan_cache[key] = plan
+    return plan
+
+
+# ----------------------------------------------------------------------------
+# Radon ray end points  (src/radon.pyx:30-96)
+# ----------------------------------------------------------------------------
+def radon_endpoints(nw, theta):
+    """Tx, Rx of shape (nw, 2) for one angle, evaluated with numpy scalars in the reference's
+    operation order so the doubles handed to the tracer are the same."""
+    nx = ny = nw
+    idx = np.arange(nw)
+    Tx = np.zeros((nw, 2))
+    Rx = np.zeros((nw, 2))
+    th = np.float64(theta)
+    if th == 0.0:
+        Tx[:, 0] = idx
+        Rx[:, 0] = idx
+        Rx[:, 1] = ny - 1
+        return Tx, Rx
+    if np.abs(th - np.pi / 2) < 1.e-10:
+        Tx[:, 1] = idx
+        Rx[:, 0] = nx - 1
+        Rx[:, 1] = idx
+        return Tx, Rx
+    co, si = np.cos(th), np.sin(th)
+    xk = nw / 2 * (1. - co) + idx * co
+    yk = nw / 2 * (1. - si) + idx * si
+    if th < np.pi / 2:
+        tn = np.tan(th)
+        x0 = np.zeros(nw)
+        y0 = yk + (xk - x0) / tn
+        over = y0 > ny - 1
+        y0 = np.where(over, ny - 1, y0)
+        x0 = np.where(over, xk - (y0 - yk) * tn, x0)
+        x1 = np.full(nw, nx - 1.0)
+        y1 = yk - (x1 - xk) / tn
+        under = y1 < 0.0
+        y1 = np.where(under, 0.0, y1)
+        x1 = np.where(under, xk + (yk - y1) * tn, x1)
+    else:
+        tq = np.tan(th - np.pi / 2.0)
+        x0 = np.full(nw, nx - 1.0)
+        y0 = yk + (x0 - xk) * tq
+        over = y0 > ny - 1
+        y0 = np.where(over, ny - 1, y0)
+        x0 = np.where(over, xk + (y0 - yk) / tq, x0)
+        x1 = np.zeros(nw)
+        y1 = yk - (xk - x1) * tq
+        under = y1 < 0.0
+        y1 = np.where(under, 0.0, y1)
+        x1 = np.where(under, xk - (yk - y1) / tq, x1)
+    Tx[:, 0], Tx[:, 1], Rx[:, 0], Rx[:, 1] = x0, y0, x1, y1
+    return Tx, Rx
+
+
+class RadonPlan:
+    """Device CSR of the ray/cell intersection lengths for one (nw, theta list)."""
+
+    def __init__(self, nw, theta):
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.nw = int(nw)
+        self.theta = np.ascontiguousarray(theta, dtype=np.float64)
+        ends = [radon_endpoints(self.nw, t) for t in self.theta]
+        self.tx = np.ascontiguousarray(np.stack([e[0] for e in ends]))
+        self.rx = np.ascontiguousarray(np.stack([e[1] for e in ends]))
+        handle = C.c_void_p()
+        _lib.check(lib.cb_radon_plan_create(self.nw, self.theta.size, self.tx.ctypes.data, self.rx.ctypes.data,
+                                            C.byref(handle)))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, lib.cb_radon_plan_destroy, handle)
+        self.nnz = int(lib.cb_radon_plan_nnz(handle))
+
+    def csr(self):
+        """(data f64, indices i64, indptr i64 [ntheta, nw+1]) as traced on the device."""
+        data = np.empty(self.nnz, dtype=np.float64)
+        indices = np.empty(self.nnz, dtype=np.int64)
+        indptr = np.empty((self.theta.size, self.nw + 1), dtype=np.int64)
+        _lib.check(_lib.load().cb_radon_plan_get_csr(self.handle, data.ctypes.data, indices.ctypes.data,
+                                                     indptr.ctypes.data))
+        return data, indices, indptr
+
+    def apply(self, grid_t, iy0_t, ix0_t):
+        torch = _lib.require_cuda()
+        n = int(iy0_t.numel())
+        sino = torch.empty((n, self.nw, self.theta.size), dtype=torch.float64, device="cuda")
+        ny, nx = grid_t.shape
+        _lib.check(_lib.load().cb_radon_apply_batch(self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0),
+                                                    iy0_t.data_ptr(), ix0_t.data_ptr(), n, sino.data_ptr(),
+                                                    _lib.stream_ptr(torch)))
+        return sino
+
+
+_radon_cache = {}
+
+
+def radon_plan(nw, theta):
+    torch = _lib.require_cuda()
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    key = (int(nw), theta.tobytes(), torch.cuda.current_device())
+    plan = _radon_cache.get(key)
+    if plan is None:
+        if len(_radon_cache) > 8:
+            _radon_cache.clear()
+        plan = RadonPlan(nw, theta)
+        _radon_cache[key] = plan
+    return plan

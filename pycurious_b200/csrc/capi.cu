@@ -44,4 +44,53 @@ int cb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_op
     return CB_OK;
 }
 
+int cb_fp64_fma_peak(double *tflops_out);
+
 }  // extern "C"
+
+// 16 independent DFMA chains per thread, 4096 iterations: 2 * 16 * 4096 flop per thread.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, double a, double b) {
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < 4096; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fma(v[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 123456.789) sink[0] = s;     // never true; keeps the chain alive
+}
+
+extern "C" int cb_fp64_fma_peak(double *tflops_out) {
+    CB_REQUIRE(tflops_out != nullptr, "NULL output");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    int dev = 0, sms = 0;
+    CB_CUDA_TRY(cudaGetDevice(&dev));
+    CB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *sink = nullptr;
+    CB_CUDA_TRY(cudaMalloc((void **)&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CB_CUDA_TRY(cudaEventCreate(&e0));
+    CB_CUDA_TRY(cudaEventCreate(&e1));
+    const int grid = sms * 16, block = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CB_CUDA_TRY(cudaEventRecord(e0));
+        fp64_peak_kernel<<<grid, block>>>(sink, 0.999999, 1e-9);
+        CB_CUDA_TRY(cudaEventRecord(e1));
+        CB_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double flop = 2.0 * 16.0 * 4096.0 * (double)grid * (double)block;
+        const double tf = flop / ((double)ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops_out = best;
+    return CB_OK;
+}

@@ -26,6 +26,16 @@ bouligand_kernel(const double *kh, int nk, const double *params, int64_t m, doub
     }
 }
 
+__global__ void __launch_bounds__(256)
+bouligand_points_kernel(const double *kh, const double *params, int64_t n, double *out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double *p = params + 4 * i;
+        const ModelCoef mc = model_coef(p[0], p[1], p[2], p[3]);
+        const double k = kh[i];
+        out[i] = bouligand_point(mc, k, log(k));
+    }
+}
+
 struct MisfitParams {
     const double *kh;
     int32_t nk;
@@ -91,6 +101,17 @@ int cb_bouligand_forward(const double *kh_dev, int nk, const double *params_dev,
     int rc = cb_check_device();
     if (rc) return rc;
     bouligand_kernel<<<elementwise_grid(m * nk), 256, 0, (cudaStream_t)stream>>>(kh_dev, nk, params_dev, m, out_dev);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_bouligand_points(const double *kh_dev, const double *params_dev, int64_t n, double *out_dev, void *stream) {
+    CB_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return CB_OK;
+    CB_REQUIRE(kh_dev && params_dev && out_dev, "NULL buffer");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    bouligand_points_kernel<<<elementwise_grid(n), 256, 0, (cudaStream_t)stream>>>(kh_dev, params_dev, n, out_dev);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }

@@ -1,0 +1,283 @@
+"""Drop-in `CurieGrid` whose per-window work runs on a B200.
+
+Mirrors the public surface of the reference's pycurious/grid.py (v1.1.1) for the
+hot path: same constructor, method names, argument meaning, return containers
+and error messages.  The arithmetic is done by
+hand-written sm_100a kernels behind the C-ABI in include/curie_b200.h; numpy is
+only used for O(n) host-side bookkeeping (coordinates, index rules, plans).
+There is no CPU fallback: without the CUDA library / a GPU the compute
+methods raise.
+
+New, keyword-only batched entry points (not in the reference) are provided for
+callers that want many windows per call: `radial_spectrum_batch`,
+`azimuthal_spectrum_batch`, `remove_trend_linear_batch`.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+from . import _lib, _plans
+
+
+class CurieGrid(object):
+    """Accepts a 2D array and its extent (xmin, xmax, ymin, ymax) in metres
+    (reference: pycurious/grid.py:49-110).
+
+    Attributes kept from the reference: data, xmin, xmax, ymin, ymax, dx, dy, nx, ny,
+    xcoords, ycoords.
+    """
+
+    def __init__(self, grid, xmin, xmax, ymin, ymax):
+        self.data = np.array(grid)
+        ny, nx = self.data.shape
+        self.xmin, self.xmax = xmin, xmax
+        self.ymin, self.ymax = ymin, ymax
+        self.xcoords, dx = np.linspace(xmin, xmax, nx, retstep=True)
+        self.ycoords, dy = np.linspace(ymin, ymax, ny, retstep=True)
+        self.nx, self.ny = nx, ny
+        self.dx, self.dy = dx, dy
+        # grid.py:109 hands 1.0 to np.allclose as rtol; kept as is
+        if not np.allclose(dx, dy, 1.0):
+            raise ValueError("node spacing should be identical {}".format((dx, dy)))
+        self._dev_grid = None
+        self._dev_src = None
+
+    # ------------------------------------------------------------------ device residency
+    def device_grid(self):
+        """float64 CUDA copy of `self.data` (uploaded once, re-uploaded if `self.data` is rebound)."""
+        torch = _lib.require_cuda()
+        if (self._dev_grid is None or self._dev_src is not self.data
+                or self._dev_grid.device.index != torch.cuda.current_device()):
+            if getattr(self, "_pinned", None) is not None and self._pinned_src is self.data:
+                self._dev_grid = self._pinned.to("cuda", non_blocking=True)
+            else:
+                host = np.ascontiguousarray(self.data, dtype=np.float64)
+                self._dev_grid = torch.from_numpy(host).cuda()
+            self._dev_src = self.data
+        return self._dev_grid
+
+    def pin_host(self):
+        """Stage `self.data` in page-locked host memory so that uploads run at full PCIe speed
+        (used by bench.py's end-to-end leg; optional)."""
+        torch = _lib.require_cuda()
+        host = np.ascontiguousarray(self.data, dtype=np.float64)
+        self._pinned = torch.from_numpy(host).pin_memory()
+        self._pinned_src = self.data
+        return self
+
+    def invalidate_device(self):
+        """Call after modifying `self.data` in place."""
+        self._dev_grid = None
+
+    def _locate_view(self, arr):
+        """If `arr` is a square, unit-stride view into self.data (what subgrid returns), give its
+        top-left node so the resident device grid can be used instead of an upload."""
+        d = self.data
+        if (not isinstance(arr, np.ndarray) or arr.ndim != 2 or arr.dtype != d.dtype or d.dtype != np.float64
+                or not d.flags.c_contiguous or arr.strides != d.strides or arr.size == 0):
+            return None
+        off = arr.__array_interface__["data"][0] - d.__array_interface__["data"][0]
+        if off < 0 or off % d.itemsize:
+            return None
+        off //= d.itemsize
+        j0, i0 = divmod(off, self.nx)
+        if j0 + arr.shape[0] > self.ny or i0 + arr.shape[1] > self.nx:
+            return None
+        if not np.shares_memory(arr, d):
+            return None
+        return int(j0), int(i0)
+
+    def _as_device_windows(self, subgrid):
+        """(grid tensor, iy0, ix0) describing one host array as a single device window."""
+        torch = _lib.require_cuda()
+        loc = self._locate_view(subgrid)
+        if loc is not None:
+            g = self.device_grid()
+            j0, i0 = loc
+        else:
+            g = torch.from_numpy(np.ascontiguousarray(subgrid, dtype=np.float64)).cuda()
+            j0 = i0 = 0
+        iy0 = torch.tensor([j0], dtype=torch.int32, device="cuda")
+        ix0 = torch.tensor([i0], dtype=torch.int32, device="cuda")
+        return g, iy0, ix0
+
+    def _origins_device(self, window, xc_list, yc_list):
+        torch = _lib.require_cuda()
+        iy0, ix0, n = _plans.window_origins(self, window, xc_list, yc_list)
+        return (torch.from_numpy(iy0).cuda(), torch.from_numpy(ix0).cuda(), n)
+
+    # ------------------------------------------------------------------ reference API
+    def subgrid(self, window, xc, yc):
+        """Window of the data around (xc, yc); a view, like the reference (grid.py:112-157)."""
+        iy0, ix0, n = _plans.window_origins(self, window, xc, yc)
+        j0, i0 = int(iy0[0]), int(ix0[0])
+        return self.data[j0:j0 + n, i0:i0 + n]
+
+    def create_centroid_list(self, window, spacingX=None, spacingY=None):
+        """Centroids whose windows fit in the grid (grid.py:159-197); x varies fastest."""
+        _, half = _plans.window_nodes(window, self.dx)
+        xs = self.xcoords[half:-half]
+        ys = self.ycoords[half:-half]
+        if spacingX is not None:
+            xs = np.arange(xs.min(), xs.max(), spacingX)
+        if spacingY is not None:
+            ys = np.arange(ys.min(), ys.max(), spacingY)
+        xq, yq = np.meshgrid(xs, ys)
+        return xq.ravel(), yq.ravel()
+
+    def remove_trend_linear(self, data):
+        """Remove the best-fitting plane (grid.py:199-216), computed on the device in closed form."""
+        data = np.asarray(data)
+        if data.ndim != 2 or data.shape[0] != data.shape[1]:
+            raise ValueError("remove_trend_linear on the device needs a square 2D array, got {}".format(data.shape))
+        torch = _lib.require_cuda()
+        g, iy0, ix0 = self._as_device_windows(data)
+        n = data.shape[0]
+        out = torch.empty((1, n, n), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().cb_detrend_batch(g.data_ptr(), g.shape[0], g.shape[1], g.stride(0), n,
+                                                iy0.data_ptr(), ix0.data_ptr(), 1, out.data_ptr(),
+                                                _lib.stream_ptr(torch)))
+        return out[0].cpu().numpy()
+
+    def _taper_spectrum(self, subgrid, taper=np.hanning, scale=0.001, **kwargs):
+        """(vtaper, dk, kbins) as grid.py:218-246 (host-side; kept for callers that poke at it)."""
+        nr, nc = subgrid.shape
+        if nr != nc:
+            warnings.warn("subgrid is not square {}".format((nr, nc)), RuntimeWarning)
+        if taper is None:
+            vtaper = 1.0
+        else:
+            vtaper = np.outer(taper(nr, **kwargs), taper(nc, **kwargs))
+        dk = 2.0 * np.pi / (nr - 1) / (self.dx * scale)
+        return vtaper, dk, np.arange(dk, dk * nr / 2, dk)
+
+    def radial_spectrum(self, subgrid, taper=np.hanning, power=2.0, **kwargs):
+        """Radial power spectrum (k [rad/km], Phi, sigma_Phi) of one square window (grid.py:290-339)."""
+        subgrid = np.asarray(subgrid)
+        nr, nc = subgrid.shape
+        if nr != nc:
+            warnings.warn("subgrid is not square {}".format((nr, nc)), RuntimeWarning)
+            # the reference's (nr,nr) mask cannot index an (nr,nc) array either (grid.py:279-283)
+            raise IndexError("boolean index did not match: radial_spectrum needs a square subgrid")
+        plan = _plans.spectrum_plan(nr, self.dx, _plans.taper_vector(taper, nr, **kwargs))
+        g, iy0, ix0 = self._as_device_windows(subgrid)
+        phi, sig = plan.run(g, iy0, ix0, False, power)
+        return plan.k.copy(), phi[0].cpu().numpy(), sig[0].cpu().numpy()
+
+    def azimuthal_spectrum(self, subgrid, taper=np.hanning, power=2.0, theta=5.0, **kwargs):
+        """Azimuthal spectrum (kbins, S[ntheta, nk], dtheta) of one square window (grid.py:341-403)."""
+        subgrid = np.asarray(subgrid)
+        if subgrid.shape[0] != subgrid.shape[1]:
+            raise RuntimeError('data should be a square array')
+        g, iy0, ix0 = self._as_device_windows(subgrid)
+        kbins, S, dtheta = self._azimuthal_device(g, iy0, ix0, subgrid.shape[0], taper, power, theta, **kwargs)
+        return kbins, S[0].cpu().numpy(), dtheta
+
+    def _azimuthal_device(self, g, iy0, ix0, nw, taper, power, theta, **kwargs):
+        torch = _lib.require_cuda()
+        kbins, _, _, _ = _plans.radial_bins(nw, self.dx)
+        dtheta = np.arange(0.0, 180.0, theta)
+        rplan = _plans.radon_plan(nw, np.pi * dtheta / 180.0)
+        sino = rplan.apply(g, iy0, ix0)
+        n = int(iy0.numel())
+        S = torch.empty((n, dtheta.size, kbins.size), dtype=torch.float64, device="cuda")
+        tv = _plans.taper_vector(taper, nw, **kwargs)
+        _lib.check(_lib.load().cb_azimuthal_tail_batch(sino.data_ptr(), nw, dtheta.size, n,
+                                                       None if tv is None else tv.ctypes.data, kbins.size,
+                                                       float(power), S.data_ptr(), _lib.stream_ptr(torch)))
+        torch.cuda.current_stream().synchronize()     # tv is host memory read by an async copy
+        return kbins, S, dtheta
+
+    def reduce_to_pole(self, *args, **kwargs):
+        raise NotImplementedError("reduce_to_pole is outside the accelerated per-window path (SURVEY.md 8f); "
+                                  "apply it with the reference and pass the result as the grid")
+
+    def upward_continuation(self, *args, **kwargs):
+        raise NotImplementedError("upward_continuation is outside the accelerated per-window path (SURVEY.md 8f)")
+
+    # ------------------------------------------------------------------ batched extensions
+    def radial_spectrum_batch(self, window, xc_list, yc_list, *, taper=np.hanning, power=2.0, detrend=False,
+                              as_numpy=True, **kwargs):
+        """radial_spectrum for many centroids in one launch: returns (k, Phi[n, nbins], sigma[n, nbins]).
+        `detrend=True` is `process_subgrid=self.remove_trend_linear` fused into the gather."""
+        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+        plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
+        phi, sig = plan.run(self.device_grid(), iy0, ix0, detrend, power)
+        if as_numpy:
+            return plan.k.copy(), phi.cpu().numpy(), sig.cpu().numpy()
+        return plan.k.copy(), phi, sig
+
+    def azimuthal_spectrum_batch(self, window, xc_list, yc_list, *, taper=np.hanning, power=2.0, theta=5.0,
+                                 **kwargs):
+        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+        kbins, S, dtheta = self._azimuthal_device(self.device_grid(), iy0, ix0, n, taper, power, theta, **kwargs)
+        return kbins, S.cpu().numpy(), dtheta
+
+    def remove_trend_linear_batch(self, window, xc_list, yc_list):
+        torch = _lib.require_cuda()
+        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+        g = self.device_grid()
+        out = torch.empty((iy0.numel(), n, n), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().cb_detrend_batch(g.data_ptr(), g.shape[0], g.shape[1], g.stride(0), n,
+                                                iy0.data_ptr(), ix0.data_ptr(), iy0.numel(), out.data_ptr(),
+                                                _lib.stream_ptr(torch)))
+        return out.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------
+# free functions  (pycurious/grid.py:552-735)
+# ----------------------------------------------------------------------------------------------
+def bouligand2009(kh, beta, zt, dz, C):
+    """Synthetic radial power spectrum, eq. (4) of Bouligand et al. 2009 (grid.py:552-600), evaluated on
+    the device with the K_nu of csrc/besselk.cuh.  Arguments broadcast like numpy."""
+    torch = _lib.require_cuda()
+    args = np.broadcast_arrays(*[np.asarray(a, dtype=np.float64) for a in (kh, beta, zt, dz, C)])
+    shape = args[0].shape
+    n = args[0].size
+    if n == 0:
+        return np.empty(shape)
+    k_t = torch.from_numpy(np.ascontiguousarray(args[0]).reshape(-1)).cuda()
+    p_t = torch.from_numpy(np.ascontiguousarray(np.stack([a.reshape(-1) for a in args[1:]], axis=1))).cuda()
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().cb_bouligand_points(k_t.data_ptr(), p_t.data_ptr(), n, out.data_ptr(),
+                                               _lib.stream_ptr(torch)))
+    res = out.cpu().numpy().reshape(shape)
+    return res if res.ndim else res[()]
+
+
+def maus1995(beta, zt, kh, C=0.0):
+    """Maus & Dimri 1995 half-space spectrum (grid.py:702-735): the K-free part of bouligand2009."""
+    return C - 2.0 * kh * zt - (beta - 1.0) * np.log(kh)
+
+
+def _two_band_line(X, Y, E):
+    """Weighted straight line through (X, Y); the weights are 1/E**2 with E already a variance,
+    i.e. the reference's sigma^4 weighting (grid.py:630-653)."""
+    w = 1.0 / (E * E)
+    Sx, Sy, S1 = np.sum(X * w), np.sum(Y * w), np.sum(w)
+    Sxx, Sxy = np.sum(X * X * w), np.sum(X * Y * w)
+    slope = (Sx * Sy - Sxy * S1) / (Sx * Sx - Sxx * S1)
+    icept = (Sxy - slope * Sxx) / Sx
+    err = np.sqrt(S1 / (Sxx * S1 - Sx * Sx))
+    return slope, icept, err
+
+
+def tanaka1999(k, lnPhi, sigma_lnPhi, kmin_range=(0.05, 0.2), kmax_range=(0.05, 0.2)):
+    """Top / centroid depth line fits of Tanaka et al. 1999 (grid.py:603-674).  O(nbins) host
+    post-processing of radial_spectrum(power=0.5) output."""
+    var = sigma_lnPhi ** 2
+    sf = k / (2.0 * np.pi)
+    top = np.logical_and(sf >= kmin_range[0], sf <= kmin_range[1])
+    cen = np.logical_and(sf >= kmax_range[0], sf <= kmax_range[1])
+    Xc = sf[cen]
+    upper = _two_band_line(sf[top], lnPhi[top], var[top])
+    lower = _two_band_line(Xc, np.log(np.exp(lnPhi[cen]) / (Xc * 2 * np.pi)),
+                           np.log(np.exp(var[cen]) / (Xc * 2 * np.pi)))
+    return upper, lower
+
+
+def ComputeTanaka(Ztr, dZtr, Zor, dZor):
+    """Curie depth Zb = 2 Zo - Zt and its error (grid.py:677-699)."""
+    return abs(2.0 * Zor - Ztr), 2.0 * dZor + dZtr

@@ -1,0 +1,300 @@
+"""Drop-in `CurieOptimise`: MAP fits and Metropolis-Hastings sampling of the Bouligand et al.
+(2009) parameters (beta, zt, dz, C) for windows of a magnetic grid, batched on a B200.
+
+Mirrors the reference's pycurious/optimise.py (v1.1.1): same class, constructor, attributes
+(`bounds`, `prior`, `prior_pdf`, `max_processors`), method signatures, return containers and
+errors.  Where the reference forks `max_processors` workers
+and calls scipy per centroid (optimise.py:386-424), this class launches one kernel for the
+whole centroid list; `max_processors` is kept as an attribute and validated, but no process is
+ever forked (CUDA contexts do not survive fork).
+
+Differences that are deliberate and documented in DESIGN.md:
+  * the optimiser is a bounded quasi-Newton method on the device (csrc/fit_body.cuh), not
+    scipy's L-BFGS-B; it converges to the same bounded minimum more tightly
+  * Metropolis-Hastings draws from a counter-based Philox stream; `seed=None` takes the seed
+    from numpy's global RNG, so `np.random.seed(...)` still makes runs reproducible
+"""
+from __future__ import annotations
+
+import ctypes as C
+import inspect
+import warnings
+from multiprocessing import cpu_count
+
+import numpy as np
+
+from . import _lib, _plans
+from .grid import CurieGrid
+
+_KEYS = ("beta", "zt", "dz", "C")
+
+
+class CurieOptimise(CurieGrid):
+    """Extends CurieGrid with the inversion routines (reference: optimise.py:50-118).
+
+    Attributes:
+        bounds : list of (lower, upper) for beta, zt, dz, C; None = unbounded
+        prior, prior_pdf : dicts keyed by 'beta', 'zt', 'dz', 'C'
+        max_processors : kept for compatibility (validated, never used to fork)
+    """
+
+    def __init__(self, grid, xmin, xmax, ymin, ymax, **kwargs):
+        super(CurieOptimise, self).__init__(grid, xmin, xmax, ymin, ymax)
+        self.reset_priors()
+        self.bounds = [(0.0, None), (0.0, None), (0.0, None), (None, None)]
+        self.max_processors = kwargs.pop("max_processors", cpu_count())
+
+    # ------------------------------------------------------------------ priors (optimise.py:120-194)
+    def add_prior(self, **kwargs):
+        """add_prior(beta=(p, sigma_p)) or add_prior(beta=scipy.stats.norm(p, sigma_p))."""
+        for key, prior in kwargs.items():
+            if key not in self.prior:
+                raise ValueError("prior must be one of {}".format(self.prior.keys()))
+            if type(prior) == tuple:
+                from scipy import stats
+                pdf = stats.norm(*prior)
+            elif type(prior).__name__ == "rv_frozen" or hasattr(prior, "rvs") and hasattr(prior, "args"):
+                pdf = prior
+            else:
+                raise ValueError("Use a distribution from scipy.stats module")
+            self.prior_pdf[key] = pdf
+            self.prior[key] = list(pdf.args)
+
+    def reset_priors(self):
+        self.prior = {"beta": None, "zt": None, "dz": None, "C": None}
+        self.prior_pdf = {"beta": None, "zt": None, "dz": None, "C": None}
+
+    def objective_function(self, x, x0, sigma_x0, *args):
+        """0.5 * sum((x - x0)^2 / sigma^2)  (optimise.py:181-194); O(1) host helper."""
+        return 0.5 * np.sum((x - x0) ** 2 / sigma_x0 ** 2)
+
+    def objective_routine(self, **kwargs):
+        """Sum of the prior penalties of the given parameters (optimise.py:159-179)."""
+        c = 0.0
+        for key, val in kwargs.items():
+            if key in self.prior and self.prior[key] is not None:
+                c += self.objective_function(val, *self.prior[key])
+        return c
+
+    def _prior_arrays(self):
+        mu = np.full(4, np.nan)
+        sg = np.full(4, np.nan)
+        for j, key in enumerate(_KEYS):
+            p = self.prior[key]
+            if p is not None:
+                if len(p) < 2:
+                    raise TypeError("prior for {} needs (mean, sigma) positional arguments".format(key))
+                mu[j], sg[j] = float(p[0]), float(p[1])     # first two positional args (optimise.py:178)
+        return mu, sg
+
+    def _bound_arrays(self):
+        lb = np.array([-np.inf if b[0] is None else float(b[0]) for b in self.bounds])
+        ub = np.array([np.inf if b[1] is None else float(b[1]) for b in self.bounds])
+        if lb.size != 4:
+            raise ValueError("bounds must hold four (lower, upper) pairs")
+        return lb, ub
+
+    # ------------------------------------------------------------------ objective (optimise.py:196-230)
+    def min_func(self, x, kh, Phi, sigma_Phi):
+        """Misfit 0.5*sum((bouligand2009(kh,*x) - Phi)^2) + priors; non-finite -> 1e99.
+        `sigma_Phi` is accepted and ignored, as in the reference (optimise.py:225)."""
+        torch = _lib.require_cuda()
+        mu, sg = self._prior_arrays()
+        k_t = torch.from_numpy(np.ascontiguousarray(kh, dtype=np.float64)).cuda()
+        p_t = torch.from_numpy(np.ascontiguousarray(Phi, dtype=np.float64)).cuda()
+        x_t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).reshape(1, 4)).cuda()
+        out = torch.empty(1, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().cb_misfit(k_t.data_ptr(), k_t.numel(), p_t.data_ptr(), 0, x_t.data_ptr(), 1,
+                                         mu.ctypes.data, sg.ctypes.data, out.data_ptr(), _lib.stream_ptr(torch)))
+        return float(out.item())
+
+    # ------------------------------------------------------------------ spectra for a centroid batch
+    def _is_detrend(self, process_subgrid):
+        return (inspect.ismethod(process_subgrid) and process_subgrid.__self__ is self
+                and process_subgrid.__func__ is CurieGrid.remove_trend_linear)
+
+    def _batch_spectra(self, window, xc_list, yc_list, taper, process_subgrid, kwargs):
+        """(k, Phi_dev[n, nbins], sigma_dev) on the device for every centroid.  process_subgrid None and
+        self.remove_trend_linear run fused in the gather kernel; any other callable is applied on the
+        host window by window (its result is then uploaded as a stack of windows)."""
+        torch = _lib.require_cuda()
+        kwargs = dict(kwargs)
+        power = kwargs.pop("power", 2.0)
+        if process_subgrid is None or self._is_detrend(process_subgrid):
+            iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+            plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
+            phi, sig = plan.run(self.device_grid(), iy0, ix0, process_subgrid is not None, power)
+            return plan.k, phi, sig
+        wins = [np.asarray(process_subgrid(self.subgrid(window, xc, yc)), dtype=np.float64)
+                for xc, yc in zip(xc_list, yc_list)]
+        n = wins[0].shape[0]
+        for w in wins:
+            if w.shape != (n, n):
+                raise ValueError("process_subgrid must return square windows of one size, got {}".format(w.shape))
+        stack = torch.from_numpy(np.ascontiguousarray(np.concatenate(wins, axis=0))).cuda()
+        iy0 = torch.arange(len(wins), dtype=torch.int32, device="cuda") * n
+        ix0 = torch.zeros(len(wins), dtype=torch.int32, device="cuda")
+        plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
+        phi, sig = plan.run(stack, iy0, ix0, False, power)
+        return plan.k, phi, sig
+
+    # ------------------------------------------------------------------ MAP fit
+    def _fit_device(self, k, phi_t, x0, x0_dev=None, max_iter=0, gtol=0.0, ftol=0.0, diagnostics=False):
+        torch = _lib.require_cuda()
+        n = phi_t.shape[0]
+        opt = _lib.FitOptions()
+        lb, ub = self._bound_arrays()
+        mu, sg = self._prior_arrays()
+        for j in range(4):
+            opt.x0[j], opt.lb[j], opt.ub[j] = float(x0[j]), lb[j], ub[j]
+            opt.prior_mu[j], opt.prior_sigma[j] = mu[j], sg[j]
+        opt.max_iter, opt.gtol, opt.ftol = int(max_iter), float(gtol), float(ftol)
+        k_t = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float64)).cuda()
+        x_t = torch.empty((n, 4), dtype=torch.float64, device="cuda")
+        f_t = torch.empty(n, dtype=torch.float64, device="cuda") if diagnostics else None
+        it_t = torch.empty(n, dtype=torch.int32, device="cuda") if diagnostics else None
+        st_t = torch.empty(n, dtype=torch.int32, device="cuda") if diagnostics else None
+        nf_t = torch.empty(n, dtype=torch.int32, device="cuda") if diagnostics else None
+        _lib.check(_lib.load().cb_fit_batch(k_t.data_ptr(), k_t.numel(), phi_t.data_ptr(), n, C.byref(opt),
+                                            _lib.ptr(x0_dev), x_t.data_ptr(), _lib.ptr(f_t), _lib.ptr(it_t),
+                                            _lib.ptr(st_t), _lib.ptr(nf_t), _lib.stream_ptr(torch)))
+        if diagnostics:
+            return x_t, dict(f=f_t, niter=it_t, status=st_t, nfev=nf_t)
+        return x_t
+
+    def optimise(self, window, xc, yc, beta=3.0, zt=1.0, dz=10.0, C=5.0, taper=np.hanning,
+                 process_subgrid=None, **kwargs):
+        """Optimal (beta, zt, dz, C) for one centroid; ndarray (4,) like `res.x` (optimise.py:232-301)."""
+        k, phi, _ = self._batch_spectra(window, [xc], [yc], taper, process_subgrid, kwargs)
+        return self._fit_device(k, phi, (beta, zt, dz, C))[0].cpu().numpy()
+
+    def optimise_routine(self, window, xc_list, yc_list, beta=3.0, zt=1.0, dz=10.0, C=5.0, taper=np.hanning,
+                         process_subgrid=None, **kwargs):
+        """Fit every centroid of the list; returns [beta(n,), zt(n,), dz(n,), C(n,)] (optimise.py:446-509)."""
+        return self.parallelise_routine(window, xc_list, yc_list, self.optimise, beta, zt, dz, C, taper,
+                                        process_subgrid, **kwargs)
+
+    def optimise_batch(self, window, xc_list, yc_list, *, beta=3.0, zt=1.0, dz=10.0, C=5.0, taper=np.hanning,
+                       process_subgrid=None, diagnostics=False, as_numpy=True, **kwargs):
+        """Batched fit returning an (n, 4) array (and optionally solver diagnostics)."""
+        self._check_lists(xc_list, yc_list)
+        k, phi, _ = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
+        res = self._fit_device(k, phi, (beta, zt, dz, C), diagnostics=diagnostics)
+        if diagnostics:
+            x, diag = res
+            if as_numpy:
+                return x.cpu().numpy(), {kk: v.cpu().numpy() for kk, v in diag.items()}
+            return x, diag
+        return res.cpu().numpy() if as_numpy else res
+
+    # ------------------------------------------------------------------ fan-out (optimise.py:317-444)
+    @staticmethod
+    def _check_lists(xc_list, yc_list):
+        if len(xc_list) != len(yc_list):
+            raise ValueError("xc_list and yc_list must be the same size")
+
+    def parallelise_routine(self, window, xc_list, yc_list, func, *args, **kwargs):
+        """Evaluate `func(window, xc, yc, *args, **kwargs)` for every centroid.
+
+        `self.optimise` and `self.metropolis_hastings` are recognised and run as ONE batched device
+        launch over the whole list; any other callable runs as a plain serial loop (the reference's
+        `max_processors == 1` branch) -- nothing is ever forked.  Output containers follow the
+        reference: 1-D results -> list of 4 arrays (n,); 2-D results -> list[4] of list[n] arrays."""
+        n = len(xc_list)
+        self._check_lists(xc_list, yc_list)
+        nprocs = self.max_processors
+        if nprocs < 1:
+            raise ValueError("{} processors is invalid, specify a positive integer value".format(nprocs))
+
+        if self._is_own(func, "optimise"):
+            b = inspect.signature(CurieOptimise.optimise).bind(self, window, 0.0, 0.0, *args, **kwargs)
+            b.apply_defaults()
+            a = b.arguments
+            k, phi, _ = self._batch_spectra(window, xc_list, yc_list, a["taper"], a["process_subgrid"], a["kwargs"])
+            x = self._fit_device(k, phi, (a["beta"], a["zt"], a["dz"], a["C"])).cpu().numpy()
+            return list(np.ascontiguousarray(x.T))
+
+        if self._is_own(func, "metropolis_hastings"):
+            b = inspect.signature(CurieOptimise.metropolis_hastings).bind(self, window, 0.0, 0.0, *args, **kwargs)
+            b.apply_defaults()
+            a = b.arguments
+            chains = self.metropolis_hastings_batch(
+                window, xc_list, yc_list, a["nsim"], a["burnin"], x_scale=a["x_scale"], beta=a["beta"], zt=a["zt"],
+                dz=a["dz"], C=a["C"], taper=a["taper"], process_subgrid=a["process_subgrid"], seed=a["seed"],
+                reduce="chains", **a["kwargs"])
+            return [[chains[i, j] for i in range(n)] for j in range(4)]
+
+        res = None
+        xOpt = [[] for _ in range(n)]
+        for i in range(n):
+            res = func(window, xc_list[i], yc_list[i], *args, **kwargs)
+            xOpt[i] = res
+        ndim = np.array(res).ndim
+        if ndim == 1:
+            return list(np.vstack(xOpt).T)
+        elif ndim > 1:
+            out = list(np.hstack(xOpt))
+            return [np.split(o, n) for o in out]
+        raise ValueError("Cannot determine shape of output")
+
+    def _is_own(self, func, name):
+        return (inspect.ismethod(func) and func.__self__ is self
+                and func.__func__ is getattr(CurieOptimise, name))
+
+    # ------------------------------------------------------------------ Metropolis-Hastings
+    def _mh_device(self, k, phi_t, nsim, burnin, x_scale, x0, x0_dev, seed, reduce_mode, chain_offset=0):
+        torch = _lib.require_cuda()
+        n = phi_t.shape[0]
+        opt = _lib.MhOptions()
+        mu, sg = self._prior_arrays()
+        xs = np.ones(4) if x_scale is None else np.asarray(x_scale, dtype=np.float64)
+        for j in range(4):
+            opt.x0[j], opt.x_scale[j] = float(x0[j]), float(xs[j])
+            opt.prior_mu[j], opt.prior_sigma[j] = mu[j], sg[j]
+        opt.nsim, opt.burnin = int(nsim), int(burnin)
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
+        opt.seed, opt.chain_offset, opt.reduce_mode = int(seed) & (2 ** 64 - 1), int(chain_offset), reduce_mode
+        k_t = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float64)).cuda()
+        shape = (n, 4, int(nsim)) if reduce_mode == 0 else (n, 10)
+        out = torch.empty(shape, dtype=torch.float64, device="cuda")
+        acc = torch.empty(n, dtype=torch.int64, device="cuda")
+        _lib.check(_lib.load().cb_mh_batch(k_t.data_ptr(), k_t.numel(), phi_t.data_ptr(), n, C.byref(opt),
+                                           _lib.ptr(x0_dev), out.data_ptr(), acc.data_ptr(),
+                                           _lib.stream_ptr(torch)))
+        return out, acc
+
+    def metropolis_hastings(self, window, xc, yc, nsim, burnin, x_scale=None, beta=3.0, zt=1.0, dz=10.0, C=5.0,
+                            taper=np.hanning, process_subgrid=None, seed=None, **kwargs):
+        """MCMC ensemble for one centroid: [beta(nsim,), zt(nsim,), dz(nsim,), C(nsim,)] (optimise.py:511-633).
+        Burn-in is the reference's tempered greedy climb; bounds are not applied, as in the reference."""
+        k, phi, _ = self._batch_spectra(window, [xc], [yc], taper, process_subgrid, kwargs)
+        out, _ = self._mh_device(k, phi, nsim, burnin, x_scale, (beta, zt, dz, C), None, seed, 0)
+        return list(out[0].cpu().numpy())
+
+    def metropolis_hastings_batch(self, window, xc_list, yc_list, nsim, burnin, *, x_scale=None, beta=3.0, zt=1.0,
+                                  dz=10.0, C=5.0, x0=None, taper=np.hanning, process_subgrid=None, seed=None,
+                                  reduce="moments", chain_offset=0, as_numpy=True, **kwargs):
+        """One chain per centroid in a single launch.
+        reduce='chains'  -> array (n, 4, nsim)
+        reduce='moments' -> array (n, 10): mean then std of (beta, zt, dz, C, zt+dz), streamed on the device
+        `x0` (n, 4) gives per-window starting points (e.g. the MAP estimates)."""
+        torch = _lib.require_cuda()
+        self._check_lists(xc_list, yc_list)
+        if reduce not in ("moments", "chains"):
+            raise ValueError("reduce must be 'moments' or 'chains'")
+        k, phi, _ = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
+        x0_dev = None
+        if x0 is not None:
+            x0_dev = x0 if hasattr(x0, "data_ptr") else torch.from_numpy(
+                np.ascontiguousarray(x0, dtype=np.float64)).cuda()
+            if tuple(x0_dev.shape) != (phi.shape[0], 4):
+                raise ValueError("x0 must have shape (n, 4)")
+        out, acc = self._mh_device(k, phi, nsim, burnin, x_scale, (beta, zt, dz, C), x0_dev, seed,
+                                   0 if reduce == "chains" else 1, chain_offset)
+        self.last_accepted = acc
+        return out.cpu().numpy() if as_numpy else out
+
+    def sensitivity(self, *args, **kwargs):
+        raise NotImplementedError("sensitivity() is the next item after the hot path (SURVEY.md 8f item 1); "
+                                  "it will reuse the batched fit kernel")

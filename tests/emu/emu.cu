@@ -11,6 +11,7 @@
 #include "spectrum_plan.h"
 #include "fit_body.cuh"
 #include "mh_body.cuh"
+#include "radon_body.cuh"
 
 void cb_set_error(const char *fmt, ...) { (void)fmt; }
 int cb_check_device() { return CB_ERR_NO_DEVICE; }
@@ -192,6 +193,37 @@ int emu_mh(const double *kh, int nk, const double *phi, int64_t nwin, const cb_m
         P.warps_per_block = 2;
         emu_launch((int)((nwin + 1) / 2), 64, 2 * 3 * nk * sizeof(double), [&](const HostCtx &cx) { mh_body(cx, P); });
     }
+    return 0;
+}
+
+// ---- radon -------------------------------------------------------------------------------------
+// count pass (data == NULL) or fill pass; offset has nray+1 entries in the fill pass
+int emu_radon_trace(const double *tx, const double *rx, int64_t nray, int nw, int64_t *count,
+                    const int64_t *offset, double *data, int64_t *indices) {
+    RadonTraceParams P;
+    memset(&P, 0, sizeof(P));
+    P.tx = tx; P.rx = rx; P.nray = nray; P.nw = nw; P.count = count; P.offset = offset; P.data = data; P.indices = indices;
+    emu_launch((int)((nray + 63) / 64), 64, 0, [&](const HostCtx &cx) { radon_trace_body(cx, P); });
+    return 0;
+}
+
+int emu_radon_apply(const double *grid, int64_t ld, const int32_t *iy0, const int32_t *ix0, int64_t nwin, int nw,
+                    int ntheta, const int64_t *offset, const double *data, const int64_t *indices, double *sino,
+                    int window_fastest) {
+    RadonApplyParams P;
+    memset(&P, 0, sizeof(P));
+    P.grid = grid; P.ld = ld; P.iy0 = iy0; P.ix0 = ix0; P.nwin = nwin; P.nw = nw; P.ntheta = ntheta;
+    P.offset = offset; P.data = data; P.indices = indices; P.sino = sino; P.window_fastest = window_fastest;
+    const int64_t total = (int64_t)nw * ntheta * nwin;
+    emu_launch((int)((total + 63) / 64), 64, 0, [&](const HostCtx &cx) { radon_apply_body(cx, P); });
+    return 0;
+}
+
+int emu_az_tail(const double *sino, int nw, int ntheta, int64_t nwin, const double *taper, int nkb, double power,
+                double *S) {
+    AzTailParams P{sino, nw, ntheta, nkb, nwin, taper, power, S};
+    const int nk = 1 + 2 * nkb;
+    emu_launch((int)(nwin * ntheta), 32, (size_t)nk * 16 + (size_t)nw * 8, [&](const HostCtx &cx) { az_tail_body(cx, P); });
     return 0;
 }
 

@@ -1,0 +1,354 @@
+"""Parity of the CUDA path (called through the C-ABI via pycurious_b200) against the reference's
+golden vectors and the CPU oracle.  Needs a B200: run with `pytest -m gpu`."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, TAPERS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pc():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import pycurious_b200
+    from pycurious_b200 import _lib
+    _lib.load()
+    return pycurious_b200
+
+
+@pytest.fixture(scope="module")
+def grid(pc, mag):
+    d, ext = mag
+    return pc.CurieOptimise(d, *ext)
+
+
+# --------------------------------------------------------------------------- spectrum stage
+def test_spectrum_golden_cases(pc, grid, mag):
+    """Every golden radial_spectrum case of the reference: k bit-exact, Phi/sigma rtol 1e-10."""
+    d, _ = mag
+    g = load_golden("spectrum.npz")
+    for entry in g["names"]:
+        name, tp = str(entry).split(":")
+        j0, i0, n, det = (int(v) for v in g[name + "_meta"])
+        win = grid.data[j0:j0 + n, i0:i0 + n]
+        kw = {"beta": float(g[name + "_kaiser_beta"])} if tp == "kaiser" else {}
+        if det:
+            win = grid.remove_trend_linear(win)
+        k, phi, sig = grid.radial_spectrum(win, taper=TAPERS[tp], power=float(g[name + "_power"]), **kw)
+        assert np.array_equal(k, g[name + "_k"]), name
+        np.testing.assert_allclose(phi, g[name + "_phi"], rtol=1e-10, err_msg=name)
+        np.testing.assert_allclose(sig, g[name + "_sig"], rtol=1e-9, err_msg=name)
+
+
+def test_fused_detrend_matches_reference(grid):
+    g = load_golden("spectrum.npz")
+    name = "c200_hann_detrend"
+    k, phi, sig = grid.radial_spectrum_batch(200e3, [140.5e3], [160.5e3], detrend=True)
+    np.testing.assert_allclose(phi[0], g[name + "_phi"], rtol=1e-10)
+    np.testing.assert_allclose(sig[0], g[name + "_sig"], rtol=1e-9)
+    m = load_golden("misc.npz")
+    j0, i0, n = (int(v) for v in m["detrend_in_origin"])
+    out = grid.remove_trend_linear(grid.data[j0:j0 + n, i0:i0 + n])
+    np.testing.assert_allclose(out, m["detrend_out"], rtol=0, atol=1e-12 * np.abs(m["detrend_out"]).max())
+
+
+@pytest.mark.parametrize("nw", [101, 128, 129, 201, 301])
+def test_device_bin_map_bit_exact(pc, oracle, nw):
+    """The CSR the kernel reduces over is the reference's membership, folded onto the half plane:
+    integers compared exactly (gate G1a)."""
+    from pycurious_b200 import _plans
+    plan = _plans.spectrum_plan(nw, 1000.0, None)
+    ptr, idx = plan.folded_bins()
+    _, dk, edges = oracle.taper_and_bins(nw, nw, 1000.0, None)
+    _, masks = oracle.radial_bin_masks(nw, dk, edges)
+    g = load_golden("spectrum.npz")
+    half = nw // 2
+    for b, m in enumerate(masks):
+        a, c = np.nonzero(m)
+        u = (a + (nw + 1) // 2) % nw
+        v = (c + (nw + 1) // 2) % nw
+        fold = v > half
+        u = np.where(fold, (nw - u) % nw, u)
+        v = np.where(fold, nw - v, v)
+        want = np.sort(v * nw + u)
+        got = idx[ptr[b]:ptr[b + 1]]
+        uniq, cnt = np.unique(want, return_counts=True)
+        if cnt.size and np.all(cnt == cnt[0]) and cnt[0] > 1:
+            want = uniq
+            assert got.size * cnt[0] == g["bins%d_counts" % nw][b]
+        else:
+            assert got.size == g["bins%d_counts" % nw][b]
+        assert np.array_equal(got, want), (nw, b)
+
+
+def test_spectrum_batch_equals_single_and_oracle(grid, oracle, mag):
+    d, ext = mag
+    spec = oracle.GridSpec(d, *ext)
+    xc, yc = grid.create_centroid_list(128e3, 23e3, 31e3)
+    k, phi, sig = grid.radial_spectrum_batch(128e3, xc, yc, power=0.5)
+    assert phi.shape == (xc.size, k.size)
+    for i in range(0, xc.size, 7):
+        k0, p0, s0 = oracle.radial_spectrum(oracle.cut_window(spec, 128e3, xc[i], yc[i]), spec.dx, power=0.5)
+        assert np.array_equal(k, k0)
+        np.testing.assert_allclose(phi[i], p0, rtol=1e-10)
+        np.testing.assert_allclose(sig[i], s0, rtol=1e-9)
+
+
+def test_spectrum_properties_full_size(pc):
+    """Size-independent properties on a BASELINE-sized window set (4096-wide grid, 201-node windows):
+    scaling the data by a shifts Phi by power*ln(a) and leaves sigma; identical windows give identical
+    rows; a pure plane is removed by the fused detrend."""
+    ny = nx = 1024
+    data = pc.synth.fractal_grid(ny, nx, seed=5)
+    ext = pc.synth.grid_extent(ny, nx)
+    G = pc.CurieGrid(data, *ext)
+    xc, yc = G.create_centroid_list(200e3, 50e3, 50e3)
+    k, phi, sig = G.radial_spectrum_batch(200e3, xc, yc)
+    G2 = pc.CurieGrid(data * 7.5, *ext)
+    _, phi2, sig2 = G2.radial_spectrum_batch(200e3, xc, yc)
+    np.testing.assert_allclose(phi2, phi + 2.0 * np.log(7.5), rtol=1e-11, atol=1e-10)
+    np.testing.assert_allclose(sig2, sig, rtol=1e-9)
+    # periodic tiling: windows one period apart see identical data
+    tile = np.tile(data[:256, :256], (4, 4))
+    G3 = pc.CurieGrid(tile, *ext)
+    _, p3, _ = G3.radial_spectrum_batch(200e3, [150e3, 150e3 + 256e3, 150e3], [150e3, 150e3, 150e3 + 512e3])
+    assert np.array_equal(p3[0], p3[1]) and np.array_equal(p3[0], p3[2])
+    # plane + data with detrend == data's own detrended spectrum
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    G4 = pc.CurieGrid(data + 3.0 * xx - 2.0 * yy + 500.0, *ext)
+    _, p4, s4 = G4.radial_spectrum_batch(200e3, xc[:8], yc[:8], detrend=True)
+    _, p5, s5 = G.radial_spectrum_batch(200e3, xc[:8], yc[:8], detrend=True)
+    np.testing.assert_allclose(p4, p5, rtol=1e-8, atol=1e-8)
+
+
+# --------------------------------------------------------------------------- forward model
+def test_besselk_and_forward_model(pc):
+    import torch
+    from pycurious_b200 import _lib
+    g = load_golden("forward.npz")
+    nu, x = np.meshgrid(g["nu"], g["x"], indexing="ij")
+    nu_t = torch.from_numpy(np.ascontiguousarray(nu.ravel())).cuda()
+    x_t = torch.from_numpy(np.ascontiguousarray(x.ravel())).cuda()
+    out = torch.empty_like(nu_t)
+    _lib.check(_lib.load().cb_besselk(nu_t.data_ptr(), x_t.data_ptr(), nu_t.numel(), out.data_ptr(), None))
+    got, want = out.cpu().numpy(), g["kv"].ravel()
+    ok = want > 0          # scipy flushes kv(2, 700) to 0 earlier than the true value
+    np.testing.assert_allclose(got[ok], want[ok], rtol=2e-13)
+    with np.errstate(all="ignore"):
+        for p, ref in zip(g["params"], g["bouligand"]):
+            ours = pc.bouligand2009(g["kh"], *p)
+            fin = np.isfinite(ref)
+            if p[2] > 1e-6:          # dz = 1e-8 is pure cancellation noise in the reference itself
+                assert np.array_equal(np.isfinite(ours), fin), p
+            np.testing.assert_allclose(ours[fin & np.isfinite(ours)], ref[fin & np.isfinite(ours)], rtol=1e-12, atol=1e-12)
+        dense = np.array([pc.bouligand2009(g["k49"], *p) for p in g["pdense"][:50]])
+    ref = g["fdense"][:50]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(dense), fin)
+    np.testing.assert_allclose(dense[fin], ref[fin], rtol=0, atol=1e-11)
+    # SURVEY.md 8c golden values
+    np.testing.assert_allclose(pc.bouligand2009(np.array([0.05, 0.5, 1, 3]), 3, 1, 10, 5),
+                               [8.292380801142428, 4.286832827341122, 1.9013876157386207, -4.295836866004333],
+                               rtol=1e-13)
+
+
+def test_min_func_matches_reference(grid):
+    g = load_golden("fit.npz")
+    k = g["cfg1_k"]
+    for i in (0, 5, 12):
+        f = grid.min_func(g["cfg1_xref"][i], k, g["cfg1_phi"][i], None)
+        np.testing.assert_allclose(f, g["cfg1_fref"][i], rtol=1e-12)
+    assert grid.min_func(np.array([3.0, 1.0, 0.0, 5.0]), k, g["cfg1_phi"][0], None) == 1e99
+    assert grid.min_func(np.array([3.0, 1.0, 400.0, 5.0]), k, g["cfg1_phi"][0], None) == 1e99
+
+
+# --------------------------------------------------------------------------- MAP fit
+def _check_fit(oracle, g, tag, ours):
+    xref, xpol, fref = g[tag + "_xref"], g[tag + "_xpol"], g[tag + "_fref"]
+    k, phis = g[tag + "_k"], g[tag + "_phi"]
+    mu, sg = g[tag + "_prior_mu"], g[tag + "_prior_sigma"]
+    ngate = 0
+    for i in range(xref.shape[0]):
+        ref_conv = np.max(np.abs(xref[i] - xpol[i]) / np.maximum(np.abs(xpol[i]), 1e-3))
+        rel = np.max(np.abs(ours[i] - xref[i]) / np.maximum(np.abs(xref[i]), 1e-3))
+        f_ours = oracle.misfit(ours[i], k, phis[i], mu, sg)
+        # never worse than the reference's own stopping point
+        assert f_ours <= fref[i] + 1e-9 * max(1.0, abs(fref[i])), (tag, i, f_ours, fref[i])
+        if ref_conv < 3e-5:       # reference converged: parameters within 1e-4 relative (north_star gate)
+            assert rel < 1e-4, (tag, i, rel, ours[i], xref[i])
+            ngate += 1
+    return ngate
+
+
+def test_fit_config1_matches_reference(grid, oracle):
+    g = load_golden("fit.npz")
+    res = grid.optimise_routine(float(g["cfg1_window"]), g["cfg1_xc"], g["cfg1_yc"])
+    assert isinstance(res, list) and len(res) == 4 and all(r.shape == (25,) for r in res)
+    ngate = _check_fit(oracle, g, "cfg1", np.stack(res, axis=1))
+    assert ngate >= 18
+
+
+def test_fit_200km_priors_detrend(grid, oracle):
+    g = load_golden("fit.npz")
+    res = grid.optimise_routine(200e3, g["w200_xc"], g["w200_yc"])
+    assert _check_fit(oracle, g, "w200", np.stack(res, axis=1)) == 9
+    grid.reset_priors()
+    grid.add_prior(beta=(3.0, 0.5), zt=(0.5, 0.25))
+    try:
+        res = grid.optimise_routine(150e3, g["w150_prior_xc"], g["w150_prior_yc"], taper=np.hamming,
+                                    process_subgrid=grid.remove_trend_linear)
+    finally:
+        grid.reset_priors()
+    assert _check_fit(oracle, g, "w150_prior", np.stack(res, axis=1)) >= 4
+    grid.add_prior(beta=(1.0, 0.1))
+    try:
+        x = grid.optimise(300e3, float(g["w300_betaprior_xc"][0]), float(g["w300_betaprior_yc"][0]))
+    finally:
+        grid.reset_priors()
+    assert x.shape == (4,)
+    _check_fit(oracle, g, "w300_betaprior", x[None, :])
+
+
+def test_fit_custom_process_subgrid_and_single(grid, oracle, mag):
+    """An arbitrary callable goes through the host path but is still fitted on the device."""
+    d, ext = mag
+    spec = oracle.GridSpec(d, *ext)
+    xc, yc = 152.5e3, 140.5e3
+    x_dev = grid.optimise(150e3, xc, yc, process_subgrid=lambda w: w * 2.0)
+    win = oracle.cut_window(spec, 150e3, xc, yc) * 2.0
+    k, phi, _ = oracle.radial_spectrum(win, spec.dx)
+    xp, fp = oracle.polished_fit(k, phi, oracle.map_fit(k, phi))
+    np.testing.assert_allclose(x_dev, xp, rtol=2e-5)
+
+
+# --------------------------------------------------------------------------- Metropolis-Hastings
+def test_mh_chain_matches_reference_stream(grid):
+    """Same Philox stream as the monkey-patched reference run: chains coincide step by step."""
+    g = load_golden("mh.npz")
+    seed = int(g["seed"])
+    for ci in range(2):
+        xc, yc = float(g["xc"][ci]), float(g["yc"][ci])
+        chain = np.array(grid.metropolis_hastings_batch(
+            100e3, [xc], [yc], 3000, 200, x_scale=g["x_scale"], beta=3.0, zt=0.5, dz=10.0, C=-19.0, seed=seed,
+            reduce="chains", chain_offset=ci))[0]
+        want = g["philox_noprior_%d" % ci]
+        same = np.all(np.abs(chain - want) < 1e-9, axis=0)
+        first_bad = same.size if same.all() else int(np.argmin(same))
+        assert first_bad >= 2500, first_bad      # an accept/reject flip from a 1-ulp difference is tolerated late
+    grid.add_prior(beta=(3.0, 1.0), zt=(1.0, 1.0), dz=(20.0, 10.0), C=(-19.0, 5.0))
+    try:
+        res = grid.metropolis_hastings(100e3, float(g["xc"][0]), float(g["yc"][0]), 3000, 200, x_scale=g["x_scale"],
+                                       beta=3.0, zt=0.5, dz=10.0, C=-19.0, seed=seed)
+    finally:
+        grid.reset_priors()
+    assert isinstance(res, list) and len(res) == 4 and res[0].shape == (3000,)
+    want = g["philox_prior_0"]
+    same = np.all(np.abs(np.array(res) - want) < 1e-9, axis=0)
+    assert (same.size if same.all() else int(np.argmin(same))) >= 2500
+
+
+def test_mh_moments_statistical_parity(grid):
+    """Posterior means / stds of independent device chains agree with the reference's own chains
+    (numpy RNG) within Monte-Carlo error."""
+    g = load_golden("mh.npz")
+    ref = g["ref_moments"]            # (6 chains, [mean,std], 5)
+    grid.add_prior(beta=(3.0, 1.0), zt=(1.0, 1.0), dz=(20.0, 10.0), C=(-19.0, 5.0))
+    try:
+        n = 24
+        xc, yc = np.full(n, float(g["xc"][0])), np.full(n, float(g["yc"][0]))
+        mom = grid.metropolis_hastings_batch(100e3, xc, yc, int(g["ref_nsim"]), 1000, x_scale=g["x_scale"],
+                                             beta=3.0, zt=0.5, dz=10.0, C=-19.0, seed=99, reduce="moments")
+    finally:
+        grid.reset_priors()
+    dev_mean, dev_std = mom[:, :5], mom[:, 5:]
+    for q in range(5):
+        for dev, rf in ((dev_mean[:, q], ref[:, 0, q]), (dev_std[:, q], ref[:, 1, q])):
+            se = np.sqrt(dev.var(ddof=1) / dev.size + rf.var(ddof=1) / rf.size)
+            assert abs(dev.mean() - rf.mean()) < 5.0 * se + 1e-12, (q, dev.mean(), rf.mean(), se)
+    # moments mode == moments of the chains mode for the same seed
+    ch = grid.metropolis_hastings_batch(100e3, xc[:2], yc[:2], 2000, 100, x_scale=g["x_scale"], beta=3.0, zt=0.5,
+                                        dz=10.0, C=-19.0, seed=5, reduce="chains")
+    mo = grid.metropolis_hastings_batch(100e3, xc[:2], yc[:2], 2000, 100, x_scale=g["x_scale"], beta=3.0, zt=0.5,
+                                        dz=10.0, C=-19.0, seed=5, reduce="moments")
+    full = np.concatenate([ch, (ch[:, 1] + ch[:, 2])[:, None, :]], axis=1)
+    np.testing.assert_allclose(mo[:, :5], full.mean(axis=2), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(mo[:, 5:], full.std(axis=2), rtol=1e-8, atol=1e-10)
+    assert not np.array_equal(ch[0], ch[1])        # distinct chain ids -> distinct streams
+
+
+def test_parallelise_routine_containers(grid):
+    xc, yc = grid.create_centroid_list(100e3, 100e3, 100e3)
+    out = grid.parallelise_routine(100e3, xc, yc, grid.metropolis_hastings, 50, 10)
+    assert len(out) == 4 and len(out[0]) == xc.size and out[0][0].shape == (50,)
+    out = grid.parallelise_routine(100e3, xc[:3], yc[:3], lambda w, x, y: np.array([x, y, w, 0.0]))
+    assert len(out) == 4 and np.array_equal(out[0], xc[:3])
+    with pytest.raises(ValueError, match="same size"):
+        grid.parallelise_routine(100e3, xc, yc[:-1], grid.optimise)
+    with pytest.raises(ValueError, match="outside data range"):
+        grid.optimise_routine(100e3, [-5.0], [150e3])
+    with pytest.raises(ValueError, match="exceeds the data range"):
+        grid.optimise_routine(100e3, [10e3], [150e3])
+
+
+# --------------------------------------------------------------------------- Radon / azimuthal
+def test_radon_csr_bit_exact_and_sinogram(pc, grid):
+    g = load_golden("radon.npz")
+    for nw in (51, 101):
+        j0, i0, _ = (int(v) for v in g["n%d_meta" % nw])
+        theta = g["n%d_theta" % nw]
+        data, ind, ptr = pc.radon.radon_csr(nw, theta)
+        assert ind.dtype == np.int64 and ptr.dtype == np.int64
+        assert np.array_equal(ptr, g["n%d_indptr" % nw])
+        off = np.concatenate([[0], np.cumsum(ptr[:, -1])])
+        for t in range(theta.size):
+            key = "n%d_t%d_data" % (nw, t)
+            seg = slice(off[t], off[t + 1])
+            chk = np.add.reduceat(ind[seg] * (1 + np.arange(ind[seg].size) % 7), ptr[t, :-1])
+            assert np.array_equal(chk, g["n%d_index_checksum" % nw][t])
+            assert np.array_equal(np.add.reduceat(data[seg], ptr[t, :-1]), g["n%d_length_sum" % nw][t])
+            if key in g.files:
+                assert np.array_equal(data[seg], g[key]) and np.array_equal(ind[seg], g["n%d_t%d_indices" % (nw, t)])
+        win = np.ascontiguousarray(grid.data[j0:j0 + nw, i0:i0 + nw])
+        sino = pc.radon.radon2d(win, theta)
+        assert np.array_equal(sino, g["n%d_sinogram" % nw])
+        kb, S, dth = grid.azimuthal_spectrum(grid.data[j0:j0 + nw, i0:i0 + nw])
+        assert np.array_equal(kb, g["n%d_az_k" % nw]) and np.array_equal(dth, g["n%d_az_theta" % nw])
+        np.testing.assert_allclose(S, g["n%d_az_S" % nw], rtol=1e-10)
+    with pytest.raises(ValueError, match="theta should be within"):
+        pc.radon.radon2d(np.zeros((8, 8)), np.array([np.pi]))
+
+
+# --------------------------------------------------------------------------- the reference's own tests
+def test_reference_suite_behaviour(pc, grid, mag):
+    """tests/test_grid.py and tests/test_optimise.py of the reference, against the new classes."""
+    d, (xmin, xmax, ymin, ymax) = mag
+    xc, yc = 0.5 * (xmin + xmax), 0.5 * (ymin + ymax)
+    G = pc.CurieGrid(d, xmin, xmax, ymin, ymax)
+    sub = G.subgrid(100e3, xc, yc)
+    assert sub.shape[0] < G.data.shape[0] and sub.shape[1] < G.data.shape[1]
+    k, Phi, sPhi = G.radial_spectrum(G.data, taper=None)               # test_FFT
+    i3 = len(k) // 3
+    assert Phi[:i3].mean() > Phi[i3:2 * i3].mean() > Phi[2 * i3:].mean()
+    assert sPhi[:i3].mean() > sPhi[i3:2 * i3].mean() > sPhi[2 * i3:].mean()
+    _, Phi2, _ = G.radial_spectrum(G.data, taper=np.hanning)           # test_taper_functions
+    _, Phi3, _ = G.radial_spectrum(G.data, taper=np.hamming)
+    assert Phi.mean() > Phi2.mean() and Phi.mean() > Phi3.mean()
+    assert np.gradient(Phi, k).mean() > np.gradient(Phi2, k).mean()
+    k, P, sP = G.radial_spectrum(G.data, taper=np.hanning, power=0.5)  # test_Tanaka
+    (Ztr, btr, dZtr), (Zor, bor, dZor) = pc.tanaka1999(k, P, sP, (0.005, 0.03), (0.03, 0.7))
+    Zb, eZb = pc.ComputeTanaka(Ztr, dZtr, Zor, dZor)
+    assert abs(Zb - 10.0) < 2.0 and eZb < Zb
+    np.testing.assert_allclose([Ztr, btr, dZtr, Zor, bor, dZor, Zb, eZb], load_golden("misc.npz")["tanaka"], rtol=1e-7)
+    beta, zt, dz, C = grid.optimise(300e3, xc, yc, taper=np.hanning)   # test_optimisation
+    assert abs(beta - 3.0) < 0.3 and abs(zt - 0.305) < 0.1 and abs(dz - 10.305) < 2.0
+    grid.add_prior(beta=(1.0, 0.1))                                    # test_priors
+    try:
+        beta1 = grid.optimise(300e3, xc, yc)[0]
+    finally:
+        grid.reset_priors()
+    assert abs(beta1 - 1.0) < abs(beta - 1.0)
