@@ -117,7 +117,7 @@ int cb_bouligand_points(const double *kh_dev, const double *params_dev, int64_t 
 }
 
 static int per_warp_launch_shape(int nk, int64_t nwin, int *grid, size_t *smem) {
-    CB_REQUIRE(nk > 0 && nk <= 4096, "nk must be in [1, 4096]");
+    CB_REQUIRE(nk > 0 && nk <= 2048, "nk must be in [1, 2048]");
     *smem = (size_t)CB_FIT_WARPS * 3 * (size_t)nk * sizeof(double);
     int64_t g = (nwin + CB_FIT_WARPS - 1) / CB_FIT_WARPS;
     CB_REQUIRE(g <= 2147483647LL, "too many windows for one launch");
@@ -142,7 +142,7 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
         P.pr.mu[j] = prior_mu_host ? prior_mu_host[j] : NAN;
         P.pr.sigma[j] = prior_sigma_host ? prior_sigma_host[j] : NAN;
     }
-    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     misfit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
@@ -168,7 +168,7 @@ int cb_fit_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nw
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
     P.x_out = x_out_dev; P.f_out = f_out_dev; P.niter = niter_dev; P.status = status_dev; P.nfev = nfev_dev;
     P.warps_per_block = CB_FIT_WARPS;
-    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     fit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
@@ -190,7 +190,7 @@ int cb_mh_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwi
     memset(&P, 0, sizeof(P));
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
     P.out = out_dev; P.accepted = accepted_dev; P.warps_per_block = CB_FIT_WARPS;
-    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     mh_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;

@@ -138,7 +138,7 @@ int cb_azimuthal_tail_batch(const double *sinogram_dev, int nw, int ntheta, int6
     AzTailParams P{sinogram_dev, nw, ntheta, nkb, nwin, d_taper, power, S_dev};
     const int nk = 1 + 2 * nkb;
     const size_t smem = (size_t)nk * sizeof(double2) + (size_t)nw * sizeof(double);
-    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(az_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(az_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int64_t grid = nwin * ntheta;
     CB_REQUIRE(grid <= 2147483647LL, "batch too large for one launch");
     az_tail_kernel<<<(int)grid, 128, smem, (cudaStream_t)stream>>>(P);

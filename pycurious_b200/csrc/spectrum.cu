@@ -69,10 +69,12 @@ int cb_spectrum_plan_create(int nw, int nbins, const double *taper_r, const doub
     UP(d_tw, tw) UP(d_chirp, chirp) UP(d_filt, filt) UP(d_slot, slot)
     UP(d_bin_ptr, bin_ptr) UP(d_bin_idx, bin_idx) UP(d_taper_r, taper_r) UP(d_taper_c, taper_c)
 #undef UP
+    // the attribute belongs to the kernel, not to the plan: raise it once to the device limit so that
+    // plans with different line lengths can coexist
     cudaError_t e = cudaFuncSetAttribute(spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)hp.smem_bytes);
+                                         (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) {
-        cb_set_error("cudaFuncSetAttribute(smem=%lld): %s", (long long)hp.smem_bytes, cudaGetErrorString(e));
+        cb_set_error("cudaFuncSetAttribute(smem=%lld): %s", (long long)prop.sharedMemPerBlockOptin, cudaGetErrorString(e));
         cb_spectrum_plan_destroy(pl);
         return CB_ERR_CUDA;
     }

@@ -42,6 +42,8 @@ static inline void fold_bins(int n, int nbins, const int32_t *ptr, const int32_t
             int u = (a + (n + 1) / 2) % n;      // np.fft.fftshift: shifted[a] = orig[(a + ceil(n/2)) % n]
             int v = (c + (n + 1) / 2) % n;
             if (v > half) { u = (n - u) % n; v = n - v; }
+            // columns v = 0 (and v = n/2 for even n) are their own mirror: fold u as well
+            if ((v == 0 || 2 * v == n) && u > half) u = n - u;
             ids.push_back(v * n + u);
         }
         std::sort(ids.begin(), ids.end());

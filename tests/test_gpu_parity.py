@@ -75,6 +75,8 @@ def test_device_bin_map_bit_exact(pc, oracle, nw):
         fold = v > half
         u = np.where(fold, (nw - u) % nw, u)
         v = np.where(fold, nw - v, v)
+        self_mirror = ((v == 0) | (2 * v == nw)) & (u > half)
+        u = np.where(self_mirror, nw - u, u)
         want = np.sort(v * nw + u)
         got = idx[ptr[b]:ptr[b + 1]]
         uniq, cnt = np.unique(want, return_counts=True)
