@@ -8,7 +8,7 @@
 #pragma once
 #include "common.cuh"
 
-#ifdef __CUDACC__
+#if defined(__CUDACC__) && !defined(CB_EMU)
 struct DevCtx {
     char *smem_base;
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
@@ -21,6 +21,8 @@ struct DevCtx {
     __device__ __forceinline__ double shfl_xor(double v, int o) const { return __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ __forceinline__ double shfl(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
     __device__ __forceinline__ int shfl_i(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ double shfl_up(double v, int delta) const { return __shfl_up_sync(0xffffffffu, v, delta); }
+    __device__ __forceinline__ int warp_max_i(int v) const { return __reduce_max_sync(0xffffffffu, v); }
     __device__ __forceinline__ int team_lanes() const { return CB_WARP; }
     __device__ __forceinline__ double warp_sum(double v) const {
 #pragma unroll
@@ -71,6 +73,18 @@ struct HostCtx {
         return r;
     }
     int shfl_i(int v, int src) const { return (int)shfl((double)v, src); }
+    double shfl_up(double v, int delta) const {     // lanes below delta keep their own value
+        blk->shfl_buf[tid_] = v;
+        sync_warp();
+        const int lane = tid_ & 31;
+        double r = lane >= delta ? blk->shfl_buf[tid_ - delta] : v;
+        sync_warp();
+        return r;
+    }
+    int warp_max_i(int v) const {
+        for (int o = 16; o > 0; o >>= 1) { int t = (int)shfl_xor((double)v, o); v = t > v ? t : v; }
+        return v;
+    }
     int team_lanes() const { return CB_WARP; }
     double warp_sum(double v) const {
         for (int o = 16; o > 0; o >>= 1) v += shfl_xor(v, o);
@@ -105,6 +119,8 @@ struct SerialCtx {
     double shfl_xor(double v, int) const { return v; }
     double shfl(double v, int) const { return v; }
     int shfl_i(int v, int) const { return v; }
+    double shfl_up(double v, int) const { return v; }
+    int warp_max_i(int v) const { return v; }
     int team_lanes() const { return 1; }
     double warp_sum(double v) const { return v; }
     bool any(bool pred) const { return pred; }

@@ -16,7 +16,7 @@
 // pgtol 1e-5); this solver converges to the same bounded minimum more tightly, so on windows where
 // the reference is converged the parameters agree to ~1e-5 relative (tests/test_fit_parity.py).
 #pragma once
-#include "bouligand.cuh"
+#include "model_eval.cuh"
 
 struct FitParams {
     const double *kh;       // [nk]
@@ -47,28 +47,29 @@ CB_HD int tri(int i, int j) {   // i <= j
 }
 
 template <class Ctx>
-CB_BODY void fit_eval_full(const Ctx &cx, const double *kh, const double *logk, const double *phi, int nk,
-                           const double *x, const Priors &pr, int lane, FitEval &ev) {
+CB_BODY void fit_eval_full(const Ctx &cx, const WarpSlab &W, const double *x, const Priors &pr, int lane,
+                           FitEval &ev) {
     const double hb = 1e-6 * fmax(1.0, fabs(x[0]));
-    const ModelCoef m0 = model_coef(x[0], x[1], x[2], x[3]);
-    const ModelCoef mp = model_coef(x[0] + hb, x[1], x[2], x[3]);
-    const ModelCoef mm = model_coef(x[0] - hb, x[1], x[2], x[3]);
+    double xs[4] = {x[0], x[1], x[2], x[3]};
+    model_eval_warp(cx, W, xs, lane, W.p0, W.dz);
+    xs[0] = x[0] + hb;
+    model_eval_warp(cx, W, xs, lane, W.pp, nullptr);
+    xs[0] = x[0] - hb;
+    model_eval_warp(cx, W, xs, lane, W.pm, nullptr);
     double acc[15];
 #pragma unroll
     for (int q = 0; q < 15; ++q) acc[q] = 0.0;
-    for (int i = lane; i < nk; i += cx.team_lanes()) {
-        const double k = kh[i], lk = logk[i];
+    for (int i = lane; i < W.nk; i += cx.team_lanes()) {
+        const double p0 = W.p0[i], pp = W.pp[i], pm = W.pm[i];
         double J[4];
-        const double p0 = bouligand_point_ddz(m0, k, lk, J[2]);
-        const double pp = bouligand_point(mp, k, lk);
-        const double pm = bouligand_point(mm, k, lk);
         if (isfinite(pp) && isfinite(pm)) J[0] = (pp - pm) / (2.0 * hb);
         else if (isfinite(pp)) J[0] = (pp - p0) / hb;
         else if (isfinite(pm)) J[0] = (p0 - pm) / hb;
         else J[0] = 0.0;
-        J[1] = -2.0 * k;
+        J[1] = -2.0 * W.k[i];
+        J[2] = W.dz[i];
         J[3] = 1.0;
-        const double r = p0 - phi[i];
+        const double r = p0 - W.obs[i];
         acc[0] = fma(r, r, acc[0]);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -77,6 +78,7 @@ CB_BODY void fit_eval_full(const Ctx &cx, const double *kh, const double *logk, 
             for (int b = a; b < 4; ++b) acc[5 + tri(a, b)] = fma(J[a], J[b], acc[5 + tri(a, b)]);
         }
     }
+    cx.sync_warp();
 #pragma unroll
     for (int q = 0; q < 15; ++q) acc[q] = cx.warp_sum(acc[q]);
     double f = 0.5 * acc[0];
@@ -174,16 +176,10 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     const int64_t w = (int64_t)cx.bid() * P.warps_per_block + warp;
     if (w >= P.nwin) return;     // whole warp leaves together
 
-    // per-warp staging of k, ln k, Phi in shared memory
-    double *s_k = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * 3 * nk;
-    double *s_lk = s_k + nk, *s_phi = s_lk + nk;
-    for (int i = lane; i < nk; i += cx.team_lanes()) {
-        const double k = P.kh[i];
-        s_k[i] = k;
-        s_lk[i] = log(k);
-        s_phi[i] = P.phi[w * nk + i];
-    }
-    cx.sync_warp();
+    // per-warp slab in shared memory: k, ln k, Phi, model values and the order tables
+    WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * warp_slab_doubles(nk, true),
+                                 nk, true);
+    warp_slab_load(cx, W, P.kh, P.phi + w * nk, lane);
 
     const cb_fit_options &o = P.opt;
     Priors pr;
@@ -202,7 +198,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     const double ftol = o.ftol > 0.0 ? o.ftol : 1e-15;
 
     FitEval ev;
-    fit_eval_full(cx, s_k, s_lk, s_phi, nk, x, pr, lane, ev);
+    fit_eval_full(cx, W, x, pr, lane, ev);
     int status = FIT_MAXITER, it = 0, nfev = 3;
     if (!ev.ok) {
         status = FIT_BAD_START;
@@ -221,6 +217,9 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
                 if (!frozen[j]) pgn = fmax(pgn, fabs(ev.g[j]));
             }
             if (pgn <= gtol) { status = FIT_CONVERGED_PG; break; }
+#ifdef CB_FIT_TRACE
+            if (lane == 0) printf("it %3d f %.15g pgn %.3e x %.6f %.6f %.6f %.6f fresh %d nfev %d\n", it, ev.f, pgn, x[0], x[1], x[2], x[3], (int)fresh, nfev);
+#endif
 
             double d[4];
             bool have = solve_free(B, ev.g, frozen, d);
@@ -268,7 +267,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
                     move = fmax(move, fabs(xt[j] - x[j]));
                 }
                 if (move == 0.0) break;
-                ft = misfit_warp(cx, s_k, s_lk, s_phi, nk, xt, pr, lane);
+                ft = misfit_slab(cx, W, xt, pr, lane);
                 ++nfev;
                 if (ft <= ev.f + 1e-4 * dec && ft < 1e98) { accepted = true; break; }
                 if (ft >= 1e98) alpha *= 0.25;
@@ -291,7 +290,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
             }
 
             FitEval en;
-            fit_eval_full(cx, s_k, s_lk, s_phi, nk, xt, pr, lane, en);
+            fit_eval_full(cx, W, xt, pr, lane, en);
             nfev += 3;
             if (!en.ok) { status = FIT_LINESEARCH; break; }
             double s[4], y[4], sy = 0.0, ss = 0.0, yy = 0.0;

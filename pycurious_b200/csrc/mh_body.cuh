@@ -7,7 +7,7 @@
 // counter = (step, block, phase); the stream is replicated on the host by
 // oracle/curie_oracle.py:PhiloxStream so that chains are step-comparable.
 #pragma once
-#include "bouligand.cuh"
+#include "model_eval.cuh"
 
 struct MhParams {
     const double *kh;
@@ -89,15 +89,9 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     const int64_t w = (int64_t)cx.bid() * P.warps_per_block + warp;
     if (w >= P.nwin) return;
 
-    double *s_k = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * 3 * nk;
-    double *s_lk = s_k + nk, *s_phi = s_lk + nk;
-    for (int i = lane; i < nk; i += cx.team_lanes()) {
-        const double k = P.kh[i];
-        s_k[i] = k;
-        s_lk[i] = log(k);
-        s_phi[i] = P.phi[w * nk + i];
-    }
-    cx.sync_warp();
+    WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * warp_slab_doubles(nk, false),
+                                 nk, false);
+    warp_slab_load(cx, W, P.kh, P.phi + w * nk, lane);
 
     const cb_mh_options &o = P.opt;
     Priors pr;
@@ -113,13 +107,13 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     const uint32_t k0 = (uint32_t)(o.seed ^ chain), k1 = (uint32_t)((o.seed >> 32) ^ (chain >> 32));
 
     // ---- burn-in (optimise.py:598-611) ----
-    double P0 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x, pr, lane) / 1000.0);
+    double P0 = exp(-misfit_slab(cx, W, x, pr, lane) / 1000.0);
     for (int64_t t = 0; t < o.burnin; ++t) {
         double z[4], x1[4];
         philox_normal4((uint64_t)t, 0u, k0, k1, z);
 #pragma unroll
         for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
-        const double P1 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x1, pr, lane) / 1000.0);
+        const double P1 = exp(-misfit_slab(cx, W, x1, pr, lane) / 1000.0);
         if (P1 > P0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = x1[j];
@@ -128,7 +122,7 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     }
 
     // ---- sampling (optimise.py:613-631) ----
-    P0 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x, pr, lane));
+    P0 = exp(-misfit_slab(cx, W, x, pr, lane));
     int64_t nacc = 0;
     double mean[5] = {0, 0, 0, 0, 0}, m2[5] = {0, 0, 0, 0, 0};   // Welford accumulators (mode 1)
     double *chain_out = P.out + w * 4 * o.nsim;
@@ -139,7 +133,7 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
         P0 = fmax(P0, 1e-99);
-        const double P1 = exp(-misfit_warp(cx, s_k, s_lk, s_phi, nk, x1, pr, lane));
+        const double P1 = exp(-misfit_slab(cx, W, x1, pr, lane));
         const double ratio = fmin(P1 / P0, 1.0);
         if (u <= ratio) {
 #pragma unroll

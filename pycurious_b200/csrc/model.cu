@@ -52,16 +52,11 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) misfit_kernel(const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * CB_FIT_WARPS + warp;
     if (row >= P.m) return;
-    double *s_k = cb_dyn_smem_d + (int64_t)warp * 3 * P.nk, *s_lk = s_k + P.nk, *s_phi = s_lk + P.nk;
-    for (int i = lane; i < P.nk; i += CB_WARP) {
-        s_k[i] = P.kh[i];
-        s_lk[i] = log(P.kh[i]);
-        s_phi[i] = P.phi[row * P.phi_stride + i];
-    }
-    __syncwarp();
+    WarpSlab W = warp_slab_carve(cb_dyn_smem_d + (int64_t)warp * warp_slab_doubles(P.nk, false), P.nk, false);
+    warp_slab_load(cx, W, P.kh, P.phi + row * P.phi_stride, lane);
     double x[4];
     for (int j = 0; j < 4; ++j) x[j] = P.params[row * 4 + j];
-    const double f = misfit_warp(cx, s_k, s_lk, s_phi, P.nk, x, P.pr, lane);
+    const double f = misfit_slab(cx, W, x, P.pr, lane);
     if (lane == 0) P.out[row] = f;
 }
 
@@ -116,9 +111,9 @@ int cb_bouligand_points(const double *kh_dev, const double *params_dev, int64_t 
     return CB_OK;
 }
 
-static int per_warp_launch_shape(int nk, int64_t nwin, int *grid, size_t *smem) {
-    CB_REQUIRE(nk > 0 && nk <= 2048, "nk must be in [1, 2048]");
-    *smem = (size_t)CB_FIT_WARPS * 3 * (size_t)nk * sizeof(double);
+static int per_warp_launch_shape(int nk, int64_t nwin, bool fit, int *grid, size_t *smem) {
+    CB_REQUIRE(nk > 0 && nk <= 512, "nk must be in [1, 512]");
+    *smem = (size_t)CB_FIT_WARPS * (size_t)warp_slab_doubles(nk, fit) * sizeof(double);
     int64_t g = (nwin + CB_FIT_WARPS - 1) / CB_FIT_WARPS;
     CB_REQUIRE(g <= 2147483647LL, "too many windows for one launch");
     *grid = (int)g;
@@ -135,7 +130,7 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
     if (rc) return rc;
     int grid;
     size_t smem;
-    if ((rc = per_warp_launch_shape(nk, m, &grid, &smem)) != CB_OK) return rc;
+    if ((rc = per_warp_launch_shape(nk, m, false, &grid, &smem)) != CB_OK) return rc;
     MisfitParams P;
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.phi_stride = phi_stride; P.params = params_dev; P.m = m; P.out = out_dev;
     for (int j = 0; j < 4; ++j) {
@@ -162,7 +157,7 @@ int cb_fit_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nw
     if (rc) return rc;
     int grid;
     size_t smem;
-    if ((rc = per_warp_launch_shape(nk, nwin, &grid, &smem)) != CB_OK) return rc;
+    if ((rc = per_warp_launch_shape(nk, nwin, true, &grid, &smem)) != CB_OK) return rc;
     FitParams P;
     memset(&P, 0, sizeof(P));
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
@@ -185,7 +180,7 @@ int cb_mh_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwi
     if (rc) return rc;
     int grid;
     size_t smem;
-    if ((rc = per_warp_launch_shape(nk, nwin, &grid, &smem)) != CB_OK) return rc;
+    if ((rc = per_warp_launch_shape(nk, nwin, false, &grid, &smem)) != CB_OK) return rc;
     MhParams P;
     memset(&P, 0, sizeof(P));
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;

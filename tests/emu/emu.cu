@@ -149,11 +149,13 @@ void emu_misfit(const double *kh, int nk, const double *phi, int64_t phi_stride,
                 const double *prior_mu, const double *prior_sigma, double *out) {
     Priors pr;
     for (int j = 0; j < 4; ++j) { pr.mu[j] = prior_mu ? prior_mu[j] : NAN; pr.sigma[j] = prior_sigma ? prior_sigma[j] : NAN; }
-    std::vector<double> lk(nk);
-    for (int j = 0; j < nk; ++j) lk[j] = log(kh[j]);
-    SerialCtx cx{0, 1, 0, 1, nullptr};
-    for (int64_t r = 0; r < m; ++r)
-        out[r] = misfit_warp(cx, kh, lk.data(), phi + r * phi_stride, nk, params + 4 * r, pr, 0);
+    std::vector<double> sm(warp_slab_doubles(nk, false));
+    SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
+    for (int64_t r = 0; r < m; ++r) {
+        WarpSlab W = warp_slab_carve(sm.data(), nk, false);
+        warp_slab_load(cx, W, kh, phi + r * phi_stride, 0);
+        out[r] = misfit_slab(cx, W, params + 4 * r, pr, 0);
+    }
 }
 
 // mode 0: SerialCtx (one lane per warp, fast); mode 1: HostCtx (32 pthreads per warp, checks the shuffles)
@@ -165,14 +167,14 @@ int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_
     P.x_out = x_out; P.f_out = f_out; P.niter = niter; P.status = status; P.nfev = nfev;
     if (mode == 0) {
         P.warps_per_block = 1;
-        std::vector<double> sm(3 * nk);
+        std::vector<double> sm(warp_slab_doubles(nk, true));
         for (int64_t w = 0; w < nwin; ++w) {
             SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
             fit_body(cx, P);
         }
     } else {
         P.warps_per_block = 2;
-        emu_launch((int)((nwin + 1) / 2), 64, 2 * 3 * nk * sizeof(double), [&](const HostCtx &cx) { fit_body(cx, P); });
+        emu_launch((int)((nwin + 1) / 2), 64, 2 * warp_slab_doubles(nk, true) * sizeof(double), [&](const HostCtx &cx) { fit_body(cx, P); });
     }
     return 0;
 }
@@ -184,14 +186,14 @@ int emu_mh(const double *kh, int nk, const double *phi, int64_t nwin, const cb_m
     P.kh = kh; P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0; P.out = out; P.accepted = accepted;
     if (mode == 0) {
         P.warps_per_block = 1;
-        std::vector<double> sm(3 * nk);
+        std::vector<double> sm(warp_slab_doubles(nk, false));
         for (int64_t w = 0; w < nwin; ++w) {
             SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
             mh_body(cx, P);
         }
     } else {
         P.warps_per_block = 2;
-        emu_launch((int)((nwin + 1) / 2), 64, 2 * 3 * nk * sizeof(double), [&](const HostCtx &cx) { mh_body(cx, P); });
+        emu_launch((int)((nwin + 1) / 2), 64, 2 * warp_slab_doubles(nk, false) * sizeof(double), [&](const HostCtx &cx) { mh_body(cx, P); });
     }
     return 0;
 }
@@ -225,6 +227,26 @@ int emu_az_tail(const double *sino, int nw, int ntheta, int64_t nwin, const doub
     const int nk = 1 + 2 * nkb;
     emu_launch((int)(nwin * ntheta), 32, (size_t)nk * 16 + (size_t)nw * 8, [&](const HostCtx &cx) { az_tail_body(cx, P); });
     return 0;
+}
+
+// Warp-cooperative model evaluation (fast path) for direct comparison with bouligand2009: mode 0 serial, 1 = 32 lanes
+void emu_model_eval(const double *kh, int nk, const double *x, double *phi, double *ddz, int mode) {
+    std::vector<double> zero(nk, 0.0);
+    if (mode == 0) {
+        std::vector<double> sm(warp_slab_doubles(nk, true));
+        SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
+        WarpSlab W = warp_slab_carve(sm.data(), nk, true);
+        warp_slab_load(cx, W, kh, zero.data(), 0);
+        model_eval_warp(cx, W, x, 0, W.p0, W.dz);
+        for (int i = 0; i < nk; ++i) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
+    } else {
+        emu_launch(1, 32, warp_slab_doubles(nk, true) * sizeof(double), [&](const HostCtx &cx) {
+            WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()), nk, true);
+            warp_slab_load(cx, W, kh, zero.data(), cx.tid());
+            model_eval_warp(cx, W, x, cx.tid(), W.p0, W.dz);
+            for (int i = cx.tid(); i < nk; i += 32) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
+        });
+    }
 }
 
 void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {

@@ -182,6 +182,38 @@ def test_ddz_derivative(emu, oracle):
         np.testing.assert_allclose(phi, oracle.bouligand2009(k, *p), rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_model_eval_warp_fast_path(emu, oracle, mode):
+    """Warp-cooperative evaluation (Temme / Miller / K-negligible classes, model_eval.cuh) against
+    bouligand2009 for parameter vectors that exercise every class and the generic fallback."""
+    k99 = load_golden("fit.npz")["w200_k"]
+    k49 = load_golden("forward.npz")["k49"]
+    cases = [(3.0, 1.0, 10.0, 5.0), (3.0, 1.0, 0.3, 5.0), (2.2, 0.4, 2.0, -19.0), (0.0, 0.0, 1.0, 0.0),
+             (4.7, 0.1, 35.0, 3.0), (1.0, 2.0, 100.0, -5.0), (3.0, 1.0, 240.0, 5.0), (15.9, 1.0, 7.0, 2.0),
+             (3.0, 1.0, 1e-3, 5.0), (6.5, 0.0, 0.05, 1.0), (-0.5, 1.0, 3.0, 5.0), (3.0, 1.0, 0.0, 5.0)]
+    for k in (k49, k99):
+        for p in cases:
+            p = np.array(p, dtype=np.float64)
+            phi, ddz = np.empty(k.size), np.empty(k.size)
+            emu.emu_model_eval(P(k), k.size, P(p), P(phi), P(ddz), mode)
+            with np.errstate(all="ignore"):
+                ref = oracle.bouligand2009(k, *p)
+                h = 1e-5 * max(1.0, p[2])
+                fd = (oracle.bouligand2009(k, p[0], p[1], p[2] + h, p[3]) -
+                      oracle.bouligand2009(k, p[0], p[1], p[2] - h, p[3])) / (2 * h)
+            assert np.array_equal(np.isfinite(phi), np.isfinite(ref)), p
+            fin = np.isfinite(ref)
+            if not fin.any():
+                continue
+            # the bracket of grid.py:595 cancels like eps / (k dz)^2 for small k dz in the reference itself
+            xmin = max(k[0] * p[2], 1e-300)
+            atol = 2e-12 * max(1.0, np.abs(ref[fin]).max()) + 1e-14 / min(1.0, xmin * xmin)
+            np.testing.assert_allclose(phi[fin], ref[fin], rtol=0, atol=atol, err_msg=str(p))
+            if p[2] > 1e-2 and p[0] >= 0:
+                ok = fin & np.isfinite(fd)
+                np.testing.assert_allclose(ddz[ok], fd[ok], rtol=1e-6, atol=5e-8, err_msg=str(p))
+
+
 def test_misfit_matches_min_func(emu, oracle):
     g = load_golden("fit.npz")
     k = g["cfg1_k"]
