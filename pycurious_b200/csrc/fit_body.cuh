@@ -4,12 +4,17 @@
 // differences, by a bounded quasi-Newton method on the same objective:
 //
 //   * lanes own wavenumbers; one evaluation gives the misfit, its gradient and the Gauss-Newton
-//     matrix J^T J in one pass (warp-shuffle reductions of 15 scalars)
+//     matrix J^T J in one pass (warp-shuffle reductions of 15 scalars); the 4x4 algebra between
+//     evaluations is done by lane 0 on a small state block in shared memory
 //   * dPhi/dC = 1, dPhi/dzt = -2k and dPhi/ddz (via K_{nu-1}) are analytic; dPhi/dbeta is a
 //     central difference of the model in beta (no closed form for dK_nu/dnu)
 //   * projected BFGS: the Hessian model starts from J^T J + prior precision and receives BFGS
 //     secant updates; variables sitting on a bound with the gradient pointing outward are frozen
-//     (two-metric projection), the line search is a projected Armijo backtracking
+//     (two-metric projection), the line search is a projected Armijo backtracking whose accepted
+//     trial evaluation is reused as the next iterate's model values
+//   * dz is additionally bounded by the cosh-overflow wall 710.4758/k_max, beyond which min_func is
+//     1e99: windows whose misfit valley runs flat towards large dz end on that wall instead of
+//     creeping up to it through rejected steps
 //   * non-finite model values give 1e99 exactly like min_func (optimise.py:226-227)
 //
 // The reference's stopping point is set by its own noisy forward-difference gradient (factr 1e7,
@@ -35,78 +40,24 @@ struct FitParams {
 
 enum { FIT_CONVERGED_PG = 0, FIT_CONVERGED_F = 1, FIT_LINESEARCH = 2, FIT_MAXITER = 3, FIT_BAD_START = 4 };
 
-struct FitEval {
-    double f;        // objective incl. priors (1e99 when non-finite)
-    double g[4];
-    double H[10];    // packed upper triangle of J^T J + prior precision: (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)
-    bool ok;
-};
-
 CB_HD int tri(int i, int j) {   // i <= j
     return i * 4 - (i * (i - 1)) / 2 + (j - i);
 }
 
-template <class Ctx>
-CB_BODY void fit_eval_full(const Ctx &cx, const WarpSlab &W, const double *x, const Priors &pr, int lane,
-                           FitEval &ev) {
-    const double hb = 1e-6 * fmax(1.0, fabs(x[0]));
-    double xs[4] = {x[0], x[1], x[2], x[3]};
-    model_eval_warp(cx, W, xs, lane, W.p0, W.dz);
-    xs[0] = x[0] + hb;
-    model_eval_warp(cx, W, xs, lane, W.pp, nullptr);
-    xs[0] = x[0] - hb;
-    model_eval_warp(cx, W, xs, lane, W.pm, nullptr);
-    double acc[15];
-#pragma unroll
-    for (int q = 0; q < 15; ++q) acc[q] = 0.0;
-    for (int i = lane; i < W.nk; i += cx.team_lanes()) {
-        const double p0 = W.p0[i], pp = W.pp[i], pm = W.pm[i];
-        double J[4];
-        if (isfinite(pp) && isfinite(pm)) J[0] = (pp - pm) / (2.0 * hb);
-        else if (isfinite(pp)) J[0] = (pp - p0) / hb;
-        else if (isfinite(pm)) J[0] = (p0 - pm) / hb;
-        else J[0] = 0.0;
-        J[1] = -2.0 * W.k[i];
-        J[2] = W.dz[i];
-        J[3] = 1.0;
-        const double r = p0 - W.obs[i];
-        acc[0] = fma(r, r, acc[0]);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            acc[1 + a] = fma(r, J[a], acc[1 + a]);
-#pragma unroll
-            for (int b = a; b < 4; ++b) acc[5 + tri(a, b)] = fma(J[a], J[b], acc[5 + tri(a, b)]);
-        }
-    }
-    cx.sync_warp();
-#pragma unroll
-    for (int q = 0; q < 15; ++q) acc[q] = cx.warp_sum(acc[q]);
-    double f = 0.5 * acc[0];
-    bool ok = isfinite(f);
-#pragma unroll
-    for (int q = 1; q < 15; ++q) ok = ok && isfinite(acc[q]);
-    ev.ok = ok;
-    if (!ok) {
-        ev.f = CB_BIG_MISFIT;
-#pragma unroll
-        for (int a = 0; a < 4; ++a) ev.g[a] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 10; ++q) ev.H[q] = 0.0;
-        return;
-    }
-    ev.f = f + prior_penalty(pr, x);
-#pragma unroll
-    for (int a = 0; a < 4; ++a) ev.g[a] = acc[1 + a];
-#pragma unroll
-    for (int q = 0; q < 10; ++q) ev.H[q] = acc[5 + q];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-        if (!isnan(pr.mu[a])) {
-            const double w = 1.0 / (pr.sigma[a] * pr.sigma[a]);
-            ev.g[a] += (x[a] - pr.mu[a]) * w;
-            ev.H[tri(a, a)] += w;
-        }
-}
+// Solver state of one window, in the warp's shared-memory slab.  The 4x4 algebra is done by lane 0
+// (the other lanes wait at the next warp barrier); the model evaluations are done by all lanes.
+struct FitState {
+    double x[4], lb[4], ub[4];
+    double f, g[4], H[10];        // current iterate: objective, gradient, Gauss-Newton matrix (+ prior precision)
+    double B[10];                 // quasi-Newton metric (packed upper triangle)
+    double d[4], gd;              // search direction and g.d
+    double xt[4], dec, move, pen_t, hb;   // trial point, g.(xt-x), max |xt-x|, prior penalty at xt, beta step
+    double fn, gn[4], Hn[10];     // full evaluation at the accepted trial point
+    int32_t okn, fresh, stall, status, action, it, nfev, pad_;
+};
+#define CB_FIT_STATE_DOUBLES ((int)((sizeof(FitState) + 7) / 8))
+enum { FIT_GO = 0, FIT_DONE = 1 };
+CB_HD int fit_slab_doubles(int nk) { return warp_slab_doubles(nk, true, CB_FIT_STATE_DOUBLES); }
 
 // Solve B d = -g on the free variables (frozen ones get d = 0) by Cholesky; returns false when the
 // reduced matrix is not positive definite.
@@ -168,6 +119,242 @@ CB_HD bool solve_free(const double *B /*packed*/, const double *g, const bool *f
 
 CB_HD double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
+CB_HD double fit_prior_penalty(const cb_fit_options *o, const double *x) {
+    double c = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (!isnan(o->prior_mu[j])) {
+            const double dl = x[j] - o->prior_mu[j];
+            c += 0.5 * dl * dl / (o->prior_sigma[j] * o->prior_sigma[j]);
+        }
+    return c;
+}
+
+// ---- lane-0 phases ------------------------------------------------------------------------------
+// Start: clip x0 into the bounds (scipy does, _lbfgsb_py.py:359) and into the cosh wall.
+CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const double *x0, double kmax) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { S->lb[j] = o->lb[j]; S->ub[j] = o->ub[j]; }
+    if (kmax > 0.0) {
+        double wall = CB_COSH_OVERFLOW / kmax;
+        while (kmax * wall > CB_COSH_OVERFLOW) wall = nextafter(wall, 0.0);
+        S->ub[2] = fmin(S->ub[2], wall);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S->xt[j] = clampd(x0[j], S->lb[j], S->ub[j]);
+    S->hb = 1e-6 * fmax(1.0, fabs(S->xt[0]));
+    S->pen_t = fit_prior_penalty(o, S->xt);
+    S->fresh = 1; S->stall = 0; S->status = FIT_MAXITER; S->action = FIT_GO; S->it = 0; S->nfev = 0; S->pad_ = 0;
+}
+
+// Make the evaluated trial point the current iterate (first evaluation: B = Gauss-Newton metric).
+CB_NOINLINE_BODY void fit_accept_first(FitState *S) {
+    if (!S->okn) { S->status = FIT_BAD_START; S->action = FIT_DONE; }
+    S->f = S->fn;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { S->x[j] = S->xt[j]; S->g[j] = S->gn[j]; }
+#pragma unroll
+    for (int q = 0; q < 10; ++q) { S->H[q] = S->Hn[q]; S->B[q] = S->Hn[q]; }
+}
+
+// Convergence test on the projected gradient, then the quasi-Newton direction on the free variables.
+CB_NOINLINE_BODY void fit_direction(FitState *S, double gtol) {
+    bool frozen[4];
+    double pgn = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        frozen[j] = (S->x[j] <= S->lb[j] && S->g[j] > 0.0) || (S->x[j] >= S->ub[j] && S->g[j] < 0.0);
+        if (!frozen[j]) pgn = fmax(pgn, fabs(S->g[j]));
+    }
+    if (pgn <= gtol) { S->status = FIT_CONVERGED_PG; S->action = FIT_DONE; return; }
+#ifdef CB_FIT_TRACE
+    printf("it %3d f %.15g pgn %.3e x %.6f %.6f %.6f %.6f fresh %d nfev %d\n", S->it, S->f, pgn, S->x[0], S->x[1],
+           S->x[2], S->x[3], S->fresh, S->nfev);
+#endif
+    double d[4], gd = 0.0;
+    bool have = solve_free(S->B, S->g, frozen, d);
+    if (have) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gd += S->g[j] * d[j];
+        have = (gd < 0.0) && isfinite(gd);
+    }
+    if (!have && !S->fresh) {        // fall back to the Gauss-Newton metric of this point
+#pragma unroll
+        for (int q = 0; q < 10; ++q) S->B[q] = S->H[q];
+        S->fresh = 1;
+        have = solve_free(S->B, S->g, frozen, d);
+        gd = 0.0;
+        if (have) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gd += S->g[j] * d[j];
+            have = (gd < 0.0) && isfinite(gd);
+        }
+    }
+    if (!have) {                      // steepest descent, scaled by the diagonal
+        gd = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double hjj = fmax(S->H[tri(j, j)], 1e-12);
+            d[j] = frozen[j] ? 0.0 : -S->g[j] / hjj;
+            gd += S->g[j] * d[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S->d[j] = d[j];
+    S->gd = gd;
+    // Newton decrement: the model predicts a decrease of -gd/2; below the rounding noise of the
+    // objective no line search can confirm progress, so this is convergence.
+    if (-gd <= 1e-13 * fmax(1.0, fabs(S->f))) { S->status = FIT_CONVERGED_F; S->action = FIT_DONE; }
+}
+
+CB_NOINLINE_BODY void fit_trial(FitState *S, const cb_fit_options *o, double alpha) {
+    double dec = 0.0, move = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double t = clampd(S->x[j] + alpha * S->d[j], S->lb[j], S->ub[j]);
+        S->xt[j] = t;
+        dec += S->g[j] * (t - S->x[j]);
+        move = fmax(move, fabs(t - S->x[j]));
+    }
+    S->dec = dec;
+    S->move = move;
+    S->hb = 1e-6 * fmax(1.0, fabs(S->xt[0]));
+    S->pen_t = fit_prior_penalty(o, S->xt);
+}
+
+// The line search failed: retry once from the Gauss-Newton metric, else give up.
+CB_NOINLINE_BODY void fit_linesearch_failed(FitState *S) {
+    if (!S->fresh) {
+#pragma unroll
+        for (int q = 0; q < 10; ++q) S->B[q] = S->H[q];
+        S->fresh = 1;
+    } else {
+        S->status = FIT_LINESEARCH;
+        S->action = FIT_DONE;
+    }
+}
+
+// BFGS secant update (skipped, i.e. reset to Gauss-Newton, when the curvature condition fails), move
+// to the accepted point, stall test on the relative decrease.
+CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
+    if (!S->okn) { S->status = FIT_LINESEARCH; S->action = FIT_DONE; return; }
+    double s[4], y[4], sy = 0.0, ss = 0.0, yy = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s[j] = S->xt[j] - S->x[j];
+        y[j] = S->gn[j] - S->g[j];
+        sy += s[j] * y[j];
+        ss += s[j] * s[j];
+        yy += y[j] * y[j];
+    }
+    bool updated = false;
+    if (sy > 1e-10 * sqrt(ss * yy) && sy > 0.0) {
+        double Bs[4], sBs = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t += S->B[i <= j ? tri(i, j) : tri(j, i)] * s[j];
+            Bs[i] = t;
+            sBs += t * s[i];
+        }
+        if (sBs > 0.0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = i; j < 4; ++j) S->B[tri(i, j)] += y[i] * y[j] / sy - Bs[i] * Bs[j] / sBs;
+            updated = true;
+            S->fresh = 0;
+        }
+    }
+    if (!updated) {
+#pragma unroll
+        for (int q = 0; q < 10; ++q) S->B[q] = S->Hn[q];
+        S->fresh = 1;
+    }
+    const double fold = S->f;
+    S->f = S->fn;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { S->x[j] = S->xt[j]; S->g[j] = S->gn[j]; }
+#pragma unroll
+    for (int q = 0; q < 10; ++q) S->H[q] = S->Hn[q];
+    S->it += 1;
+    const double rel = (fold - S->f) / fmax(fmax(fabs(fold), fabs(S->f)), 1.0);
+    S->stall = (rel <= ftol) ? S->stall + 1 : 0;
+    if (S->stall >= 3) { S->status = FIT_CONVERGED_F; S->action = FIT_DONE; }
+    else if (S->it >= max_iter) { S->status = FIT_MAXITER; S->action = FIT_DONE; }
+}
+
+// ---- all-lane phases ----------------------------------------------------------------------------
+// Objective, gradient and Gauss-Newton matrix at S->xt from the staged model values
+// (p0, dPhi/ddz at xt; pp, pm at beta +- hb): 15 warp reductions, lane 0 stores the result.
+template <class Ctx>
+CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState *S, const cb_fit_options *o, int lane) {
+    const double hb = S->hb;
+    const double rh = 1.0 / hb, rh2 = 0.5 * rh;
+    double acc[15];
+#pragma unroll
+    for (int q = 0; q < 15; ++q) acc[q] = 0.0;
+    for (int i = lane; i < W.nk; i += cx.team_lanes()) {
+        const double p0 = W.p0[i], pp = W.pp[i], pm = W.pm[i];
+        double J[4];
+        if (isfinite(pp) && isfinite(pm)) J[0] = (pp - pm) * rh2;
+        else if (isfinite(pp)) J[0] = (pp - p0) * rh;
+        else if (isfinite(pm)) J[0] = (p0 - pm) * rh;
+        else J[0] = 0.0;
+        J[1] = -2.0 * W.k[i];
+        J[2] = W.dz[i];
+        J[3] = 1.0;
+        const double r = p0 - W.obs[i];
+        acc[0] = fma(r, r, acc[0]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            acc[1 + a] = fma(r, J[a], acc[1 + a]);
+#pragma unroll
+            for (int b = a; b < 4; ++b) acc[5 + tri(a, b)] = fma(J[a], J[b], acc[5 + tri(a, b)]);
+        }
+    }
+    cx.sync_warp();
+#pragma unroll
+    for (int q = 0; q < 15; ++q) acc[q] = cx.warp_sum(acc[q]);
+    if (lane == 0) {
+        const double f = 0.5 * acc[0];
+        bool ok = isfinite(f);
+#pragma unroll
+        for (int q = 1; q < 15; ++q) ok = ok && isfinite(acc[q]);
+        S->okn = ok ? 1 : 0;
+        if (!ok) {
+            S->fn = CB_BIG_MISFIT;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) S->gn[a] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 10; ++q) S->Hn[q] = 0.0;
+        } else {
+            S->fn = f + S->pen_t;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) S->gn[a] = acc[1 + a];
+#pragma unroll
+            for (int q = 0; q < 10; ++q) S->Hn[q] = acc[5 + q];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                if (!isnan(o->prior_mu[a])) {
+                    const double w = 1.0 / (o->prior_sigma[a] * o->prior_sigma[a]);
+                    S->gn[a] += (S->xt[a] - o->prior_mu[a]) * w;
+                    S->Hn[tri(a, a)] += w;
+                }
+        }
+    }
+    cx.sync_warp();
+}
+
+template <class Ctx>
+CB_BODY bool fit_poll(const Ctx &cx, const FitState *S) {
+    cx.sync_warp();
+    const bool go = S->action == FIT_GO;
+    cx.sync_warp();
+    return go;
+}
+
 template <class Ctx>
 CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     const int tid = cx.tid();
@@ -176,174 +363,76 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     const int64_t w = (int64_t)cx.bid() * P.warps_per_block + warp;
     if (w >= P.nwin) return;     // whole warp leaves together
 
-    // per-warp slab in shared memory: k, ln k, Phi, model values and the order tables
-    WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * warp_slab_doubles(nk, true),
-                                 nk, true);
+    // per-warp slab in shared memory: wavenumber tables, model values, order tables, solver state
+    WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) +
+                                     (int64_t)warp * fit_slab_doubles(nk), nk, true);
     warp_slab_load(cx, W, P.kh, P.phi + w * nk, lane);
+    FitState *S = reinterpret_cast<FitState *>(W.scratch);
+    const cb_fit_options *o = &P.opt;
+    const int max_iter = o->max_iter > 0 ? o->max_iter : 200;
+    const double gtol = o->gtol > 0.0 ? o->gtol : 1e-9;
+    const double ftol = o->ftol > 0.0 ? o->ftol : 1e-15;
 
-    const cb_fit_options &o = P.opt;
-    Priors pr;
-    double lb[4], ub[4], x[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        pr.mu[j] = o.prior_mu[j];
-        pr.sigma[j] = o.prior_sigma[j];
-        lb[j] = o.lb[j];
-        ub[j] = o.ub[j];
-        const double s = P.x0_dev ? P.x0_dev[w * 4 + j] : o.x0[j];
-        x[j] = clampd(s, lb[j], ub[j]);     // scipy clips x0 into the bounds (_lbfgsb_py.py:359)
-    }
-    const int max_iter = o.max_iter > 0 ? o.max_iter : 200;
-    const double gtol = o.gtol > 0.0 ? o.gtol : 1e-9;
-    const double ftol = o.ftol > 0.0 ? o.ftol : 1e-15;
+    if (lane == 0) fit_init(S, o, P.x0_dev ? P.x0_dev + w * 4 : o->x0, W.sorted ? W.kmax : 0.0);
+    cx.sync_warp();
 
-    FitEval ev;
-    fit_eval_full(cx, W, x, pr, lane, ev);
-    int status = FIT_MAXITER, it = 0, nfev = 3;
-    if (!ev.ok) {
-        status = FIT_BAD_START;
-    } else {
-        double B[10];
-#pragma unroll
-        for (int q = 0; q < 10; ++q) B[q] = ev.H[q];
-        bool fresh = true;      // B is the Gauss-Newton matrix of the current point
-        int stall = 0;
-        for (it = 0; it < max_iter; ++it) {
-            bool frozen[4];
-            double pgn = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                frozen[j] = (x[j] <= lb[j] && ev.g[j] > 0.0) || (x[j] >= ub[j] && ev.g[j] < 0.0);
-                if (!frozen[j]) pgn = fmax(pgn, fabs(ev.g[j]));
-            }
-            if (pgn <= gtol) { status = FIT_CONVERGED_PG; break; }
-#ifdef CB_FIT_TRACE
-            if (lane == 0) printf("it %3d f %.15g pgn %.3e x %.6f %.6f %.6f %.6f fresh %d nfev %d\n", it, ev.f, pgn, x[0], x[1], x[2], x[3], (int)fresh, nfev);
-#endif
+    // full evaluation at the start
+    model_coefs_warp(cx, W, S->xt, S->hb, 0, 3, lane);
+    model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
+    model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
+    model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
+    fit_reduce_full(cx, W, S, o, lane);
+    if (lane == 0) { fit_accept_first(S); S->nfev = 3; }
 
-            double d[4];
-            bool have = solve_free(B, ev.g, frozen, d);
-            double gd = 0.0;
-            if (have) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) gd += ev.g[j] * d[j];
-                have = (gd < 0.0) && isfinite(gd);
-            }
-            if (!have && !fresh) {       // fall back to the Gauss-Newton metric of this point
-#pragma unroll
-                for (int q = 0; q < 10; ++q) B[q] = ev.H[q];
-                fresh = true;
-                have = solve_free(B, ev.g, frozen, d);
-                gd = 0.0;
-                if (have) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) gd += ev.g[j] * d[j];
-                    have = (gd < 0.0) && isfinite(gd);
-                }
-            }
-            if (!have) {                  // steepest descent, scaled by the diagonal
-                gd = 0.0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double hjj = fmax(ev.H[tri(j, j)], 1e-12);
-                    d[j] = frozen[j] ? 0.0 : -ev.g[j] / hjj;
-                    gd += ev.g[j] * d[j];
-                }
-            }
+    // S->action is written by lane 0 only; every read is fenced by a barrier on both sides so that
+    // lane 0 cannot change it again before all lanes have seen the same value
+    while (fit_poll(cx, S)) {
+        if (lane == 0) fit_direction(S, gtol);
+        if (!fit_poll(cx, S)) break;
 
-            // Newton decrement: the model predicts a decrease of -gd/2; below the rounding noise of
-            // the objective no line search can confirm progress, so this is convergence.
-            if (-gd <= 1e-13 * fmax(1.0, fabs(ev.f))) { status = FIT_CONVERGED_F; break; }
-
-            // projected Armijo backtracking
-            double alpha = 1.0, xt[4], ft = CB_BIG_MISFIT;
-            bool accepted = false;
-            for (int ls = 0; ls < 40; ++ls) {
-                double dec = 0.0, move = 0.0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    xt[j] = clampd(x[j] + alpha * d[j], lb[j], ub[j]);
-                    dec += ev.g[j] * (xt[j] - x[j]);
-                    move = fmax(move, fabs(xt[j] - x[j]));
-                }
-                if (move == 0.0) break;
-                ft = misfit_slab(cx, W, xt, pr, lane);
-                ++nfev;
-                if (ft <= ev.f + 1e-4 * dec && ft < 1e98) { accepted = true; break; }
-                if (ft >= 1e98) alpha *= 0.25;
-                else {
-                    // minimiser of the quadratic through f(0), f'(0), f(alpha)
-                    const double den = 2.0 * (ft - ev.f - dec);
-                    double an = den > 0.0 ? -dec * alpha / den : 0.5 * alpha;
-                    alpha = clampd(an, 0.1 * alpha, 0.5 * alpha);
-                }
+        // projected Armijo backtracking
+        const double f0 = S->f;
+        double alpha = 1.0;
+        bool accepted = false;
+        int nls = 0;
+        for (int ls = 0; ls < 40; ++ls) {
+            if (lane == 0) fit_trial(S, o, alpha);
+            cx.sync_warp();
+            const double dec = S->dec;
+            if (S->move == 0.0) break;
+            model_coefs_warp(cx, W, S->xt, 0.0, 0, 1, lane);
+            model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
+            ++nls;
+            double ft = slab_half_ssq(cx, W, lane);
+            ft = isfinite(ft) ? ft + S->pen_t : CB_BIG_MISFIT;
+            if (ft <= f0 + 1e-4 * dec && ft < 1e98) { accepted = true; break; }
+            if (ft >= 1e98) alpha *= 0.25;
+            else {
+                // minimiser of the quadratic through f(0), f'(0), f(alpha)
+                const double den = 2.0 * (ft - f0 - dec);
+                const double an = den > 0.0 ? -dec * alpha / den : 0.5 * alpha;
+                alpha = clampd(an, 0.1 * alpha, 0.5 * alpha);
             }
-            if (!accepted) {
-                if (!fresh) {             // retry once from the Gauss-Newton metric
-#pragma unroll
-                    for (int q = 0; q < 10; ++q) B[q] = ev.H[q];
-                    fresh = true;
-                    continue;
-                }
-                status = FIT_LINESEARCH;
-                break;
-            }
-
-            FitEval en;
-            fit_eval_full(cx, W, xt, pr, lane, en);
-            nfev += 3;
-            if (!en.ok) { status = FIT_LINESEARCH; break; }
-            double s[4], y[4], sy = 0.0, ss = 0.0, yy = 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                s[j] = xt[j] - x[j];
-                y[j] = en.g[j] - ev.g[j];
-                sy += s[j] * y[j];
-                ss += s[j] * s[j];
-                yy += y[j] * y[j];
-            }
-            // BFGS secant update, skipped (reset to Gauss-Newton) when the curvature condition fails
-            bool updated = false;
-            if (sy > 1e-10 * sqrt(ss * yy) && sy > 0.0) {
-                double Bs[4], sBs = 0.0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) t += B[i <= j ? tri(i, j) : tri(j, i)] * s[j];
-                    Bs[i] = t;
-                    sBs += t * s[i];
-                }
-                if (sBs > 0.0) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = i; j < 4; ++j)
-                            B[tri(i, j)] += y[i] * y[j] / sy - Bs[i] * Bs[j] / sBs;
-                    updated = true;
-                    fresh = false;
-                }
-            }
-            if (!updated) {
-#pragma unroll
-                for (int q = 0; q < 10; ++q) B[q] = en.H[q];
-                fresh = true;
-            }
-            const double fold = ev.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = xt[j];
-            ev = en;
-            const double rel = (fold - ev.f) / fmax(fmax(fabs(fold), fabs(ev.f)), 1.0);
-            stall = (rel <= ftol) ? stall + 1 : 0;
-            if (stall >= 3) { status = FIT_CONVERGED_F; ++it; break; }
+            cx.sync_warp();
         }
+        if (!accepted) {
+            cx.sync_warp();
+            if (lane == 0) { S->nfev += nls; fit_linesearch_failed(S); }
+            continue;
+        }
+        // derivatives at the accepted point: beta +- hb (p0 and dPhi/ddz are already staged)
+        model_coefs_warp(cx, W, S->xt, S->hb, 1, 2, lane);
+        model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
+        model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
+        fit_reduce_full(cx, W, S, o, lane);
+        if (lane == 0) { S->nfev += nls + 2; fit_update(S, ftol, max_iter); }
     }
     if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) P.x_out[w * 4 + j] = x[j];
-        if (P.f_out) P.f_out[w] = ev.f;
-        if (P.niter) P.niter[w] = it;
-        if (P.status) P.status[w] = status;
-        if (P.nfev) P.nfev[w] = nfev;
+        for (int j = 0; j < 4; ++j) P.x_out[w * 4 + j] = S->x[j];
+        if (P.f_out) P.f_out[w] = S->f;
+        if (P.niter) P.niter[w] = S->it;
+        if (P.status) P.status[w] = S->status;
+        if (P.nfev) P.nfev[w] = S->nfev;
     }
 }

@@ -6,7 +6,11 @@
 
 extern __shared__ double cb_dyn_smem_d[];
 
-#define CB_FIT_WARPS 4      // warps (= windows) per CTA in the per-warp kernels
+// One warp (= one window / chain) per CTA: fit and chain lengths vary between windows, and with
+// single-warp CTAs the hardware block scheduler balances them; 16 CTAs per SM keep 4 warps per
+// scheduler in flight to hide the FP64 dependency chains of the Bessel recurrences.
+#define CB_FIT_WARPS 1
+#define CB_FIT_CTAS_PER_SM 16
 
 __global__ void __launch_bounds__(256) besselk_kernel(const double *nu, const double *x, int64_t n, double *out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -47,7 +51,7 @@ struct MisfitParams {
     double *out;
 };
 
-__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) misfit_kernel(const __grid_constant__ MisfitParams P) {
+__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) misfit_kernel(const __grid_constant__ MisfitParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * CB_FIT_WARPS + warp;
@@ -60,12 +64,12 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) misfit_kernel(const __
     if (lane == 0) P.out[row] = f;
 }
 
-__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) fit_kernel(const __grid_constant__ FitParams P) {
+__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) fit_kernel(const __grid_constant__ FitParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
     fit_body(cx, P);
 }
 
-__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP) mh_kernel(const __grid_constant__ MhParams P) {
+__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) mh_kernel(const __grid_constant__ MhParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
     mh_body(cx, P);
 }
@@ -113,7 +117,7 @@ int cb_bouligand_points(const double *kh_dev, const double *params_dev, int64_t 
 
 static int per_warp_launch_shape(int nk, int64_t nwin, bool fit, int *grid, size_t *smem) {
     CB_REQUIRE(nk > 0 && nk <= 512, "nk must be in [1, 512]");
-    *smem = (size_t)CB_FIT_WARPS * (size_t)warp_slab_doubles(nk, fit) * sizeof(double);
+    *smem = (size_t)CB_FIT_WARPS * (size_t)(fit ? fit_slab_doubles(nk) : warp_slab_doubles(nk, false)) * sizeof(double);
     int64_t g = (nwin + CB_FIT_WARPS - 1) / CB_FIT_WARPS;
     CB_REQUIRE(g <= 2147483647LL, "too many windows for one launch");
     *grid = (int)g;

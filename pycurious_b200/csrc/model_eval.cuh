@@ -1,8 +1,9 @@
 // Warp-cooperative evaluation of the Bouligand model over all wavenumbers of one window.
-// This is the hot loop of the fit and MCMC kernels (pycurious/optimise.py:223 executed ~70 x per fit,
-// 101,000 x per chain).  Compared with calling bouligand_point() per lane it
+// This is the hot loop of the fit and MCMC kernels (pycurious/optimise.py:223 executed ~50 x per fit,
+// 101,000 x per chain).  One warp owns one window; its shared-memory slab holds the window's
+// wavenumber tables, the model outputs and the per-evaluation order tables.
 //
-//   * splits the (ascending) wavenumbers into three contiguous classes by x = k dz, so that a
+//   * the (ascending) wavenumbers are split into three contiguous classes by x = k dz, so that a
 //     warp pass never mixes code paths:
 //       x <= 2          Temme's series (few points)
 //       2 < x < x_skip  K_mu, K_mu+1 by Miller's backward recurrence on Temme's three-term
@@ -14,66 +15,149 @@
 //       x >= x_skip     the K term is below 2^-60 of the cosh term, i.e. it cannot change the
 //                       rounded bracket: Phi = C - 2 k zt - (beta-1) ln k + ln(lead Gamma(nu)/4),
 //                       dPhi/ddz = 0 (cosh overflow at x > 710.47 still gives +inf like numpy)
-//   * hoists everything that depends on the order only into per-evaluation tables in shared
-//     memory, built lane-parallel: C_n (prefix product by warp shuffles), 1/(i-mu), 1/(i+mu), 1/i
+//   * the bracket is evaluated in the scaled form  e^-x [..] = Gamma(nu)/4 (1 + e^-2x) - e^-x K hx,
+//     so the "-x + log(bracket)" pair of grid.py:598 collapses to one log and nothing overflows
+//   * everything that depends on the order only lives in per-evaluation tables in shared memory,
+//     built lane-parallel: ModelCoef (lane o computes the coefficients of parameter vector o),
+//     C_n / a_n (prefix product by warp shuffles), 1/(j-mu), 1/(j+mu)
+//   * everything that depends on the wavenumber only (ln k, 1/k, sqrt(pi/2k)) is tabulated once per
+//     window, so the per-point work has no division by x and no sqrt
 //
 // Falls back to the per-point generic path (bouligand.cuh) for unsorted k, dz <= 0, beta < 0,
 // very large orders or non-finite parameters, where the reference's nan/inf pattern matters more
-// than speed.
+// than speed.  The heavy functions are deliberately NOT inlined on the device: the first version
+// of the fit kernel inlined them at every call site, grew to 770 KB of SASS and spent 75 % of its
+// issue slots waiting on the instruction cache (profiles/r01_fit_icache.md).
 #pragma once
 #include "bouligand.cuh"
 
-#define CB_MILLER_NMAX 97
+#define CB_MILLER_NMAX 97                     /* tables hold n = 0..97 */
 #define CB_TEMME_TAB 28
 #define CB_SKIP_LOG 43.0                      /* > 60 ln 2 + ln(4 sqrt(pi/4)) */
 #define CB_COSH_OVERFLOW 710.4758600739439    /* np.cosh overflows above this */
+#define CB_MAX_ORDERS 3                       /* parameter vectors evaluated per call group: x, x+h e_beta, x-h e_beta */
 
-struct WarpSlab {          // views into one warp's shared-memory slab
-    double *k, *logk, *obs;        // [nk] wavenumber, ln k, observed Phi
-    double *p0, *pp, *pm, *dz;     // [nk] model values (p0) and, for the fit, Phi(beta+-h), dPhi/ddz
-    double *C;                     // [CB_MILLER_NMAX + 1]
-    double *rp, *rq, *ri;          // [CB_TEMME_TAB]
-    int nk;
-    bool sorted;
+#if defined(__CUDACC__) && !defined(CB_EMU)
+#define CB_NOINLINE_BODY __device__ __noinline__
+#else
+#define CB_NOINLINE_BODY inline
+#endif
+
+// ModelCoef plus what the fast path needs, one per parameter vector, in shared memory.
+struct EvalCoef {
+    ModelCoef m;
+    double a1;          // 1/4 - mu^2
+    double rdz;         // 1/dz
+    double rsdz;        // 1/sqrt(dz)
+    double lgnu;        // ln Gamma(nu)
+    double lgc;         // ln(lead Gamma(nu)/4)
+    double hp, hq;      // 1/(2 Gamma(1+mu)), 1/(2 Gamma(1-mu))
+    int32_t fast;       // 1: the class-split path applies
+    int32_t pad_;
 };
 
-CB_HD int warp_slab_doubles(int nk, bool fit) {
-    return (fit ? 7 : 4) * nk + (CB_MILLER_NMAX + 1) + 3 * CB_TEMME_TAB;
+struct WarpSlab {          // views into one warp's shared-memory slab
+    double *k, *logk, *rk, *sq, *obs;   // [nk] k, ln k, 1/k, sqrt(pi/(2k)), observed Phi
+    double *p0, *pp, *pm, *dz;          // [nk] model values (p0) and, for the fit, Phi(beta+-h), dPhi/ddz
+    double *rn;                         // [CB_MILLER_NMAX + 1] 1/n
+    double2 *CA;                        // [CB_MILLER_NMAX + 1] (C_n, a_{n+1}) of the order being evaluated
+    double2 *rpq;                       // [CB_TEMME_TAB] (1/(j-mu), 1/(j+mu))
+    EvalCoef *coef;                     // [CB_MAX_ORDERS]
+    double *scratch;                    // solver state (fit) behind the tables
+    int nk;
+    bool sorted;
+    double kmax;
+};
+
+#define CB_SLAB_COEF_DOUBLES ((int)((sizeof(EvalCoef) + 7) / 8))
+
+CB_HD int warp_slab_doubles(int nk, bool fit, int scratch_doubles = 0) {
+    int n = (fit ? 9 : 6) * nk + (CB_MILLER_NMAX + 1) + 2 * (CB_MILLER_NMAX + 1) + 2 * CB_TEMME_TAB +
+            CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES + scratch_doubles;
+    return (n + 1) & ~1;      // keep every slab 16-byte aligned
 }
 
 CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit) {
     WarpSlab W;
     W.nk = nk;
-    W.k = base; W.logk = base + nk; W.obs = base + 2 * nk; W.p0 = base + 3 * nk;
-    double *t = base + 4 * nk;
+    double *t = base;
+    W.CA = reinterpret_cast<double2 *>(t); t += 2 * (CB_MILLER_NMAX + 1);
+    W.rpq = reinterpret_cast<double2 *>(t); t += 2 * CB_TEMME_TAB;
+    W.coef = reinterpret_cast<EvalCoef *>(t); t += CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES;
+    W.rn = t; t += CB_MILLER_NMAX + 1;
+    W.k = t; W.logk = t + nk; W.rk = t + 2 * nk; W.sq = t + 3 * nk; W.obs = t + 4 * nk; W.p0 = t + 5 * nk;
+    t += 6 * nk;
     if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; t += 3 * nk; }
     else { W.pp = W.pm = W.dz = nullptr; }
-    W.C = t; W.rp = t + CB_MILLER_NMAX + 1; W.rq = W.rp + CB_TEMME_TAB; W.ri = W.rq + CB_TEMME_TAB;
+    W.scratch = t;
     W.sorted = false;
+    W.kmax = 0.0;
     return W;
 }
 
-// Stage k, ln k and the observed spectrum; detect ascending k.
+// Stage the per-window tables; detect ascending positive k.
 template <class Ctx>
 CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *kh, const double *phi_row, int lane) {
     const int L = cx.team_lanes();
     bool asc = true;
+    double kmax = 0.0;
     for (int i = lane; i < W.nk; i += L) {
         const double k = kh[i];
         W.k[i] = k;
         W.logk[i] = log(k);
+        W.rk[i] = 1.0 / k;
+        W.sq[i] = sqrt(0.5 * CB_PI / k);
         W.obs[i] = phi_row[i];
         if (i + 1 < W.nk && !(kh[i + 1] > k)) asc = false;
         if (!(k > 0.0)) asc = false;
+        kmax = fmax(kmax, k);
     }
+    for (int n = lane; n <= CB_MILLER_NMAX; n += L) W.rn[n] = n ? 1.0 / (double)n : 0.0;
+    for (int o = 16; o > 0; o >>= 1) kmax = fmax(kmax, cx.shfl_xor(kmax, o));
+    W.kmax = kmax;
     W.sorted = cx.all(asc);
     cx.sync_warp();
 }
 
-// K_nu, K_nu-1 from K_mu, K_mu+1 (nl >= 1), then the model value and d/ddz.
-CB_HD double finish_point(const ModelCoef &m, double k, double logk, double x, double invx, double emx,
-                          double kmu, double kmu1, double *ddz) {
-    double a = kmu, b = kmu1;
+// Coefficients of `count` parameter vectors x + off[idx] e_beta, idx = first .. first+count-1, with
+// off = (0, +hb, -hb): lane l computes vector first+l (the lanes run the same code on different data).
+template <class Ctx>
+CB_NOINLINE_BODY void model_coefs_warp(const Ctx &cx, const WarpSlab &W, const double *x, double hb, int first,
+                                       int count, int lane) {
+    const int L = cx.team_lanes();
+    for (int l = lane; l < count; l += L) {
+        const int idx = first + l;
+        const double beta = x[0] + (idx == 1 ? hb : (idx == 2 ? -hb : 0.0));
+        EvalCoef e;
+        e.m = model_coef(beta, x[1], x[2], x[3]);
+        const ModelCoef &m = e.m;
+        e.a1 = 0.25 - m.ord.mu * m.ord.mu;
+        e.rdz = 1.0 / m.dz;
+        e.rsdz = 1.0 / sqrt(m.dz);
+        e.lgnu = log(m.gnu);
+        e.lgc = log(m.lead * m.gnu * 0.25);
+        e.hp = 0.5 / m.ord.gampl;
+        e.hq = 0.5 / m.ord.gammi;
+        e.fast = (m.dz > 0.0 && m.dz < 1e300 && m.nu >= 0.5 && m.nu <= 8.5 && isfinite(m.zt) && isfinite(m.C) &&
+                  m.gnu > 0.0 && m.lead > 0.0 && isfinite(m.gnu) && isfinite(m.lead)) ? 1 : 0;
+        e.pad_ = 0;
+        W.coef[idx] = e;
+    }
+    cx.sync_warp();
+}
+
+// Reference-order arithmetic for one point (the slow, always-valid path).
+CB_NOINLINE_BODY double generic_point(const ModelCoef *m, double k, double logk, double *ddz) {
+    if (ddz) return bouligand_point_ddz(*m, k, logk, *ddz);
+    return bouligand_point(*m, k, logk);
+}
+
+// K_nu e^-x, K_nu-1 e^-x from K_mu e^-x, K_mu+1 e^-x (nl >= 1), then the model value and d/ddz.
+//   e2 = e^-2x;  bracket e^-x = Gamma(nu)/4 (1 + e2) - hx (K_nu e^-x)
+CB_HD double finish_point(const EvalCoef &e, double k, double logk, double invx, double e2, double kmuE, double kmu1E,
+                          double *ddz) {
+    const ModelCoef &m = e.m;
+    double a = kmuE, b = kmu1E;
     const double tox = 2.0 * invx;
     for (int j = 1; j < m.ord.nl; ++j) {
         const double c = fma((m.ord.mu + (double)j) * tox, b, a);
@@ -81,95 +165,114 @@ CB_HD double finish_point(const ModelCoef &m, double k, double logk, double x, d
         b = c;
     }
     const double hx = exp(m.nu * (logk + m.lhalfdz));
-    const double ex = 1.0 / emx;
-    const double ch = 0.5 * (ex + emx), sh = 0.5 * (ex - emx);
-    const double bracket = 0.5 * ch * m.gnu - b * hx;
-    if (ddz) *ddz = -k + k * (0.5 * sh * m.gnu + hx * a) / bracket;
-    return m.C - 2.0 * k * m.zt - (m.beta - 1.0) * logk - x + log(m.lead * bracket);
+    const double qg = 0.25 * m.gnu;
+    const double br = fma(qg, 1.0 + e2, -b * hx);
+    if (ddz) *ddz = k * (fma(qg, 1.0 - e2, hx * a) / br - 1.0);
+    return fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * logk + log(m.lead * br);
 }
 
-// Phi(k_i) for every wavenumber of the slab -> out_phi[i] (and dPhi/ddz -> out_ddz[i] if not NULL).
+// Phi(k_i) of parameter vector `idx` (coefficients prepared by model_coefs_warp) for every
+// wavenumber of the slab -> out_phi[i] (and dPhi/ddz -> out_ddz[i] if not NULL).
 template <class Ctx>
-CB_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, const double *x, int lane, double *out_phi,
-                             double *out_ddz) {
-    const ModelCoef m = model_coef(x[0], x[1], x[2], x[3]);
+CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int lane, double *out_phi,
+                                      double *out_ddz) {
+    const EvalCoef &e = W.coef[idx];
+    const ModelCoef &m = e.m;
     const int nk = W.nk, L = cx.team_lanes();
-    const bool fast = W.sorted && m.dz > 0.0 && m.dz < 1e300 && m.nu >= 0.5 && m.nu <= 8.5 &&
-                      isfinite(m.zt) && isfinite(m.C) && m.gnu > 0.0 && m.lead > 0.0 && isfinite(m.gnu) &&
-                      isfinite(m.lead);
-    if (!fast) {                       // generic per-point path, reference nan/inf semantics
-        for (int i = lane; i < nk; i += L) {
-            if (out_ddz) out_phi[i] = bouligand_point_ddz(m, W.k[i], W.logk[i], out_ddz[i]);
-            else out_phi[i] = bouligand_point(m, W.k[i], W.logk[i]);
-        }
+    if (!(W.sorted && e.fast)) {                       // generic per-point path, reference nan/inf semantics
+        for (int i = lane; i < nk; i += L)
+            out_phi[i] = generic_point(&m, W.k[i], W.logk[i], out_ddz ? out_ddz + i : nullptr);
         cx.sync_warp();
         return;
     }
-    const double mu = m.ord.mu, a1 = 0.25 - mu * mu;
+    const double mu = m.ord.mu, a1 = e.a1, dz = m.dz;
 
     // ---- classes: [0,nT) Temme, [nT,nS) Miller, [nS,nk) K negligible ---------------------------
-    const double lgnu = log(m.gnu);
     int lastT = -1, lastC = -1;
     for (int i = lane; i < nk; i += L) {
-        const double xi = W.k[i] * m.dz;
+        const double xi = W.k[i] * dz;
         if (xi <= 2.0) lastT = i;
-        const bool skip = xi > 2.0 && (2.0 * xi - m.nu * (W.logk[i] + m.lhalfdz) + lgnu > CB_SKIP_LOG);
+        const bool skip = xi > 2.0 && (2.0 * xi - m.nu * (W.logk[i] + m.lhalfdz) + e.lgnu > CB_SKIP_LOG);
         if (!skip) lastC = i;
     }
     const int nT = cx.warp_max_i(lastT) + 1;
     int nS = cx.warp_max_i(lastC) + 1;
     if (nS < nT) nS = nT;
 
-    // ---- order-only tables, built lane-parallel ----------------------------------------------------
-    if (nS > nT) {                     // C_0 = 1, C_1 = a1, C_n = C_{n-1} (a1 + n(n-1)) / n
-        if (lane == 0) { W.C[0] = 1.0; W.C[1] = a1; }
-        double carry = a1;
-        for (int n0 = 2; n0 <= CB_MILLER_NMAX; n0 += L) {
-            const int n = n0 + lane;
-            double g = (n <= CB_MILLER_NMAX) ? (a1 + (double)n * (double)(n - 1)) / (double)n : 1.0;
-            for (int d = 1; d < L; d <<= 1) {
-                const double t = cx.shfl_up(g, d);
-                if (lane >= d) g *= t;
+    // ---- order-only tables, built lane-parallel ------------------------------------------------
+    if (nS > nT) {
+        // C_0 = 1, C_1 = a1, C_n = C_{n-1} (a1 + n(n-1)) / n;  CA[n].y = a_{n+1} = -(a1 + n(n+1))
+        // lane l owns n = 3l+2 .. 3l+4; local prefix, product scan over lanes, expand
+        double q[3];
+        double run = 1.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int n = 3 * lane + 2 + j;
+            const double g = n <= CB_MILLER_NMAX ? fma(a1, W.rn[n], (double)(n - 1)) : 1.0;
+            run *= g;
+            q[j] = run;
+        }
+        double incl = run;
+        for (int d = 1; d < L; d <<= 1) {
+            const double t = cx.shfl_up(incl, d);
+            if (lane >= d) incl *= t;
+        }
+        double excl = cx.shfl_up(incl, 1);
+        if (lane == 0) excl = 1.0;
+        if (L == 1) {                                   // serial emulation: one lane builds the whole table
+            double c = a1;
+            W.CA[0] = make_double2(1.0, -a1);
+            W.CA[1] = make_double2(a1, -(a1 + 2.0));
+            for (int n = 2; n <= CB_MILLER_NMAX; ++n) {
+                c *= fma(a1, W.rn[n], (double)(n - 1));
+                W.CA[n] = make_double2(c, -(a1 + (double)n * (double)(n + 1)));
             }
-            g *= carry;
-            if (n <= CB_MILLER_NMAX) W.C[n] = g;
-            carry = cx.shfl(g, L - 1);
+        } else {
+            const double base = a1 * excl;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n = 3 * lane + 2 + j;
+                if (n <= CB_MILLER_NMAX) W.CA[n] = make_double2(base * q[j], -(a1 + (double)n * (double)(n + 1)));
+            }
+            if (lane == 0) {
+                W.CA[0] = make_double2(1.0, -a1);
+                W.CA[1] = make_double2(a1, -(a1 + 2.0));
+            }
         }
     }
     if (nT > 0) {
-        for (int i = 1 + lane; i < CB_TEMME_TAB; i += L) {
-            W.rp[i] = 1.0 / ((double)i - mu);
-            W.rq[i] = 1.0 / ((double)i + mu);
-            W.ri[i] = 1.0 / (double)i;
-        }
+        for (int j = 1 + lane; j < CB_TEMME_TAB; j += L)
+            W.rpq[j] = make_double2(1.0 / ((double)j - mu), 1.0 / ((double)j + mu));
     }
     cx.sync_warp();
 
     // ---- x <= 2: Temme's series ---------------------------------------------------------------
-    const double hp = 0.5 / m.ord.gampl, hq = 0.5 / m.ord.gammi;
     for (int i = lane; i < nT; i += L) {
-        const double k = W.k[i], lk = W.logk[i], xi = k * m.dz;
+        const double k = W.k[i], lk = W.logk[i], xi = k * dz;
         const double d = -(lk + m.lhalfdz);             // ln(2/x)
         const double sg = mu * d;
-        const double e = exp(sg), ei = 1.0 / e;
-        const double shc = fabs(sg) < 1e-4 ? 1.0 + sg * sg * (1.0 / 6.0) : 0.5 * (e - ei) / sg;
-        double ff = m.ord.sinc * (m.ord.gam1 * 0.5 * (e + ei) + m.ord.gam2 * shc * d);
-        double p = hp * e, q = hq * ei, c = 1.0;
+        const double ee = exp(sg), ei = 1.0 / ee;
+        const double shc = fabs(sg) < 1e-4 ? 1.0 + sg * sg * (1.0 / 6.0) : 0.5 * (ee - ei) / sg;
+        double ff = m.ord.sinc * (m.ord.gam1 * 0.5 * (ee + ei) + m.ord.gam2 * shc * d);
+        double p = e.hp * ee, q = e.hq * ei, c = 1.0;
         const double x2 = 0.5 * xi, dd = x2 * x2;
         double sum = ff, sum1 = p;
         for (int j = 1; j < CB_TEMME_TAB; ++j) {
-            const double fj = (double)j, rpj = W.rp[j], rqj = W.rq[j];
-            ff = (fj * ff + p + q) * (rpj * rqj);
-            c *= dd * W.ri[j];
-            p *= rpj;
-            q *= rqj;
+            const double fj = (double)j;
+            const double2 r = W.rpq[j];
+            ff = (fj * ff + p + q) * (r.x * r.y);
+            c *= dd * W.rn[j];
+            p *= r.x;
+            q *= r.y;
             const double del = c * ff;
             sum += del;
             sum1 = fma(c, p - fj * ff, sum1);
             if (fabs(del) < fabs(sum) * CB_KNU_EPS) break;
         }
-        const double invx = 1.0 / xi;
-        out_phi[i] = finish_point(m, k, lk, xi, invx, exp(-xi), sum, sum1 * (2.0 * invx), out_ddz ? out_ddz + i : nullptr);
+        const double invx = W.rk[i] * e.rdz;
+        const double emx = exp(-xi);
+        out_phi[i] = finish_point(e, k, lk, invx, emx * emx, sum * emx, sum1 * (2.0 * invx) * emx,
+                                  out_ddz ? out_ddz + i : nullptr);
     }
 
     // ---- 2 < x < x_skip: Miller backward recurrence, uniform trip count per pass -------------------
@@ -177,26 +280,25 @@ CB_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, const double *x, 
         const int i = base + lane;
         const bool act = i < nS;
         const int ii = act ? i : nS - 1;
-        const double k = W.k[ii], lk = W.logk[ii], xi = k * m.dz;
-        const double xmin = W.k[base] * m.dz;          // smallest x of this pass (k ascending)
-        int N = (int)(12.0 + 140.0 / xmin) + 1;
+        const double k = W.k[ii], lk = W.logk[ii], xi = k * dz;
+        int N = (int)(12.0 + 140.0 * (W.rk[base] * e.rdz)) + 1;     // from the smallest x of this pass (k ascending)
         if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
-        double yp = 0.0, y = 1.0, S = W.C[N];
+        double yp = 0.0, y = 1.0, S = W.CA[N].x;
         double bn = 2.0 * ((double)N + xi);
-        double an1 = -(a1 + (double)(N + 1) * (double)N);
         for (int n = N; n >= 1; --n) {
-            const double ym = fma(bn, y, an1 * yp);
+            const double ym = fma(bn, y, W.CA[n].y * yp);
             yp = y;
             y = ym;
-            S = fma(W.C[n - 1], y, S);
+            S = fma(W.CA[n - 1].x, y, S);
             bn -= 2.0;
-            an1 += 2.0 * (double)n;
         }
-        const double invx = 1.0 / xi, emx = exp(-xi);
-        const double kmu = sqrt(CB_PI * 0.5 * invx) * emx * y / S;
-        const double kmu1 = kmu * (mu + xi + 0.5 - a1 * yp / y) * invx;
+        const double invx = W.rk[ii] * e.rdz;
+        const double cS = W.sq[ii] * e.rsdz / S;                   // sqrt(pi/(2x)) / S
+        const double kmuE = cS * y;                                 // K_mu e^x
+        const double kmu1E = cS * fma(mu + xi + 0.5, y, -a1 * yp) * invx;
+        const double e2 = exp(-2.0 * xi);
         double dv;
-        const double ph = finish_point(m, k, lk, xi, invx, emx, kmu, kmu1, out_ddz ? &dv : nullptr);
+        const double ph = finish_point(e, k, lk, invx, e2, kmuE * e2, kmu1E * e2, out_ddz ? &dv : nullptr);
         if (act) {
             out_phi[i] = ph;
             if (out_ddz) out_ddz[i] = dv;
@@ -204,27 +306,33 @@ CB_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, const double *x, 
     }
 
     // ---- x >= x_skip: the Bessel term cannot change the rounded bracket ----------------------------
-    const double lgc = log(m.lead * m.gnu * 0.25);
     for (int i = nS + lane; i < nk; i += L) {
         const double k = W.k[i];
-        const bool over = k * m.dz > CB_COSH_OVERFLOW;
-        out_phi[i] = over ? INFINITY : fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * W.logk[i] + lgc;
+        const bool over = k * dz > CB_COSH_OVERFLOW;
+        out_phi[i] = over ? INFINITY : fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * W.logk[i] + e.lgc;
         if (out_ddz) out_ddz[i] = over ? NAN : 0.0;
     }
     cx.sync_warp();
 }
 
-// min_func for the staged spectrum (optimise.py:220-230).
+// 0.5 sum (p0 - obs)^2 over the slab (every lane returns the total).
 template <class Ctx>
-CB_BODY double misfit_slab(const Ctx &cx, const WarpSlab &W, const double *x, const Priors &pr, int lane) {
-    model_eval_warp(cx, W, x, lane, W.p0, nullptr);
+CB_BODY double slab_half_ssq(const Ctx &cx, const WarpSlab &W, int lane) {
     double acc = 0.0;
     for (int i = lane; i < W.nk; i += cx.team_lanes()) {
         const double r = W.p0[i] - W.obs[i];
         acc = fma(r, r, acc);
     }
+    return 0.5 * cx.warp_sum(acc);
+}
+
+// min_func for the staged spectrum (optimise.py:220-230).
+template <class Ctx>
+CB_BODY double misfit_slab(const Ctx &cx, const WarpSlab &W, const double *x, const Priors &pr, int lane) {
+    model_coefs_warp(cx, W, x, 0.0, 0, 1, lane);
+    model_eval_warp(cx, W, 0, lane, W.p0, nullptr);
+    const double f = slab_half_ssq(cx, W, lane);
     cx.sync_warp();
-    const double f = 0.5 * cx.warp_sum(acc);
     if (!isfinite(f)) return CB_BIG_MISFIT;
     return f + prior_penalty(pr, x);
 }

@@ -167,14 +167,14 @@ int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_
     P.x_out = x_out; P.f_out = f_out; P.niter = niter; P.status = status; P.nfev = nfev;
     if (mode == 0) {
         P.warps_per_block = 1;
-        std::vector<double> sm(warp_slab_doubles(nk, true));
+        std::vector<double> sm(fit_slab_doubles(nk));
         for (int64_t w = 0; w < nwin; ++w) {
             SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
             fit_body(cx, P);
         }
     } else {
         P.warps_per_block = 2;
-        emu_launch((int)((nwin + 1) / 2), 64, 2 * warp_slab_doubles(nk, true) * sizeof(double), [&](const HostCtx &cx) { fit_body(cx, P); });
+        emu_launch((int)((nwin + 1) / 2), 64, 2 * fit_slab_doubles(nk) * sizeof(double), [&](const HostCtx &cx) { fit_body(cx, P); });
     }
     return 0;
 }
@@ -237,13 +237,15 @@ void emu_model_eval(const double *kh, int nk, const double *x, double *phi, doub
         SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
         WarpSlab W = warp_slab_carve(sm.data(), nk, true);
         warp_slab_load(cx, W, kh, zero.data(), 0);
-        model_eval_warp(cx, W, x, 0, W.p0, W.dz);
+        model_coefs_warp(cx, W, x, 0.0, 0, 1, 0);
+        model_eval_warp(cx, W, 0, 0, W.p0, W.dz);
         for (int i = 0; i < nk; ++i) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
     } else {
         emu_launch(1, 32, warp_slab_doubles(nk, true) * sizeof(double), [&](const HostCtx &cx) {
             WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()), nk, true);
             warp_slab_load(cx, W, kh, zero.data(), cx.tid());
-            model_eval_warp(cx, W, x, cx.tid(), W.p0, W.dz);
+            model_coefs_warp(cx, W, x, 0.0, 0, 1, cx.tid());
+            model_eval_warp(cx, W, 0, cx.tid(), W.p0, W.dz);
             for (int i = cx.tid(); i < nk; i += 32) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
         });
     }
