@@ -18,44 +18,51 @@
 #define CB_KNU_EPS 1.0e-16
 #define CB_KNU_MAXIT 400
 
-// 1/Gamma(1+m) = sum_k RG[k] m^k  (mpmath, 40 digits, rounded)
-#define CB_RGAMMA_TERMS 24
-CB_HD double cb_rgamma_coef(int k) {
-    const double RG[CB_RGAMMA_TERMS] = {
-        1.0, 0.5772156649015328606065, -0.655878071520253881077, -0.042002635034095235529,
-        0.1665386113822914895017, -0.04219773455554433674821, -0.009621971527876973562115,
-        0.007218943246663099542395, -0.001165167591859065112114, -0.0002152416741149509728157,
-        0.0001280502823881161861532, -0.00002013485478078823865569, -0.000001250493482142670657345,
-        0.000001133027231981695882374, -2.05633841697760710345e-7, 6.116095104481415817862e-9,
-        5.002007644469222930056e-9, -1.181274570487020144588e-9, 1.043426711691100510492e-10,
-        7.78226343990507125405e-12, -3.696805618642205708188e-12, 5.100370287454475979015e-13,
-        -2.058326053566506783222e-14, -5.34812253942301798237e-15};
-    return RG[k];
-}
+// Code-size discipline: the fit / MCMC kernels run ~16 independent warps per SM through this code,
+// each at a different place, and the SM's instruction cache holds 32 KB.  Helpers that are used from
+// several places are therefore real functions on the device (one copy), not inlined.
+#if defined(__CUDACC__) && !defined(CB_EMU)
+#define CB_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define CB_HD_NOINLINE CB_HD
+#endif
+CB_HD_NOINLINE double cb_exp(double x) { return exp(x); }
+CB_HD_NOINLINE double cb_log(double x) { return log(x); }
 
-// even / odd parts of the series: E(m) = sum_{k even} c_k m^k, O(m) = sum_{k odd} c_k m^(k-1)
-// so that 1/Gamma(1+m) = E + m O and 1/Gamma(1-m) = E - m O.
-CB_HD void cb_rgamma_parts(double m, double &even, double &odd) {
+// 1/Gamma(1+m) = sum_k c_k m^k  (mpmath, 40 digits, rounded), split into even / odd parts:
+// E(m) = sum_{k even} c_k m^k, O(m) = sum_{k odd} c_k m^(k-1), so that
+// 1/Gamma(1+m) = E + m O and 1/Gamma(1-m) = E - m O.
+CB_HD_NOINLINE void cb_rgamma_parts(double m, double &even, double &odd) {
     const double m2 = m * m;
-    double e = 0.0, o = 0.0;
-#pragma unroll
-    for (int k = CB_RGAMMA_TERMS - 2; k >= 0; k -= 2) {
-        e = fma(e, m2, cb_rgamma_coef(k));
-        o = fma(o, m2, cb_rgamma_coef(k + 1));
-    }
+    double e = -2.058326053566506783222e-14, o = -5.34812253942301798237e-15;
+#define CB_RG(ce, co) e = fma(e, m2, ce); o = fma(o, m2, co);
+    CB_RG(-3.696805618642205708188e-12, 5.100370287454475979015e-13)
+    CB_RG(1.043426711691100510492e-10, 7.78226343990507125405e-12)
+    CB_RG(5.002007644469222930056e-9, -1.181274570487020144588e-9)
+    CB_RG(-2.05633841697760710345e-7, 6.116095104481415817862e-9)
+    CB_RG(-0.000001250493482142670657345, 0.000001133027231981695882374)
+    CB_RG(0.0001280502823881161861532, -0.00002013485478078823865569)
+    CB_RG(-0.001165167591859065112114, -0.0002152416741149509728157)
+    CB_RG(-0.009621971527876973562115, 0.007218943246663099542395)
+    CB_RG(0.1665386113822914895017, -0.04219773455554433674821)
+    CB_RG(-0.655878071520253881077, -0.042002635034095235529)
+    CB_RG(1.0, 0.5772156649015328606065)
+#undef CB_RG
     even = e;
     odd = o;
 }
 
-// Gamma(z).  0 < z <= 24: shift into [0.5, 1.5] and use the reciprocal-gamma series (a few
-// ulp); elsewhere (poles, negative or large arguments) defer to the C library tgamma, which
-// has the same pole conventions as scipy.special.gamma (gamma(0) = inf, gamma(-n) = nan).
-CB_HD double cb_gamma(double z) {
-    if (!(z > 0.0) || z > 24.0) {
-        if (z == 0.0) return copysign(INFINITY, z);
-        if (z < 0.0 && z == floor(z)) return NAN;
-        return tgamma(z);
-    }
+// Poles, negative and large arguments: the C library tgamma, which has the same pole conventions
+// as scipy.special.gamma (gamma(0) = inf, gamma(-n) = nan).  Cold path.
+CB_HD_NOINLINE double cb_gamma_slow(double z) {
+    if (z == 0.0) return copysign(INFINITY, z);
+    if (z < 0.0 && z == floor(z)) return NAN;
+    return tgamma(z);
+}
+
+// Gamma(z).  0 < z <= 24: shift into [0.5, 1.5] and use the reciprocal-gamma series (a few ulp).
+CB_HD_NOINLINE double cb_gamma(double z) {
+    if (!(z > 0.0) || z > 24.0) return cb_gamma_slow(z);
     double w = z, num = 1.0, den = 1.0;
     while (w > 1.5) { w -= 1.0; num *= w; }
     while (w < 0.5) { den *= w; w += 1.0; }
@@ -76,6 +83,14 @@ struct KnuOrder {
     double sinc;     // pi mu / sin(pi mu)
 };
 
+CB_HD double cb_sinpi(double t) {          // |t| <= 1/2
+#ifdef __CUDA_ARCH__
+    return sinpi(t);
+#else
+    return sin(CB_PI * t);
+#endif
+}
+
 CB_HD KnuOrder knu_order(double nu_signed) {
     KnuOrder o;
     o.nu = fabs(nu_signed);
@@ -94,7 +109,7 @@ CB_HD KnuOrder knu_order(double nu_signed) {
     o.gam1 = -od;
     o.gam2 = e;
     const double pm = CB_PI * o.mu;
-    o.sinc = (fabs(pm) < 1e-8) ? 1.0 : pm / sin(pm);
+    o.sinc = (fabs(pm) < 1e-8) ? 1.0 : pm / cb_sinpi(o.mu);
     return o;
 }
 

@@ -32,7 +32,7 @@ CB_HD ModelCoef model_coef(double beta, double zt, double dz, double C) {
     m.ord = knu_order(m.nu);
     m.gnu = cb_gamma(m.nu);
     m.lead = CB_SQRT_PI / cb_gamma(1.0 + 0.5 * beta);
-    m.lhalfdz = log(0.5 * dz);
+    m.lhalfdz = cb_log(0.5 * dz);
     return m;
 }
 

@@ -53,6 +53,8 @@ struct FitState {
     double d[4], gd;              // search direction and g.d
     double xt[4], dec, move, pen_t, hb;   // trial point, g.(xt-x), max |xt-x|, prior penalty at xt, beta step
     double fn, gn[4], Hn[10];     // full evaluation at the accepted trial point
+    double pmu[4], pw[4];         // prior mean and inverse variance (0 = no prior)
+    double one;                   // 1.0 (the dPhi/dC column of the Jacobian, read with stride 0)
     int32_t okn, fresh, stall, status, action, it, nfev, pad_;
 };
 #define CB_FIT_STATE_DOUBLES ((int)((sizeof(FitState) + 7) / 8))
@@ -61,7 +63,7 @@ CB_HD int fit_slab_doubles(int nk) { return warp_slab_doubles(nk, true, CB_FIT_S
 
 // Solve B d = -g on the free variables (frozen ones get d = 0) by Cholesky; returns false when the
 // reduced matrix is not positive definite.
-CB_HD bool solve_free(const double *B /*packed*/, const double *g, const bool *frozen, double *d) {
+CB_HD_NOINLINE bool solve_free(const double *B /*packed*/, const double *g, const bool *frozen, double *d) {
     double A[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -82,8 +84,8 @@ CB_HD bool solve_free(const double *B /*packed*/, const double *g, const bool *f
         for (int k = 0; k < 4; ++k)
             if (k < j) s -= L[j][k] * L[j][k];
         if (!(s > 0.0) || !isfinite(s)) return false;
-        const double ljj = sqrt(s);
-        L[j][j] = ljj;
+        const double ljj = sqrt(s), rjj = 1.0 / ljj;
+        L[j][j] = rjj;                 // the diagonal holds the reciprocal
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (i > j) {
@@ -91,7 +93,7 @@ CB_HD bool solve_free(const double *B /*packed*/, const double *g, const bool *f
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k < j) t -= L[i][k] * L[j][k];
-                L[i][j] = t / ljj;
+                L[i][j] = t * rjj;
             }
     }
     double y[4];
@@ -101,7 +103,7 @@ CB_HD bool solve_free(const double *B /*packed*/, const double *g, const bool *f
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (k < i) t -= L[i][k] * y[k];
-        y[i] = t / L[i][i];
+        y[i] = t * L[i][i];
     }
 #pragma unroll
     for (int i = 3; i >= 0; --i) {
@@ -109,7 +111,7 @@ CB_HD bool solve_free(const double *B /*packed*/, const double *g, const bool *f
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (k > i) t -= L[k][i] * d[k];
-        d[i] = t / L[i][i];
+        d[i] = t * L[i][i];
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -119,14 +121,13 @@ CB_HD bool solve_free(const double *B /*packed*/, const double *g, const bool *f
 
 CB_HD double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
 
-CB_HD double fit_prior_penalty(const cb_fit_options *o, const double *x) {
+CB_HD double fit_prior_penalty(const FitState *S, const double *x) {
     double c = 0.0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (!isnan(o->prior_mu[j])) {
-            const double dl = x[j] - o->prior_mu[j];
-            c += 0.5 * dl * dl / (o->prior_sigma[j] * o->prior_sigma[j]);
-        }
+    for (int j = 0; j < 4; ++j) {
+        const double dl = x[j] - S->pmu[j];
+        c = fma(0.5 * dl * dl, S->pw[j], c);
+    }
     return c;
 }
 
@@ -134,7 +135,13 @@ CB_HD double fit_prior_penalty(const cb_fit_options *o, const double *x) {
 // Start: clip x0 into the bounds (scipy does, _lbfgsb_py.py:359) and into the cosh wall.
 CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const double *x0, double kmax) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { S->lb[j] = o->lb[j]; S->ub[j] = o->ub[j]; }
+    for (int j = 0; j < 4; ++j) {
+        S->lb[j] = o->lb[j];
+        S->ub[j] = o->ub[j];
+        const bool has = !isnan(o->prior_mu[j]);
+        S->pmu[j] = has ? o->prior_mu[j] : 0.0;
+        S->pw[j] = has ? 1.0 / (o->prior_sigma[j] * o->prior_sigma[j]) : 0.0;
+    }
     if (kmax > 0.0) {
         double wall = CB_COSH_OVERFLOW / kmax;
         while (kmax * wall > CB_COSH_OVERFLOW) wall = nextafter(wall, 0.0);
@@ -143,7 +150,7 @@ CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const doubl
 #pragma unroll
     for (int j = 0; j < 4; ++j) S->xt[j] = clampd(x0[j], S->lb[j], S->ub[j]);
     S->hb = 1e-6 * fmax(1.0, fabs(S->xt[0]));
-    S->pen_t = fit_prior_penalty(o, S->xt);
+    S->pen_t = fit_prior_penalty(S, S->xt);
     S->fresh = 1; S->stall = 0; S->status = FIT_MAXITER; S->action = FIT_GO; S->it = 0; S->nfev = 0; S->pad_ = 0;
 }
 
@@ -207,7 +214,7 @@ CB_NOINLINE_BODY void fit_direction(FitState *S, double gtol) {
     if (-gd <= 1e-13 * fmax(1.0, fabs(S->f))) { S->status = FIT_CONVERGED_F; S->action = FIT_DONE; }
 }
 
-CB_NOINLINE_BODY void fit_trial(FitState *S, const cb_fit_options *o, double alpha) {
+CB_NOINLINE_BODY void fit_trial(FitState *S, double alpha) {
     double dec = 0.0, move = 0.0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -219,7 +226,7 @@ CB_NOINLINE_BODY void fit_trial(FitState *S, const cb_fit_options *o, double alp
     S->dec = dec;
     S->move = move;
     S->hb = 1e-6 * fmax(1.0, fabs(S->xt[0]));
-    S->pen_t = fit_prior_penalty(o, S->xt);
+    S->pen_t = fit_prior_penalty(S, S->xt);
 }
 
 // The line search failed: retry once from the Gauss-Newton metric, else give up.
@@ -259,10 +266,11 @@ CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
             sBs += t * s[i];
         }
         if (sBs > 0.0) {
+            const double rsy = 1.0 / sy, rsBs = 1.0 / sBs;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = i; j < 4; ++j) S->B[tri(i, j)] += y[i] * y[j] / sy - Bs[i] * Bs[j] / sBs;
+                for (int j = i; j < 4; ++j) S->B[tri(i, j)] += y[i] * y[j] * rsy - Bs[i] * Bs[j] * rsBs;
             updated = true;
             S->fresh = 0;
         }
@@ -287,61 +295,77 @@ CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
 
 // ---- all-lane phases ----------------------------------------------------------------------------
 // Objective, gradient and Gauss-Newton matrix at S->xt from the staged model values
-// (p0, dPhi/ddz at xt; pp, pm at beta +- hb): 15 warp reductions, lane 0 stores the result.
+// (p0, dPhi/ddz at xt; pp, pm at beta +- hb).  The 15 sums are sum_i u_a[i] u_b[i] over the five
+// per-point vectors u = (r, dPhi/dbeta, k, dPhi/ddz, 1) (dPhi/dzt = -2k is applied as a scale).
+// Pass 1 stages r and the central difference in beta, lane-parallel over the points; in pass 2
+// lane q < 15 (and lane 16+q for the second half of the points) owns ONE of the 15 products and
+// walks the points with broadcast-free strided reads -- no 15-wide butterfly, ~100 instructions.
 template <class Ctx>
-CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState *S, const cb_fit_options *o, int lane) {
+CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState *S, int lane) {
+    const int L = cx.team_lanes(), nk = W.nk;
     const double hb = S->hb;
     const double rh = 1.0 / hb, rh2 = 0.5 * rh;
-    double acc[15];
-#pragma unroll
-    for (int q = 0; q < 15; ++q) acc[q] = 0.0;
-    for (int i = lane; i < W.nk; i += cx.team_lanes()) {
+#pragma unroll 1
+    for (int i = lane; i < nk; i += L) {
         const double p0 = W.p0[i], pp = W.pp[i], pm = W.pm[i];
-        double J[4];
-        if (isfinite(pp) && isfinite(pm)) J[0] = (pp - pm) * rh2;
-        else if (isfinite(pp)) J[0] = (pp - p0) * rh;
-        else if (isfinite(pm)) J[0] = (p0 - pm) * rh;
-        else J[0] = 0.0;
-        J[1] = -2.0 * W.k[i];
-        J[2] = W.dz[i];
-        J[3] = 1.0;
-        const double r = p0 - W.obs[i];
-        acc[0] = fma(r, r, acc[0]);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            acc[1 + a] = fma(r, J[a], acc[1 + a]);
-#pragma unroll
-            for (int b = a; b < 4; ++b) acc[5 + tri(a, b)] = fma(J[a], J[b], acc[5 + tri(a, b)]);
+        const bool fp = isfinite(pp), fm = isfinite(pm);
+        W.kb[i] = (fp && fm) ? (pp - pm) * rh2 : (fp ? (pp - p0) * rh : (fm ? (p0 - pm) * rh : 0.0));
+        W.ka[i] = p0 - W.obs[i];
+    }
+    if (lane == 0) S->one = 1.0;
+    cx.sync_warp();
+    const bool split = (L == 32);
+    const int half = split ? (lane >> 4) : 0;
+    const int lo = half ? (nk + 1) / 2 : 0, hi = split ? (half ? nk : (nk + 1) / 2) : nk;
+    const int qstep = split ? 16 : L;
+#pragma unroll 1
+    for (int q = split ? (lane & 15) : lane; q < 16; q += qstep) {
+        // q = 0: r.r;  1..4: r.J_a;  5..14: J_a.J_b packed upper triangle;  15: idle (keeps the shuffle convergent)
+        int va = 0, vb = 0;
+        if (q >= 1 && q < 5) vb = q;
+        else if (q >= 5) {
+            const int t = q - 5;
+            const int a = t < 4 ? 0 : (t < 7 ? 1 : (t < 9 ? 2 : 3));
+            va = a + 1;
+            vb = t - (a * 4 - (a * (a - 1)) / 2) + a + 1;
+        }
+        const double *pa = va == 0 ? W.ka : (va == 1 ? W.kb : (va == 2 ? W.k : (va == 3 ? W.dz : &S->one)));
+        const double *pb = vb == 0 ? W.ka : (vb == 1 ? W.kb : (vb == 2 ? W.k : (vb == 3 ? W.dz : &S->one)));
+        const int sa = va == 4 ? 0 : 1, sb = vb == 4 ? 0 : 1;
+        double acc = 0.0;
+        if (q < 15) {
+#pragma unroll 1
+            for (int i = lo; i < hi; ++i) acc = fma(pa[i * sa], pb[i * sb], acc);
+        }
+        if (split) acc += cx.shfl_xor(acc, 16);
+        acc *= (va == 2 ? -2.0 : 1.0) * (vb == 2 ? -2.0 : 1.0);
+        if (half == 0 && q < 15) {
+            if (q == 0) S->fn = 0.5 * acc;
+            else if (q < 5) S->gn[q - 1] = acc;
+            else S->Hn[q - 5] = acc;
         }
     }
     cx.sync_warp();
-#pragma unroll
-    for (int q = 0; q < 15; ++q) acc[q] = cx.warp_sum(acc[q]);
     if (lane == 0) {
-        const double f = 0.5 * acc[0];
-        bool ok = isfinite(f);
-#pragma unroll
-        for (int q = 1; q < 15; ++q) ok = ok && isfinite(acc[q]);
+        bool ok = isfinite(S->fn);
+#pragma unroll 1
+        for (int a = 0; a < 4; ++a) ok = ok && isfinite(S->gn[a]);
+#pragma unroll 1
+        for (int q = 0; q < 10; ++q) ok = ok && isfinite(S->Hn[q]);
         S->okn = ok ? 1 : 0;
         if (!ok) {
             S->fn = CB_BIG_MISFIT;
-#pragma unroll
+#pragma unroll 1
             for (int a = 0; a < 4; ++a) S->gn[a] = 0.0;
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 10; ++q) S->Hn[q] = 0.0;
         } else {
-            S->fn = f + S->pen_t;
+            S->fn += S->pen_t;
 #pragma unroll
-            for (int a = 0; a < 4; ++a) S->gn[a] = acc[1 + a];
-#pragma unroll
-            for (int q = 0; q < 10; ++q) S->Hn[q] = acc[5 + q];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-                if (!isnan(o->prior_mu[a])) {
-                    const double w = 1.0 / (o->prior_sigma[a] * o->prior_sigma[a]);
-                    S->gn[a] += (S->xt[a] - o->prior_mu[a]) * w;
-                    S->Hn[tri(a, a)] += w;
-                }
+            for (int a = 0; a < 4; ++a) {
+                S->gn[a] = fma(S->xt[a] - S->pmu[a], S->pw[a], S->gn[a]);
+                S->Hn[tri(a, a)] += S->pw[a];
+            }
         }
     }
     cx.sync_warp();
@@ -381,7 +405,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
     model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
     model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
-    fit_reduce_full(cx, W, S, o, lane);
+    fit_reduce_full(cx, W, S, lane);
     if (lane == 0) { fit_accept_first(S); S->nfev = 3; }
 
     // S->action is written by lane 0 only; every read is fenced by a barrier on both sides so that
@@ -396,7 +420,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
         bool accepted = false;
         int nls = 0;
         for (int ls = 0; ls < 40; ++ls) {
-            if (lane == 0) fit_trial(S, o, alpha);
+            if (lane == 0) fit_trial(S, alpha);
             cx.sync_warp();
             const double dec = S->dec;
             if (S->move == 0.0) break;
@@ -424,7 +448,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
         model_coefs_warp(cx, W, S->xt, S->hb, 1, 2, lane);
         model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
         model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
-        fit_reduce_full(cx, W, S, o, lane);
+        fit_reduce_full(cx, W, S, lane);
         if (lane == 0) { S->nfev += nls + 2; fit_update(S, ftol, max_iter); }
     }
     if (lane == 0) {

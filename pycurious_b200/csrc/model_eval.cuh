@@ -38,7 +38,7 @@
 #define CB_MAX_ORDERS 3                       /* parameter vectors evaluated per call group: x, x+h e_beta, x-h e_beta */
 
 #if defined(__CUDACC__) && !defined(CB_EMU)
-#define CB_NOINLINE_BODY __device__ __noinline__
+#define CB_NOINLINE_BODY static __device__ __noinline__
 #else
 #define CB_NOINLINE_BODY inline
 #endif
@@ -52,6 +52,7 @@ struct EvalCoef {
     double lgnu;        // ln Gamma(nu)
     double lgc;         // ln(lead Gamma(nu)/4)
     double hp, hq;      // 1/(2 Gamma(1+mu)), 1/(2 Gamma(1-mu))
+    double rmu;         // 1/mu (unused when mu ln(2/x) is tiny)
     int32_t fast;       // 1: the class-split path applies
     int32_t pad_;
 };
@@ -59,6 +60,7 @@ struct EvalCoef {
 struct WarpSlab {          // views into one warp's shared-memory slab
     double *k, *logk, *rk, *sq, *obs;   // [nk] k, ln k, 1/k, sqrt(pi/(2k)), observed Phi
     double *p0, *pp, *pm, *dz;          // [nk] model values (p0) and, for the fit, Phi(beta+-h), dPhi/ddz
+    double *ka, *kb;                    // [nk] K_mu, K_mu+1 between the phases of one evaluation
     double *rn;                         // [CB_MILLER_NMAX + 1] 1/n
     double2 *CA;                        // [CB_MILLER_NMAX + 1] (C_n, a_{n+1}) of the order being evaluated
     double2 *rpq;                       // [CB_TEMME_TAB] (1/(j-mu), 1/(j+mu))
@@ -72,7 +74,7 @@ struct WarpSlab {          // views into one warp's shared-memory slab
 #define CB_SLAB_COEF_DOUBLES ((int)((sizeof(EvalCoef) + 7) / 8))
 
 CB_HD int warp_slab_doubles(int nk, bool fit, int scratch_doubles = 0) {
-    int n = (fit ? 9 : 6) * nk + (CB_MILLER_NMAX + 1) + 2 * (CB_MILLER_NMAX + 1) + 2 * CB_TEMME_TAB +
+    int n = (fit ? 11 : 8) * nk + (CB_MILLER_NMAX + 1) + 2 * (CB_MILLER_NMAX + 1) + 2 * CB_TEMME_TAB +
             CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES + scratch_doubles;
     return (n + 1) & ~1;      // keep every slab 16-byte aligned
 }
@@ -86,7 +88,8 @@ CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit) {
     W.coef = reinterpret_cast<EvalCoef *>(t); t += CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES;
     W.rn = t; t += CB_MILLER_NMAX + 1;
     W.k = t; W.logk = t + nk; W.rk = t + 2 * nk; W.sq = t + 3 * nk; W.obs = t + 4 * nk; W.p0 = t + 5 * nk;
-    t += 6 * nk;
+    W.ka = t + 6 * nk; W.kb = t + 7 * nk;
+    t += 8 * nk;
     if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; t += 3 * nk; }
     else { W.pp = W.pm = W.dz = nullptr; }
     W.scratch = t;
@@ -101,10 +104,11 @@ CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *kh, const 
     const int L = cx.team_lanes();
     bool asc = true;
     double kmax = 0.0;
+#pragma unroll 1
     for (int i = lane; i < W.nk; i += L) {
         const double k = kh[i];
         W.k[i] = k;
-        W.logk[i] = log(k);
+        W.logk[i] = cb_log(k);
         W.rk[i] = 1.0 / k;
         W.sq[i] = sqrt(0.5 * CB_PI / k);
         W.obs[i] = phi_row[i];
@@ -112,6 +116,7 @@ CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *kh, const 
         if (!(k > 0.0)) asc = false;
         kmax = fmax(kmax, k);
     }
+#pragma unroll 1
     for (int n = lane; n <= CB_MILLER_NMAX; n += L) W.rn[n] = n ? 1.0 / (double)n : 0.0;
     for (int o = 16; o > 0; o >>= 1) kmax = fmax(kmax, cx.shfl_xor(kmax, o));
     W.kmax = kmax;
@@ -134,10 +139,11 @@ CB_NOINLINE_BODY void model_coefs_warp(const Ctx &cx, const WarpSlab &W, const d
         e.a1 = 0.25 - m.ord.mu * m.ord.mu;
         e.rdz = 1.0 / m.dz;
         e.rsdz = 1.0 / sqrt(m.dz);
-        e.lgnu = log(m.gnu);
-        e.lgc = log(m.lead * m.gnu * 0.25);
+        e.lgnu = cb_log(m.gnu);
+        e.lgc = cb_log(m.lead * m.gnu * 0.25);
         e.hp = 0.5 / m.ord.gampl;
         e.hq = 0.5 / m.ord.gammi;
+        e.rmu = 1.0 / m.ord.mu;
         e.fast = (m.dz > 0.0 && m.dz < 1e300 && m.nu >= 0.5 && m.nu <= 8.5 && isfinite(m.zt) && isfinite(m.C) &&
                   m.gnu > 0.0 && m.lead > 0.0 && isfinite(m.gnu) && isfinite(m.lead)) ? 1 : 0;
         e.pad_ = 0;
@@ -152,27 +158,13 @@ CB_NOINLINE_BODY double generic_point(const ModelCoef *m, double k, double logk,
     return bouligand_point(*m, k, logk);
 }
 
-// K_nu e^-x, K_nu-1 e^-x from K_mu e^-x, K_mu+1 e^-x (nl >= 1), then the model value and d/ddz.
-//   e2 = e^-2x;  bracket e^-x = Gamma(nu)/4 (1 + e2) - hx (K_nu e^-x)
-CB_HD double finish_point(const EvalCoef &e, double k, double logk, double invx, double e2, double kmuE, double kmu1E,
-                          double *ddz) {
-    const ModelCoef &m = e.m;
-    double a = kmuE, b = kmu1E;
-    const double tox = 2.0 * invx;
-    for (int j = 1; j < m.ord.nl; ++j) {
-        const double c = fma((m.ord.mu + (double)j) * tox, b, a);
-        a = b;
-        b = c;
-    }
-    const double hx = exp(m.nu * (logk + m.lhalfdz));
-    const double qg = 0.25 * m.gnu;
-    const double br = fma(qg, 1.0 + e2, -b * hx);
-    if (ddz) *ddz = k * (fma(qg, 1.0 - e2, hx * a) / br - 1.0);
-    return fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * logk + log(m.lead * br);
-}
-
 // Phi(k_i) of parameter vector `idx` (coefficients prepared by model_coefs_warp) for every
 // wavenumber of the slab -> out_phi[i] (and dPhi/ddz -> out_ddz[i] if not NULL).
+// Four phases, each a single copy of its code (exp / log / division sites are not duplicated):
+//   T  x <= 2           Temme series          -> ka = K_mu,      kb = K_mu+1        (unscaled)
+//   M  2 < x < x_skip   Miller recurrence     -> ka = K_mu e^x,  kb = K_mu+1 e^x
+//   F  all of the above: scale by e^-x resp. e^-2x, upward recurrence in the order, bracket, log
+//   S  x >= x_skip      closed form
 template <class Ctx>
 CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int lane, double *out_phi,
                                       double *out_ddz) {
@@ -180,6 +172,7 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     const ModelCoef &m = e.m;
     const int nk = W.nk, L = cx.team_lanes();
     if (!(W.sorted && e.fast)) {                       // generic per-point path, reference nan/inf semantics
+#pragma unroll 1
         for (int i = lane; i < nk; i += L)
             out_phi[i] = generic_point(&m, W.k[i], W.logk[i], out_ddz ? out_ddz + i : nullptr);
         cx.sync_warp();
@@ -189,6 +182,7 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
 
     // ---- classes: [0,nT) Temme, [nT,nS) Miller, [nS,nk) K negligible ---------------------------
     int lastT = -1, lastC = -1;
+#pragma unroll 1
     for (int i = lane; i < nk; i += L) {
         const double xi = W.k[i] * dz;
         if (xi <= 2.0) lastT = i;
@@ -203,22 +197,6 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     if (nS > nT) {
         // C_0 = 1, C_1 = a1, C_n = C_{n-1} (a1 + n(n-1)) / n;  CA[n].y = a_{n+1} = -(a1 + n(n+1))
         // lane l owns n = 3l+2 .. 3l+4; local prefix, product scan over lanes, expand
-        double q[3];
-        double run = 1.0;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int n = 3 * lane + 2 + j;
-            const double g = n <= CB_MILLER_NMAX ? fma(a1, W.rn[n], (double)(n - 1)) : 1.0;
-            run *= g;
-            q[j] = run;
-        }
-        double incl = run;
-        for (int d = 1; d < L; d <<= 1) {
-            const double t = cx.shfl_up(incl, d);
-            if (lane >= d) incl *= t;
-        }
-        double excl = cx.shfl_up(incl, 1);
-        if (lane == 0) excl = 1.0;
         if (L == 1) {                                   // serial emulation: one lane builds the whole table
             double c = a1;
             W.CA[0] = make_double2(1.0, -a1);
@@ -228,6 +206,23 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
                 W.CA[n] = make_double2(c, -(a1 + (double)n * (double)(n + 1)));
             }
         } else {
+            double q[3];
+            double run = 1.0;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int n = 3 * lane + 2 + j;
+                const double g = n <= CB_MILLER_NMAX ? fma(a1, W.rn[n], (double)(n - 1)) : 1.0;
+                run *= g;
+                q[j] = run;
+            }
+            double incl = run;
+#pragma unroll 1
+            for (int d = 1; d < L; d <<= 1) {
+                const double t = cx.shfl_up(incl, d);
+                if (lane >= d) incl *= t;
+            }
+            double excl = cx.shfl_up(incl, 1);
+            if (lane == 0) excl = 1.0;
             const double base = a1 * excl;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -241,22 +236,25 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
         }
     }
     if (nT > 0) {
+#pragma unroll 1
         for (int j = 1 + lane; j < CB_TEMME_TAB; j += L)
             W.rpq[j] = make_double2(1.0 / ((double)j - mu), 1.0 / ((double)j + mu));
     }
     cx.sync_warp();
 
-    // ---- x <= 2: Temme's series ---------------------------------------------------------------
+    // ---- T: Temme's series ----------------------------------------------------------------------
+#pragma unroll 1
     for (int i = lane; i < nT; i += L) {
-        const double k = W.k[i], lk = W.logk[i], xi = k * dz;
-        const double d = -(lk + m.lhalfdz);             // ln(2/x)
+        const double d = -(W.logk[i] + m.lhalfdz);      // ln(2/x)
         const double sg = mu * d;
-        const double ee = exp(sg), ei = 1.0 / ee;
-        const double shc = fabs(sg) < 1e-4 ? 1.0 + sg * sg * (1.0 / 6.0) : 0.5 * (ee - ei) / sg;
-        double ff = m.ord.sinc * (m.ord.gam1 * 0.5 * (ee + ei) + m.ord.gam2 * shc * d);
+        const double ee = cb_exp(sg), ei = 1.0 / ee;
+        // sinh(sg)/sg * d = sinh(sg)/mu
+        const double shd = fabs(sg) < 1e-4 ? d * (1.0 + sg * sg * (1.0 / 6.0)) : 0.5 * (ee - ei) * e.rmu;
+        double ff = m.ord.sinc * (m.ord.gam1 * 0.5 * (ee + ei) + m.ord.gam2 * shd);
         double p = e.hp * ee, q = e.hq * ei, c = 1.0;
-        const double x2 = 0.5 * xi, dd = x2 * x2;
+        const double x2 = 0.5 * W.k[i] * dz, dd = x2 * x2;
         double sum = ff, sum1 = p;
+#pragma unroll 1
         for (int j = 1; j < CB_TEMME_TAB; ++j) {
             const double fj = (double)j;
             const double2 r = W.rpq[j];
@@ -269,22 +267,21 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
             sum1 = fma(c, p - fj * ff, sum1);
             if (fabs(del) < fabs(sum) * CB_KNU_EPS) break;
         }
-        const double invx = W.rk[i] * e.rdz;
-        const double emx = exp(-xi);
-        out_phi[i] = finish_point(e, k, lk, invx, emx * emx, sum * emx, sum1 * (2.0 * invx) * emx,
-                                  out_ddz ? out_ddz + i : nullptr);
+        W.ka[i] = sum;
+        W.kb[i] = sum1 * (2.0 * W.rk[i] * e.rdz);
     }
 
-    // ---- 2 < x < x_skip: Miller backward recurrence, uniform trip count per pass -------------------
+    // ---- M: Miller backward recurrence, uniform trip count per pass ----------------------------
+#pragma unroll 1
     for (int base = nT; base < nS; base += L) {
         const int i = base + lane;
-        const bool act = i < nS;
-        const int ii = act ? i : nS - 1;
-        const double k = W.k[ii], lk = W.logk[ii], xi = k * dz;
+        const int ii = i < nS ? i : nS - 1;
+        const double xi = W.k[ii] * dz;
         int N = (int)(12.0 + 140.0 * (W.rk[base] * e.rdz)) + 1;     // from the smallest x of this pass (k ascending)
         if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
         double yp = 0.0, y = 1.0, S = W.CA[N].x;
         double bn = 2.0 * ((double)N + xi);
+#pragma unroll 2
         for (int n = N; n >= 1; --n) {
             const double ym = fma(bn, y, W.CA[n].y * yp);
             yp = y;
@@ -292,20 +289,43 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
             S = fma(W.CA[n - 1].x, y, S);
             bn -= 2.0;
         }
-        const double invx = W.rk[ii] * e.rdz;
-        const double cS = W.sq[ii] * e.rsdz / S;                   // sqrt(pi/(2x)) / S
-        const double kmuE = cS * y;                                 // K_mu e^x
-        const double kmu1E = cS * fma(mu + xi + 0.5, y, -a1 * yp) * invx;
-        const double e2 = exp(-2.0 * xi);
-        double dv;
-        const double ph = finish_point(e, k, lk, invx, e2, kmuE * e2, kmu1E * e2, out_ddz ? &dv : nullptr);
-        if (act) {
-            out_phi[i] = ph;
-            if (out_ddz) out_ddz[i] = dv;
+        if (i < nS) {
+            const double invx = W.rk[ii] * e.rdz;
+            const double cS = W.sq[ii] * e.rsdz / S;               // sqrt(pi/(2x)) / S
+            W.ka[i] = cS * y;
+            W.kb[i] = cS * fma(mu + xi + 0.5, y, -a1 * yp) * invx;
+        }
+    }
+    cx.sync_warp();
+
+    // ---- F: scale, raise the order, bracket ------------------------------------------------------
+    //   bracket e^-x = Gamma(nu)/4 (1 + e^-2x) - hx (K_nu e^-x)
+    {
+        const double qg = 0.25 * m.gnu;
+        const int nl = m.ord.nl;
+#pragma unroll 1
+        for (int i = lane; i < nS; i += L) {
+            const double k = W.k[i], lk = W.logk[i], xi = k * dz;
+            const bool temme = i < nT;
+            const double ex = cb_exp(temme ? -xi : -2.0 * xi);     // scales ka, kb to K e^-x in both classes
+            const double e2 = temme ? ex * ex : ex;
+            double a = W.ka[i] * ex, b = W.kb[i] * ex;
+            const double tox = 2.0 * W.rk[i] * e.rdz;
+#pragma unroll 1
+            for (int j = 1; j < nl; ++j) {
+                const double c = fma((mu + (double)j) * tox, b, a);
+                a = b;
+                b = c;
+            }
+            const double hx = cb_exp(m.nu * (lk + m.lhalfdz));
+            const double br = fma(qg, 1.0 + e2, -b * hx);
+            out_phi[i] = fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * lk + cb_log(m.lead * br);
+            if (out_ddz) out_ddz[i] = k * (fma(qg, 1.0 - e2, hx * a) / br - 1.0);
         }
     }
 
-    // ---- x >= x_skip: the Bessel term cannot change the rounded bracket ----------------------------
+    // ---- S: the Bessel term cannot change the rounded bracket ------------------------------------
+#pragma unroll 1
     for (int i = nS + lane; i < nk; i += L) {
         const double k = W.k[i];
         const bool over = k * dz > CB_COSH_OVERFLOW;
@@ -319,6 +339,7 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
 template <class Ctx>
 CB_BODY double slab_half_ssq(const Ctx &cx, const WarpSlab &W, int lane) {
     double acc = 0.0;
+#pragma unroll 1
     for (int i = lane; i < W.nk; i += cx.team_lanes()) {
         const double r = W.p0[i] - W.obs[i];
         acc = fma(r, r, acc);
