@@ -93,7 +93,7 @@ def run_reference(args):
     data, ext = make_inputs(args.grid)
     xc, yc = CurieGrid.create_centroid_list(_HostGrid(data, ext), WINDOW, STRIDE, STRIDE)
     cores = host_cores()
-    nsample = args.cpu_sample or max(2 * cores, min(4096, cores * 24))
+    nsample = args.cpu_sample or cores * 500           # ~25 ms per window per core -> 10-20 s per step
     vals = []
     for s in range(args.warmup + args.steps):
         v, dt = cpu_windows_per_s(data, ext, xc, yc, nsample, cores)
@@ -193,7 +193,7 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        nsample = args.cpu_sample or max(2 * cores, min(2048, cores * 12))
+        nsample = args.cpu_sample or cores * 500       # ~25 ms per window per core -> 10-20 s of wall clock
         v, dt = cpu_windows_per_s(data, ext, xc, yc, nsample, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d of %d windows (evenly spaced) in %.1f s, oracle port, fork pool, OPENBLAS_NUM_THREADS=1"
@@ -262,6 +262,35 @@ def run_gpu(args):
                   "fit_nfev_mean": float(nfev.mean().item()), "fit_niter_mean": float(diag["niter"].double().mean().item()),
                   "fit_status_counts": [int((diag["status"] == s).sum().item()) for s in range(5)]}
 
+    # MCMC samples/s (BASELINE config 4, bounded): one Metropolis-Hastings chain per window on a
+    # sample of the centroid list, priors and proposal scale of SURVEY 8d, moments streamed on the device
+    mcmc = None
+    if rank == 0 and args.mcmc_steps > 0:
+        nch = min(nwin, args.mcmc_chains)
+        sel = np.linspace(0, nwin - 1, nch).astype(np.int64)
+        sel_t = torch.from_numpy(sel).cuda()
+        phi_all, _ = plan.run(g_dev, iy0, ix0, False, 2.0)
+        phi_s = phi_all.index_select(0, sel_t).contiguous()
+        x_map = grid._fit_device(plan.k, phi_s, x0)
+        grid.add_prior(beta=(3.0, 1.0), zt=(1.0, 1.0), dz=(20.0, 10.0), C=(float(x_map[:, 3].mean().item()), 5.0))
+        burn = max(1, args.mcmc_steps // 100)
+        tm = []
+        for _ in range(3):
+            a, b = ev(), ev()
+            a.record()
+            mom, acc = grid._mh_device(plan.k, phi_s, args.mcmc_steps, burn, [0.25, 0.1, 1.0, 0.5], x0, x_map,
+                                       SEED, 1)
+            b.record()
+            torch.cuda.synchronize()
+            tm.append(a.elapsed_time(b))
+        grid.reset_priors()
+        steps = nch * (args.mcmc_steps + burn)
+        mcmc = {"metric": "mcmc_samples_per_s", "value": steps / (min(tm[1:]) * 1e-3), "unit": "MH steps/s (burn-in included)",
+                "chains": int(nch), "nsim": int(args.mcmc_steps), "burnin": int(burn), "ms": float(min(tm[1:])),
+                "acceptance_mean": float(acc.double().mean().item() / args.mcmc_steps),
+                "nominal_fp64_tflops": steps * nb_points(plan) * 400.0 / (min(tm[1:]) * 1e-3) / 1e12,
+                "config": "config 4 sample: priors beta=(3,1) zt=(1,1) dz=(20,10) C=(mean MAP C,5), x_scale=[0.25,0.1,1,0.5], start = per-window MAP"}
+
     # end to end through the public API: host grid (pinned) -> device, fits -> host, every step
     e2e = None
     if rank == 0 or world > 1:
@@ -324,10 +353,14 @@ def run_gpu(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps, "roofline": roofline, "stages": stages,
                 "plan": {"fft_len": info.fft_len, "bluestein": info.bluestein, "radix": list(info.radix[:info.npass]),
                          "teams": info.teams, "ctas": info.grid_max, "smem_bytes": info.smem_bytes},
-                "cpu_baseline": cpu}
+                "mcmc": mcmc, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def nb_points(plan):
+    return plan.nbins
 
 
 def main():
@@ -339,6 +372,8 @@ def main():
     ap.add_argument("--grid", type=int, default=GRID_N, help="synthetic grid edge (default: BASELINE's 4096)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="windows in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mcmc-steps", type=int, default=2000, help="MH steps per chain in the MCMC leg (0 = skip)")
+    ap.add_argument("--mcmc-chains", type=int, default=148 * 64, help="chains (= windows) in the MCMC leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,5 +1,6 @@
 // Spectrum stage: plan objects, launches and C-ABI entry points (include/curie_b200.h).
 // Kernel body: spectrum_body.cuh.  Replaces pycurious/grid.py:112-157, :199-216, :218-288.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "spectrum_plan.h"
@@ -58,8 +59,15 @@ int cb_spectrum_plan_create(int nw, int nbins, const double *taper_r, const doub
     cudaDeviceProp prop;
     CB_CUDA_TRY(cudaGetDeviceProperties(&prop, pl->device));
     pl->sm_count = prop.multiProcessorCount;
+    // CB_SPEC_TEAMS (tuning knob): FFT teams (warps) per CTA; fewer teams -> more CTAs per SM, each on
+    // its own window and in its own phase of the pipeline
+    int max_teams = CB_SPEC_MAX_TEAMS;
+    if (const char *env = getenv("CB_SPEC_TEAMS")) {
+        const int t = atoi(env);
+        if (t >= 1 && t <= CB_SPEC_MAX_TEAMS) max_teams = t;
+    }
     if (!spectrum_plan_build_host(pl->hp, nw, nbins, taper_r, taper_c, bin_ptr, bin_idx,
-                                  (int64_t)prop.sharedMemPerBlockOptin)) {
+                                  (int64_t)prop.sharedMemPerBlockOptin, max_teams)) {
         cb_set_error("spectrum plan for nw=%d: %s", nw, pl->hp.error.c_str());
         delete pl;
         return CB_ERR_UNSUPPORTED;

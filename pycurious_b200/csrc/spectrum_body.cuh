@@ -46,7 +46,7 @@ struct SpectrumParams {
     double *lh;               // [nvh][n]
     int64_t gt_stride, lh_stride;   // elements per CTA
     // shared-memory carve-up (in double2 slots)
-    int32_t sm_tw, sm_filt, sm_chirp, sm_buf, line_slots;
+    int32_t sm_tw, sm_filt, sm_chirp, sm_cw, sm_buf, line_slots;
 };
 
 CB_HD double2 bluestein_out(const double2 *buf, const double2 *chirp, int k) {
@@ -63,6 +63,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
     double2 *s_tw = sm + P.sm_tw;
     double2 *s_filt = sm + P.sm_filt;
     double2 *s_chirp = sm + P.sm_chirp;
+    double2 *s_cw = sm + P.sm_cw;
     double2 *buf = sm + P.sm_buf + (int64_t)warp * P.line_slots;
     double *s_red = reinterpret_cast<double *>(sm);   // 3*32 doubles reserved in front of sm_tw
 
@@ -70,6 +71,10 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
     if (P.bluestein) {
         for (int i = tid; i < P.line_slots; i += nthr) s_filt[i] = P.filt[i];
         for (int i = tid; i < n; i += nthr) s_chirp[i] = P.chirp[i];
+    }
+    for (int i = tid; i < n; i += nthr) {
+        const double tc = P.taper_c ? P.taper_c[i] : 1.0;
+        s_cw[i] = P.bluestein ? cscale(P.chirp[i], tc) : cplx(tc, 0.0);
     }
     cx.sync_block();
 
@@ -121,22 +126,32 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
             const double t0 = P.taper_r ? Ctx::ldg(P.taper_r + y0) : 1.0;
             const double t1 = (P.taper_r && has1) ? Ctx::ldg(P.taper_r + y1) : 1.0;
             const double pl0 = c0 + cy1 * ((double)y0 - ctr), pl1 = c0 + cy1 * ((double)y1 - ctr);
-            for (int x = lane; x < M; x += CB_WARP) {
-                double2 z = cplx(0.0, 0.0);
-                if (x < n) {
-                    double a = Ctx::ldg(r0 + x);
-                    double b = has1 ? Ctx::ldg(r1 + x) : 0.0;
-                    if (P.detrend) {
-                        const double px = cx1 * ((double)x - ctr);
-                        a -= pl0 + px;
-                        b = has1 ? b - (pl1 + px) : 0.0;
-                    }
-                    const double tc = P.taper_c ? Ctx::ldg(P.taper_c + x) : 1.0;
-                    z = cplx(a * (tc * t0), b * (tc * t1));
-                    if (P.bluestein) z = cmul(z, s_chirp[x]);
+            // all global loads of a chunk are issued before the first use (4 x 2 loads in flight per lane)
+            for (int xb = 0; xb < n; xb += 4 * CB_WARP) {
+                double a[4], b[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = xb + j * CB_WARP + lane;
+                    a[j] = x < n ? Ctx::ldg(r0 + x) : 0.0;
+                    b[j] = (x < n && has1) ? Ctx::ldg(r1 + x) : 0.0;
                 }
-                buf[CB_PAD(x)] = z;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = xb + j * CB_WARP + lane;
+                    if (x < n) {
+                        double av = a[j], bv = b[j];
+                        if (P.detrend) {
+                            const double px = cx1 * ((double)x - ctr);
+                            av -= pl0 + px;
+                            bv = has1 ? bv - (pl1 + px) : 0.0;
+                        }
+                        // s_cw = column taper (x chirp for Bluestein), staged once per CTA
+                        const double2 cw = s_cw[x];
+                        buf[CB_PAD(x)] = P.bluestein ? cmul(cplx(av * t0, bv * t1), cw) : cplx(av * t0 * cw.x, bv * t1 * cw.x);
+                    }
+                }
             }
+            for (int x = n + lane; x < M; x += CB_WARP) buf[CB_PAD(x)] = cplx(0.0, 0.0);
             if (P.bluestein) bluestein_convolve(cx, buf, s_tw, s_filt, P.fft, lane);
             else fft_forward_dif(cx, buf, s_tw, P.fft, lane);
             // untangle: row y0 spectrum A[v] = (Z[v] + conj Z[-v])/2, row y1: B[v] = (Z[v] - conj Z[-v])/(2i)
@@ -163,14 +178,20 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
         // ---- phase B: columns -------------------------------------------------------------------
         for (int v = warp; v < nvh; v += nwarps) {
             const double2 *col = Gt + (int64_t)v * npad;
-            for (int y = lane; y < M; y += CB_WARP) {
-                double2 z = cplx(0.0, 0.0);
-                if (y < n) {
-                    z = Ctx::ldcg(col + y);
-                    if (P.bluestein) z = cmul(z, s_chirp[y]);
+            for (int yb = 0; yb < n; yb += 4 * CB_WARP) {
+                double2 z[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int y = yb + j * CB_WARP + lane;
+                    z[j] = y < n ? Ctx::ldcg(col + y) : cplx(0.0, 0.0);
                 }
-                buf[CB_PAD(y)] = z;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int y = yb + j * CB_WARP + lane;
+                    if (y < n) buf[CB_PAD(y)] = P.bluestein ? cmul(z[j], s_chirp[y]) : z[j];
+                }
             }
+            for (int y = n + lane; y < M; y += CB_WARP) buf[CB_PAD(y)] = cplx(0.0, 0.0);
             if (P.bluestein) bluestein_convolve(cx, buf, s_tw, s_filt, P.fft, lane);
             else fft_forward_dif(cx, buf, s_tw, P.fft, lane);
             double *out = Lh + (int64_t)v * n;
@@ -183,20 +204,35 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
         }
         cx.sync_block();
 
-        // ---- phase C: radial bins (grid.py:281-286), two-pass mean / population std --------------
+        // ---- phase C: radial bins (grid.py:281-286), mean / population std --------------
         for (int b = warp; b < P.nbins; b += nwarps) {
             const int lo = Ctx::ldg(P.bin_ptr + b), hi = Ctx::ldg(P.bin_ptr + b + 1);
-            double s = 0.0;
-            for (int e = lo + lane; e < hi; e += CB_WARP) s += Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e));
-            s = cx.warp_sum(s);
-            const double cnt = (double)(hi - lo);
-            const double mean = s / cnt;
-            double q = 0.0;
-            for (int e = lo + lane; e < hi; e += CB_WARP) {
-                const double d = Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e)) - mean;
-                q = fma(d, d, q);
+            // one pass over the members: sum and sum of squares about a pivot member (the population
+            // variance is shift invariant; the pivot removes the mean^2 cancellation), 4 gathers in flight
+            double pivot = lo < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + lo)) : 0.0;
+            if (!isfinite(pivot)) pivot = 0.0;          // log(0) = -inf members: plain sums, numpy's -inf / nan result
+            double s = 0.0, q = 0.0;
+            for (int eb = lo; eb < hi; eb += 4 * CB_WARP) {
+                double v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = eb + j * CB_WARP + lane;
+                    v[j] = e < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e)) : pivot;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double d = v[j] - pivot;      // padding lanes contribute exactly 0
+                    s += d;
+                    q = fma(d, d, q);
+                }
             }
+            s = cx.warp_sum(s);
             q = cx.warp_sum(q);
+            const double cnt = (double)(hi - lo);
+            const double md = s / cnt;                  // mean - pivot
+            const double mean = pivot + md;
+            q -= s * md;                                // sum (x - mean)^2
+            if (q < 0.0) q = 0.0;                       // (a nan stays a nan)
             if (lane == 0) {
                 P.phi[w * P.nbins + b] = P.power * mean;
                 P.sigma[w * P.nbins + b] = fabs(P.power) * sqrt(q / cnt);

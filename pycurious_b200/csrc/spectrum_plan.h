@@ -17,7 +17,7 @@ struct SpectrumHostPlan {
     std::vector<int32_t> bin_ptr, bin_idx;
     int nnz_full = 0;
     // shared memory layout (double2 slots) and launch shape
-    int sm_tw = 0, sm_filt = 0, sm_chirp = 0, sm_buf = 0, line_slots = 0;
+    int sm_tw = 0, sm_filt = 0, sm_chirp = 0, sm_cw = 0, sm_buf = 0, line_slots = 0;
     int teams = 0, threads = 0;
     int64_t smem_bytes = 0;
     int64_t gt_stride = 0, lh_stride = 0, ws_per_cta = 0;
@@ -68,7 +68,8 @@ static inline void fold_bins(int n, int nbins, const int32_t *ptr, const int32_t
 
 static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nbins, const double *taper_r,
                                             const double *taper_c, const int32_t *bin_ptr,
-                                            const int32_t *bin_idx, int64_t smem_limit_bytes) {
+                                            const int32_t *bin_idx, int64_t smem_limit_bytes,
+                                            int max_teams = CB_SPEC_MAX_TEAMS) {
     if (nw < 4 || nw > 16384) { hp.error = "window edge must be in [4, 16384]"; return false; }
     if (nbins < 1) { hp.error = "nbins must be >= 1"; return false; }
     hp.n = nw;
@@ -101,9 +102,10 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
     hp.sm_tw = CB_SPEC_RED_SLOTS;
     hp.sm_filt = hp.sm_tw + hp.fft.tw_count;
     hp.sm_chirp = hp.sm_filt + (hp.bluestein ? hp.line_slots : 0);
-    hp.sm_buf = hp.sm_chirp + (hp.bluestein ? nw : 0);
+    hp.sm_cw = hp.sm_chirp + (hp.bluestein ? nw : 0);
+    hp.sm_buf = hp.sm_cw + nw;
     int64_t slots_avail = smem_limit_bytes / 16 - hp.sm_buf;
-    int teams = (int)std::min<int64_t>(CB_SPEC_MAX_TEAMS, slots_avail / hp.line_slots);
+    int teams = (int)std::min<int64_t>(max_teams, slots_avail / hp.line_slots);
     if (teams < 1) { hp.error = "window too large for the shared-memory FFT line"; return false; }
     teams = std::min(teams, std::max(1, hp.nvh));
     hp.teams = teams;
@@ -127,6 +129,6 @@ static inline void spectrum_fill_params(const SpectrumHostPlan &hp, SpectrumPara
     P.taper_c = hp.has_taper ? taper_c : nullptr;
     P.bin_ptr = bin_ptr; P.bin_idx = bin_idx; P.nbins = hp.nbins;
     P.gt_stride = hp.gt_stride; P.lh_stride = hp.lh_stride;
-    P.sm_tw = hp.sm_tw; P.sm_filt = hp.sm_filt; P.sm_chirp = hp.sm_chirp; P.sm_buf = hp.sm_buf;
+    P.sm_tw = hp.sm_tw; P.sm_filt = hp.sm_filt; P.sm_chirp = hp.sm_chirp; P.sm_cw = hp.sm_cw; P.sm_buf = hp.sm_buf;
     P.line_slots = hp.line_slots;
 }
