@@ -226,3 +226,240 @@ CB_BODY void bluestein_convolve(const Ctx &cx, double2 *buf, const double2 *tw, 
     }
     cx.sync_warp();
 }
+
+// =====================================================================================
+// Static engine: the same passes with every radix / stride a compile-time constant.
+// The generic engine above spends as many issue slots on index arithmetic (fastdiv, CB_PAD,
+// runtime strides: IMAD + LEA = 24 % of the spectrum kernel's instructions, ncu r01e) as on FP64
+// work; with the pass list in the template all of it folds into immediates and the butterfly
+// loops unroll.  Selected on the host for the pass lists the BASELINE window sizes produce
+// (201 -> 512 = 8.8.8, 101 -> 256 = 8.8.4, 129 -> 320 = 8.8.5, 301 -> 625 = 5.5.5.5); anything
+// else runs the generic engine.  Table layouts (twiddles, filter) are identical.
+// =====================================================================================
+// w[s] = w1^s, s = 1..R-1, by at most three dependent complex products (<= 4 ulp): the static
+// engine loads ONE twiddle per butterfly instead of R-1 -- the kernel is shared-memory-bandwidth
+// bound (78 % of the 128 B/clk pipe, ncu r01e), the FP64 pipe has the headroom.
+template <int R> CB_HD void tw_powers(double2 w1, double2 *w) {
+    w[1] = w1;
+#pragma unroll
+    for (int s = 2; s < R; ++s) w[s] = (s % 2 == 0) ? cmul(w[s / 2], w[s / 2]) : cmul(w[s - 1], w1);
+}
+
+// Radix-8 butterfly whose inputs v[4..7] are zero (first Bluestein pass: the line is zero padded
+// beyond n <= N/2):  y_s = E_s + w^s O_s, y_{s+4} = E_s - w^s O_s with E_s = v0 + (-i)^s v2,
+// O_s = v1 + (-i)^s v3.
+CB_HD void dft8_half_in(double2 *v) {
+    const double H = 0.70710678118654752440;
+    const double2 e0 = cadd(v[0], v[2]), e2 = csub(v[0], v[2]);
+    const double2 e1 = cadd(v[0], cmul_mi(v[2])), e3 = cadd(v[0], cmul_pi(v[2]));
+    const double2 o0 = cadd(v[1], v[3]), o2 = csub(v[1], v[3]);
+    const double2 o1 = cadd(v[1], cmul_mi(v[3])), o3 = cadd(v[1], cmul_pi(v[3]));
+    const double2 t0 = o0;
+    const double2 t1 = cplx(H * (o1.x + o1.y), H * (o1.y - o1.x));     // o1 * exp(-i pi/4)
+    const double2 t2 = cmul_mi(o2);
+    const double2 t3 = cplx(H * (o3.y - o3.x), -H * (o3.x + o3.y));    // o3 * exp(-3i pi/4)
+    v[0] = cadd(e0, t0); v[4] = csub(e0, t0);
+    v[1] = cadd(e1, t1); v[5] = csub(e1, t1);
+    v[2] = cadd(e2, t2); v[6] = csub(e2, t2);
+    v[3] = cadd(e3, t3); v[7] = csub(e3, t3);
+}
+
+// Radix-8 butterfly of which only the outputs y_0..y_3 are wanted (last Bluestein pass: only the
+// first n <= N/2 points of the convolution are read).
+CB_HD void dft8_half_out(double2 *v) {
+    const double H = 0.70710678118654752440;
+    double2 e[4] = {v[0], v[2], v[4], v[6]};
+    double2 o[4] = {v[1], v[3], v[5], v[7]};
+    Dft<4>::run(e);
+    Dft<4>::run(o);
+    const double2 o1 = cplx(H * (o[1].x + o[1].y), H * (o[1].y - o[1].x));
+    const double2 o2 = cmul_mi(o[2]);
+    const double2 o3 = cplx(H * (o[3].y - o[3].x), -H * (o[3].x + o[3].y));
+    v[0] = cadd(e[0], o[0]);
+    v[1] = cadd(e[1], o1);
+    v[2] = cadd(e[2], o2);
+    v[3] = cadd(e[3], o3);
+}
+
+template <int R0, int R1, int R2, int R3 = 1>
+struct StaticFft {
+    static constexpr int N = R0 * R1 * R2 * R3;
+    static constexpr int NPASS = (R3 > 1) ? 4 : 3;
+    template <int P> struct Pass {
+        static constexpr int R = P == 0 ? R0 : (P == 1 ? R1 : (P == 2 ? R2 : R3));
+        static constexpr int LEN = P == 0 ? N : (P == 1 ? N / R0 : (P == 2 ? N / (R0 * R1) : N / (R0 * R1 * R2)));
+        static constexpr int SUB = LEN / R;
+        // offset of this pass' twiddle table (layout of cbplan::build_fft_plan: passes with sub > 1 only)
+        static constexpr int TW = (P > 0 ? (R0 - 1) * (N / R0) : 0) + (P > 1 ? (R1 - 1) * (N / (R0 * R1)) : 0) +
+                                  (P > 2 ? (R2 - 1) * (N / (R0 * R1 * R2)) : 0);
+    };
+    static bool matches(const FftPlan &pl) {
+        if (pl.n != N || pl.npass != NPASS) return false;
+        const int r[4] = {R0, R1, R2, R3};
+        int off = 0;
+        for (int p = 0; p < NPASS; ++p) {
+            if (pl.pass[p].radix != r[p]) return false;
+            if (pl.pass[p].sub > 1) {
+                if (pl.pass[p].tw_off != off) return false;
+                off += (r[p] - 1) * pl.pass[p].sub;
+            }
+        }
+        return true;
+    }
+
+    // slot of element i0 + t*SUB given i0 (SUB % 8 == 0 keeps the pad linear in t)
+    template <int SUB> CB_HD static int slot(int i0, int pad0, int t) {
+        if (SUB % 8 == 0) return pad0 + t * (SUB + SUB / 8);
+        return CB_PAD(i0 + t * SUB);
+    }
+
+    template <int P, bool DIT> CB_HD static void pass(double2 *buf, const double2 *tw, int lane) {
+        constexpr int R = Pass<P>::R, LEN = Pass<P>::LEN, SUB = Pass<P>::SUB, NB = N / R;
+        const double2 *w0 = tw + Pass<P>::TW;
+#pragma unroll
+        for (int b0 = 0; b0 < NB; b0 += CB_WARP) {
+            const int b = b0 + lane;
+            if (NB % CB_WARP != 0 && b >= NB) break;
+            const int blk = b / SUB, j = b - blk * SUB;
+            const int i0 = blk * LEN + j, pad0 = CB_PAD(i0);
+            double2 v[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t] = buf[slot<SUB>(i0, pad0, t)];
+            double2 w[R];
+            if (SUB > 1) tw_powers<R>(w0[j], w);
+            if (DIT && SUB > 1) {
+#pragma unroll
+                for (int t = 1; t < R; ++t) v[t] = cmul(v[t], w[t]);
+            }
+            Dft<R>::run(v);
+            if (!DIT && SUB > 1) {
+#pragma unroll
+                for (int s = 1; s < R; ++s) v[s] = cmul(v[s], w[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < R; ++s) buf[slot<SUB>(i0, pad0, s)] = v[s];
+        }
+    }
+
+    // fused: last DIF pass (sub == 1) -> * filter -> conj -> first DIT pass
+    CB_HD static void mid(double2 *buf, const double2 *filt, int lane) {
+        constexpr int R = Pass<NPASS - 1>::R, NB = N / R;
+#pragma unroll
+        for (int b0 = 0; b0 < NB; b0 += CB_WARP) {
+            const int b = b0 + lane;
+            if (NB % CB_WARP != 0 && b >= NB) break;
+            const int i0 = b * R;
+            double2 v[R];
+            int sl[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) sl[t] = (R == 8) ? 9 * b + t : CB_PAD(i0 + t);
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t] = buf[sl[t]];
+            Dft<R>::run(v);
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t] = cconj(cmul(v[t], filt[sl[t]]));
+            Dft<R>::run(v);
+#pragma unroll
+            for (int t = 0; t < R; ++t) buf[sl[t]] = v[t];
+        }
+    }
+
+    // Pruned first / last passes with the line's input and output fused in (no fill pass, no zero
+    // padding in memory, no read-back pass):
+    //   first: element x of the line comes from ld(x), x < HALF*SUB only (the rest is zero padding)
+    //   last : output k of the convolution goes to sk(k, value), k < HALF*SUB only
+    static constexpr int HALF = (R0 + 1) / 2;            // inputs / outputs per butterfly that can be live
+    static constexpr int FUSED_SPAN = HALF * (N / R0);   // the engine serves windows with n <= FUSED_SPAN
+
+    template <class Loader> CB_HD static void first_pass(double2 *buf, const double2 *tw, int lane, Loader ld) {
+        constexpr int R = R0, SUB = N / R0, NB = N / R;
+#pragma unroll
+        for (int b0 = 0; b0 < NB; b0 += CB_WARP) {
+            const int j = b0 + lane;                     // LEN == N: blk = 0
+            if (NB % CB_WARP != 0 && j >= NB) break;
+            double2 v[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t] = t < HALF ? ld(j + t * SUB) : cplx(0.0, 0.0);
+            if (R == 8) dft8_half_in(v);
+            else Dft<R>::run(v);
+            double2 w[R];
+            tw_powers<R>(tw[j], w);
+#pragma unroll
+            for (int s = 1; s < R; ++s) v[s] = cmul(v[s], w[s]);
+            const int pad0 = CB_PAD(j);
+#pragma unroll
+            for (int s = 0; s < R; ++s) buf[slot<SUB>(j, pad0, s)] = v[s];
+        }
+    }
+
+    template <class Sink> CB_HD static void last_pass(double2 *buf, const double2 *tw, int lane, Sink sk) {
+        constexpr int R = R0, SUB = N / R0, NB = N / R;
+#pragma unroll
+        for (int b0 = 0; b0 < NB; b0 += CB_WARP) {
+            const int j = b0 + lane;
+            if (NB % CB_WARP != 0 && j >= NB) break;
+            const int pad0 = CB_PAD(j);
+            double2 v[R], w[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t] = buf[slot<SUB>(j, pad0, t)];
+            tw_powers<R>(tw[j], w);
+#pragma unroll
+            for (int t = 1; t < R; ++t) v[t] = cmul(v[t], w[t]);
+            if (R == 8) dft8_half_out(v);
+            else Dft<R>::run(v);
+#pragma unroll
+            for (int s = 0; s < HALF; ++s) sk(j + s * SUB, v[s]);
+        }
+    }
+
+    // conj((a (*) b)[k]) -> sk(k, .) for k < FUSED_SPAN, with a[x] = ld(x) (zero beyond FUSED_SPAN).
+    // The caller guarantees that no lane still reads buf (one warp barrier is issued first).
+    template <class Ctx, class Loader, class Sink>
+    CB_BODY static void convolve_io(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, int lane,
+                                    Loader ld, Sink sk) {
+        cx.sync_warp();
+        first_pass(buf, tw, lane, ld);
+        cx.sync_warp();
+        if (NPASS > 2) { pass<1, false>(buf, tw, lane); cx.sync_warp(); }
+        if (NPASS > 3) { pass<2, false>(buf, tw, lane); cx.sync_warp(); }
+        mid(buf, filt, lane);
+        cx.sync_warp();
+        if (NPASS > 3) { pass<2, true>(buf, tw, lane); cx.sync_warp(); }
+        if (NPASS > 2) { pass<1, true>(buf, tw, lane); cx.sync_warp(); }
+        last_pass(buf, tw, lane, sk);
+    }
+
+    template <class Ctx>
+    CB_BODY static void convolve(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, const FftPlan &,
+                                 int lane) {
+        cx.sync_warp();
+        pass<0, false>(buf, tw, lane);
+        cx.sync_warp();
+        if (NPASS > 2) { pass<1, false>(buf, tw, lane); cx.sync_warp(); }
+        if (NPASS > 3) { pass<2, false>(buf, tw, lane); cx.sync_warp(); }
+        mid(buf, filt, lane);
+        cx.sync_warp();
+        if (NPASS > 3) { pass<2, true>(buf, tw, lane); cx.sync_warp(); }
+        if (NPASS > 2) { pass<1, true>(buf, tw, lane); cx.sync_warp(); }
+        pass<0, true>(buf, tw, lane);
+        cx.sync_warp();
+    }
+    template <class Ctx>
+    CB_BODY static void forward(const Ctx &cx, double2 *buf, const double2 *tw, const FftPlan &pl, int lane) {
+        fft_forward_dif(cx, buf, tw, pl, lane);      // direct (smooth) sizes are not the hot case
+    }
+};
+
+struct GenericFft {
+    static constexpr int FUSED_SPAN = 0;                  // no fused-I/O path
+    static bool matches(const FftPlan &) { return true; }
+    template <class Ctx>
+    CB_BODY static void convolve(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, const FftPlan &pl,
+                                 int lane) {
+        bluestein_convolve(cx, buf, tw, filt, pl, lane);
+    }
+    template <class Ctx>
+    CB_BODY static void forward(const Ctx &cx, double2 *buf, const double2 *tw, const FftPlan &pl, int lane) {
+        fft_forward_dif(cx, buf, tw, pl, lane);
+    }
+};

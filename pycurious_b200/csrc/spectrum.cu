@@ -5,20 +5,43 @@
 #include <new>
 #include "spectrum_plan.h"
 
+typedef void (*spectrum_kernel_fn)(const SpectrumParams);
+
 struct cb_spectrum_plan {
     SpectrumHostPlan hp;
     int device = 0, sm_count = 0, occupancy = 1, grid_max = 0;
     double2 *d_tw = nullptr, *d_chirp = nullptr, *d_filt = nullptr;
     int32_t *d_slot = nullptr, *d_bin_ptr = nullptr, *d_bin_idx = nullptr;
     double *d_taper_r = nullptr, *d_taper_c = nullptr;
+    spectrum_kernel_fn kernel = nullptr;
+    const char *engine = "generic";
 };
 
 extern __shared__ double2 cb_dyn_smem[];
 
+template <class Engine>
 __global__ void __launch_bounds__(CB_SPEC_MAX_TEAMS * CB_WARP, 1)
 spectrum_kernel(const __grid_constant__ SpectrumParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem)};
-    spectrum_body(cx, P);
+    spectrum_body<Engine>(cx, P);
+}
+
+// FFT engines compiled in: static pass lists for the Bluestein lengths of the BASELINE window sizes,
+// the generic runtime-radix engine for everything else.
+typedef StaticFft<8, 8, 8> Fft512;      // nw 201 (and 129..256 that pad to 512)
+typedef StaticFft<8, 8, 4> Fft256;      // nw 101
+typedef StaticFft<8, 8, 5> Fft320;      // nw 129
+typedef StaticFft<5, 5, 5, 5> Fft625;   // nw 301
+
+static spectrum_kernel_fn pick_spectrum_kernel(const SpectrumHostPlan &hp, const char **name) {
+    if (hp.bluestein) {
+        if (Fft512::matches(hp.fft) && hp.n <= Fft512::FUSED_SPAN) { *name = "static 8.8.8"; return spectrum_kernel<Fft512>; }
+        if (Fft256::matches(hp.fft) && hp.n <= Fft256::FUSED_SPAN) { *name = "static 8.8.4"; return spectrum_kernel<Fft256>; }
+        if (Fft320::matches(hp.fft) && hp.n <= Fft320::FUSED_SPAN) { *name = "static 8.8.5"; return spectrum_kernel<Fft320>; }
+        if (Fft625::matches(hp.fft) && hp.n <= Fft625::FUSED_SPAN) { *name = "static 5.5.5.5"; return spectrum_kernel<Fft625>; }
+    }
+    *name = "generic";
+    return spectrum_kernel<GenericFft>;
 }
 
 __global__ void __launch_bounds__(256) detrend_kernel(const __grid_constant__ DetrendParams P) {
@@ -79,7 +102,9 @@ int cb_spectrum_plan_create(int nw, int nbins, const double *taper_r, const doub
 #undef UP
     // the attribute belongs to the kernel, not to the plan: raise it once to the device limit so that
     // plans with different line lengths can coexist
-    cudaError_t e = cudaFuncSetAttribute(spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    pl->kernel = pick_spectrum_kernel(hp, &pl->engine);
+    if (getenv("CB_SPEC_GENERIC")) { pl->kernel = spectrum_kernel<GenericFft>; pl->engine = "generic"; }
+    cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)prop.sharedMemPerBlockOptin);
     if (e != cudaSuccess) {
         cb_set_error("cudaFuncSetAttribute(smem=%lld): %s", (long long)prop.sharedMemPerBlockOptin, cudaGetErrorString(e));
@@ -87,7 +112,7 @@ int cb_spectrum_plan_create(int nw, int nbins, const double *taper_r, const doub
         return CB_ERR_CUDA;
     }
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spectrum_kernel, hp.threads, (size_t)hp.smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pl->kernel, hp.threads, (size_t)hp.smem_bytes);
     if (e != cudaSuccess || occ < 1) {
         cb_set_error("spectrum kernel does not fit an SM (threads=%d smem=%lld): %s", hp.threads,
                      (long long)hp.smem_bytes, cudaGetErrorString(e));
@@ -151,7 +176,7 @@ int cb_spectrum_batch(const cb_spectrum_plan *plan, const double *grid_dev, int6
     P.phi = phi_dev; P.sigma = sigma_dev;
     P.gt = reinterpret_cast<double2 *>(base);
     P.lh = reinterpret_cast<double *>(base + (uintptr_t)grid * (uintptr_t)hp.gt_stride * 16);
-    spectrum_kernel<<<grid, hp.threads, (size_t)hp.smem_bytes, (cudaStream_t)stream>>>(P);
+    plan->kernel<<<grid, hp.threads, (size_t)hp.smem_bytes, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }

@@ -54,7 +54,7 @@ CB_HD double2 bluestein_out(const double2 *buf, const double2 *chirp, int k) {
     return cmul(chirp[k], cconj(buf[CB_PAD(k)]));
 }
 
-template <class Ctx>
+template <class Engine, class Ctx>
 CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
     const int tid = cx.tid(), nthr = cx.nthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
@@ -126,34 +126,58 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
             const double t0 = P.taper_r ? Ctx::ldg(P.taper_r + y0) : 1.0;
             const double t1 = (P.taper_r && has1) ? Ctx::ldg(P.taper_r + y1) : 1.0;
             const double pl0 = c0 + cy1 * ((double)y0 - ctr), pl1 = c0 + cy1 * ((double)y1 - ctr);
-            // all global loads of a chunk are issued before the first use (4 x 2 loads in flight per lane)
-            for (int xb = 0; xb < n; xb += 4 * CB_WARP) {
-                double a[4], b[4];
+            bool fused = false;
+            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+                fused = true;
+                // the first FFT pass pulls its inputs straight from the grid (coalesced: lane j reads
+                // x = j + t*SUB), the last one leaves the n live outputs in the line
+                auto ld = [&](int x) -> double2 {
+                    if (x >= n) return cplx(0.0, 0.0);
+                    double av = Ctx::ldg(r0 + x);
+                    double bv = has1 ? Ctx::ldg(r1 + x) : 0.0;
+                    if (P.detrend) {
+                        const double px = cx1 * ((double)x - ctr);
+                        av -= pl0 + px;
+                        bv = has1 ? bv - (pl1 + px) : 0.0;
+                    }
+                    return cmul(cplx(av * t0, bv * t1), s_cw[x]);
+                };
+                auto sk = [&](int k, double2 z) {
+                    if (k < n) buf[CB_PAD(k)] = z;
+                };
+                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+                cx.sync_warp();
+            }
+            if (!fused) {
+                // all global loads of a chunk are issued before the first use (4 x 2 loads in flight per lane)
+                for (int xb = 0; xb < n; xb += 4 * CB_WARP) {
+                    double a[4], b[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int x = xb + j * CB_WARP + lane;
-                    a[j] = x < n ? Ctx::ldg(r0 + x) : 0.0;
-                    b[j] = (x < n && has1) ? Ctx::ldg(r1 + x) : 0.0;
-                }
+                    for (int j = 0; j < 4; ++j) {
+                        const int x = xb + j * CB_WARP + lane;
+                        a[j] = x < n ? Ctx::ldg(r0 + x) : 0.0;
+                        b[j] = (x < n && has1) ? Ctx::ldg(r1 + x) : 0.0;
+                    }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int x = xb + j * CB_WARP + lane;
-                    if (x < n) {
-                        double av = a[j], bv = b[j];
-                        if (P.detrend) {
-                            const double px = cx1 * ((double)x - ctr);
-                            av -= pl0 + px;
-                            bv = has1 ? bv - (pl1 + px) : 0.0;
+                    for (int j = 0; j < 4; ++j) {
+                        const int x = xb + j * CB_WARP + lane;
+                        if (x < n) {
+                            double av = a[j], bv = b[j];
+                            if (P.detrend) {
+                                const double px = cx1 * ((double)x - ctr);
+                                av -= pl0 + px;
+                                bv = has1 ? bv - (pl1 + px) : 0.0;
+                            }
+                            // s_cw = column taper (x chirp for Bluestein), staged once per CTA
+                            const double2 cw = s_cw[x];
+                            buf[CB_PAD(x)] = P.bluestein ? cmul(cplx(av * t0, bv * t1), cw) : cplx(av * t0 * cw.x, bv * t1 * cw.x);
                         }
-                        // s_cw = column taper (x chirp for Bluestein), staged once per CTA
-                        const double2 cw = s_cw[x];
-                        buf[CB_PAD(x)] = P.bluestein ? cmul(cplx(av * t0, bv * t1), cw) : cplx(av * t0 * cw.x, bv * t1 * cw.x);
                     }
                 }
+                for (int x = n + lane; x < M; x += CB_WARP) buf[CB_PAD(x)] = cplx(0.0, 0.0);
+                if (P.bluestein) Engine::convolve(cx, buf, s_tw, s_filt, P.fft, lane);
+                else Engine::forward(cx, buf, s_tw, P.fft, lane);
             }
-            for (int x = n + lane; x < M; x += CB_WARP) buf[CB_PAD(x)] = cplx(0.0, 0.0);
-            if (P.bluestein) bluestein_convolve(cx, buf, s_tw, s_filt, P.fft, lane);
-            else fft_forward_dif(cx, buf, s_tw, P.fft, lane);
             // untangle: row y0 spectrum A[v] = (Z[v] + conj Z[-v])/2, row y1: B[v] = (Z[v] - conj Z[-v])/(2i)
             for (int v = lane; v < nvh; v += CB_WARP) {
                 const int vm = v ? n - v : 0;
@@ -178,27 +202,42 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
         // ---- phase B: columns -------------------------------------------------------------------
         for (int v = warp; v < nvh; v += nwarps) {
             const double2 *col = Gt + (int64_t)v * npad;
-            for (int yb = 0; yb < n; yb += 4 * CB_WARP) {
-                double2 z[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int y = yb + j * CB_WARP + lane;
-                    z[j] = y < n ? Ctx::ldcg(col + y) : cplx(0.0, 0.0);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int y = yb + j * CB_WARP + lane;
-                    if (y < n) buf[CB_PAD(y)] = P.bluestein ? cmul(z[j], s_chirp[y]) : z[j];
-                }
-            }
-            for (int y = n + lane; y < M; y += CB_WARP) buf[CB_PAD(y)] = cplx(0.0, 0.0);
-            if (P.bluestein) bluestein_convolve(cx, buf, s_tw, s_filt, P.fft, lane);
-            else fft_forward_dif(cx, buf, s_tw, P.fft, lane);
             double *out = Lh + (int64_t)v * n;
-            for (int u = lane; u < n; u += CB_WARP) {
-                // |chirp| = 1, so the modulus needs no post-multiply
-                const double2 z = P.bluestein ? buf[CB_PAD(u)] : buf[CB_PAD(Ctx::ldg(P.slot + u))];
-                Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+            bool fused = false;
+            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+                fused = true;
+                auto ld = [&](int y) -> double2 {
+                    if (y >= n) return cplx(0.0, 0.0);
+                    return cmul(Ctx::ldcg(col + y), s_chirp[y]);
+                };
+                // |chirp| = 1, so the modulus needs no post-multiply; outputs go straight to the slab
+                auto sk = [&](int u, double2 z) {
+                    if (u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                };
+                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+            }
+            if (!fused) {
+                for (int yb = 0; yb < n; yb += 4 * CB_WARP) {
+                    double2 z[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int y = yb + j * CB_WARP + lane;
+                        z[j] = y < n ? Ctx::ldcg(col + y) : cplx(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int y = yb + j * CB_WARP + lane;
+                        if (y < n) buf[CB_PAD(y)] = P.bluestein ? cmul(z[j], s_chirp[y]) : z[j];
+                    }
+                }
+                for (int y = n + lane; y < M; y += CB_WARP) buf[CB_PAD(y)] = cplx(0.0, 0.0);
+                if (P.bluestein) Engine::convolve(cx, buf, s_tw, s_filt, P.fft, lane);
+                else Engine::forward(cx, buf, s_tw, P.fft, lane);
+                for (int u = lane; u < n; u += CB_WARP) {
+                    // |chirp| = 1, so the modulus needs no post-multiply
+                    const double2 z = P.bluestein ? buf[CB_PAD(u)] : buf[CB_PAD(Ctx::ldg(P.slot + u))];
+                    Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                }
             }
             cx.sync_warp();
         }

@@ -78,6 +78,10 @@ int emu_dft(int n, const double *in_re_im, double *out_re_im) {
             line[CB_PAD(x)] = z;
         }
         if (direct) fft_forward_dif(cx, line.data(), tw.data(), fft, lane);
+        else if (StaticFft<8, 8, 8>::matches(fft)) StaticFft<8, 8, 8>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
+        else if (StaticFft<8, 8, 4>::matches(fft)) StaticFft<8, 8, 4>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
+        else if (StaticFft<8, 8, 5>::matches(fft)) StaticFft<8, 8, 5>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
+        else if (StaticFft<5, 5, 5, 5>::matches(fft)) StaticFft<5, 5, 5, 5>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
         else bluestein_convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
         for (int k = lane; k < n; k += 32) {
             double2 z = direct ? line[CB_PAD(slot[k])] : bluestein_out(line.data(), chirp.data(), k);
@@ -97,9 +101,10 @@ int emu_spectrum(int nw, int nbins, const double *taper_r, const double *taper_c
         fprintf(stderr, "emu_spectrum: %s\n", hp.error.c_str());
         return -1;
     }
-    if (max_teams > 0 && hp.teams > max_teams) {
-        hp.teams = max_teams;
-        hp.threads = 32 * max_teams;
+    const int mt = max_teams < 0 ? -max_teams : max_teams;
+    if (mt > 0 && hp.teams > mt) {
+        hp.teams = mt;
+        hp.threads = 32 * mt;
         hp.smem_bytes = 16 * ((int64_t)hp.sm_buf + (int64_t)hp.teams * hp.line_slots);
     }
     SpectrumParams P;
@@ -111,7 +116,18 @@ int emu_spectrum(int nw, int nbins, const double *taper_r, const double *taper_c
     std::vector<double2> gt((size_t)nblocks * hp.gt_stride);
     std::vector<double> lh((size_t)nblocks * hp.lh_stride);
     P.gt = gt.data(); P.lh = lh.data();
-    emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body(cx, P); });
+    // same engine selection as the product (spectrum.cu:pick_spectrum_kernel); max_teams < 0 forces the generic engine
+    const bool generic = max_teams < 0 || !hp.bluestein;
+    if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN)
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 8>>(cx, P); });
+    else if (!generic && StaticFft<8, 8, 4>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 4>::FUSED_SPAN)
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 4>>(cx, P); });
+    else if (!generic && StaticFft<8, 8, 5>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 5>::FUSED_SPAN)
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 5>>(cx, P); });
+    else if (!generic && StaticFft<5, 5, 5, 5>::matches(hp.fft) && hp.n <= StaticFft<5, 5, 5, 5>::FUSED_SPAN)
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<5, 5, 5, 5>>(cx, P); });
+    else
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<GenericFft>(cx, P); });
     return 0;
 }
 

@@ -84,6 +84,7 @@ def _bins(oracle, nr, dx=1000.0):
 
 
 def _emu_spectrum(emu, oracle, grid, origins, nw, taper, detrend, power, nblocks=1, max_teams=4):
+    """max_teams < 0 forces the generic FFT engine with |max_teams| teams."""
     ptr, idx = _bins(oracle, nw)
     nb = ptr.size - 1
     tr = None if taper is None else np.ascontiguousarray(taper(nw), dtype=np.float64)
@@ -117,6 +118,21 @@ def test_spectrum_body_matches_oracle(emu, oracle, mag, nw, taper, det, power, o
         _, p0, s0 = oracle.radial_spectrum(win, 1000.0, taper=taper, power=power)
         np.testing.assert_allclose(phi[w], p0, rtol=1e-11)
         np.testing.assert_allclose(sig[w], s0, rtol=1e-9)
+
+
+def test_spectrum_static_and_generic_engines_agree(emu, oracle, mag):
+    """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 5.5.5.5) against the runtime-radix engine."""
+    d = np.ascontiguousarray(mag[0])
+    for nw in (101, 129, 201, 301):
+        origins = [(2, 3)]
+        a = _emu_spectrum(emu, oracle, d, origins, nw, np.hanning, 0, 2.0, max_teams=4)
+        b = _emu_spectrum(emu, oracle, d, origins, nw, np.hanning, 0, 2.0, max_teams=-4)
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-12)
+        np.testing.assert_allclose(a[1], b[1], rtol=1e-10)
+        win = d[2:2 + nw, 3:3 + nw]
+        _, p0, s0 = oracle.radial_spectrum(win, 1000.0, taper=np.hanning, power=2.0)
+        np.testing.assert_allclose(a[0][0], p0, rtol=1e-11)
+        np.testing.assert_allclose(a[1][0], s0, rtol=1e-9)
 
 
 def test_detrend_body(emu, oracle, mag):
