@@ -139,12 +139,14 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
  * One window per warp; bounded quasi-Newton (projected BFGS seeded with the
  * Gauss-Newton metric) on min_func.
  * ---------------------------------------------------------------------- */
+#define CB_FIT_FLAG_LINEAR_DZ 1   /* iterate in dz itself instead of u = exp(-2 k_min dz) */
 typedef struct cb_fit_options {
     double x0[4];            /* start (beta, zt, dz, C), used when x0_dev == NULL */
     double lb[4], ub[4];     /* bounds, +-INFINITY = unbounded (self.bounds, optimise.py:111-114) */
     double prior_mu[4];      /* NaN = no prior on that parameter (optimise.py:120-150) */
     double prior_sigma[4];
     int32_t max_iter;        /* 0 -> default 200 */
+    int32_t flags;           /* CB_FIT_FLAG_*; 0 = defaults */
     double gtol;             /* projected-gradient inf-norm tolerance, 0 -> 1e-9 */
     double ftol;             /* relative decrease tolerance, 0 -> 1e-15 */
 } cb_fit_options;

@@ -32,7 +32,7 @@ class SpectrumPlanInfo(C.Structure):
 class FitOptions(C.Structure):
     _fields_ = [("x0", C.c_double * 4), ("lb", C.c_double * 4), ("ub", C.c_double * 4),
                 ("prior_mu", C.c_double * 4), ("prior_sigma", C.c_double * 4),
-                ("max_iter", C.c_int32), ("gtol", C.c_double), ("ftol", C.c_double)]
+                ("max_iter", C.c_int32), ("flags", C.c_int32), ("gtol", C.c_double), ("ftol", C.c_double)]
 
 
 class MhOptions(C.Structure):

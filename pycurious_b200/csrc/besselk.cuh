@@ -17,6 +17,7 @@
 #define CB_PI 3.14159265358979323846264338327950288
 #define CB_KNU_EPS 1.0e-16
 #define CB_KNU_MAXIT 400
+#define CB_KNU_MAX_ORDER 2000
 
 // Code-size discipline: the fit / MCMC kernels run ~16 independent warps per SM through this code,
 // each at a different place, and the SM's instruction cache holds 32 KB.  Helpers that are used from
@@ -98,9 +99,12 @@ CB_HD KnuOrder knu_order(double nu_signed) {
         // use the order -nu in (-1/2, 0]: K_mu = K_nu and K_{mu+1} = K_{nu-1}
         o.nl = 0;
         o.mu = -o.nu;
-    } else {
+    } else if (o.nu < 1.0e6) {
         o.nl = (int)floor(o.nu + 0.5);
         o.mu = o.nu - (double)o.nl;
+    } else {                      // absurd orders (a runaway trial step): K overflows, see knu_pair
+        o.nl = 1000000;
+        o.mu = 0.0;
     }
     double e, od;
     cb_rgamma_parts(o.mu, e, od);
@@ -177,6 +181,12 @@ CB_HD void knu_steed_cf2(const KnuOrder &o, double x, double &kmu, double &kmu1)
 CB_HD void knu_pair(const KnuOrder &o, double x, double &k_nu, double &k_num1) {
     if (!(x > 0.0)) {
         k_nu = k_num1 = (x == 0.0) ? INFINITY : NAN;
+        return;
+    }
+    if (o.nl > CB_KNU_MAX_ORDER || isnan(o.nu)) {
+        // Gamma(nu) overflows at nu = 171.6, so the reference's bracket is already non-finite
+        // (min_func -> 1e99) far below this order; do not walk a recurrence of absurd length
+        k_nu = k_num1 = isnan(o.nu) ? NAN : INFINITY;
         return;
     }
     double a, b;

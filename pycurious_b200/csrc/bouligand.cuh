@@ -30,7 +30,14 @@ CB_HD ModelCoef model_coef(double beta, double zt, double dz, double C) {
     m.beta = beta; m.zt = zt; m.dz = dz; m.C = C;
     m.nu = 0.5 * (1.0 + beta);
     m.ord = knu_order(m.nu);
-    m.gnu = cb_gamma(m.nu);
+    // Gamma(nu) from the 1/Gamma(1+mu) the order already holds: Gamma(mu+nl) = Gamma(1+mu) prod_{i<nl} (mu+i)
+    if (m.nu >= 0.5 && m.ord.nl >= 1 && m.ord.nl <= 12) {
+        double prod = 1.0;
+        for (int i = 1; i < m.ord.nl; ++i) prod *= m.ord.mu + (double)i;
+        m.gnu = prod / m.ord.gampl;
+    } else {
+        m.gnu = cb_gamma(m.nu);
+    }
     m.lead = CB_SQRT_PI / cb_gamma(1.0 + 0.5 * beta);
     m.lhalfdz = cb_log(0.5 * dz);
     return m;

@@ -55,7 +55,9 @@ struct FitState {
     double fn, gn[4], Hn[10];     // full evaluation at the accepted trial point
     double pmu[4], pw[4];         // prior mean and inverse variance (0 = no prior)
     double one;                   // 1.0 (the dPhi/dC column of the Jacobian, read with stride 0)
-    int32_t okn, fresh, stall, status, action, it, nfev, pad_;
+    double pt[4];                 // physical parameters (beta, zt, dz, C) of the trial point
+    double cu, sdz;               // solver coordinate u = exp(-cu dz) (cu = 0: u = dz); sdz = d dz / d u at the trial point
+    int32_t okn, fresh, stall, status, action, it, nfev, mask;
 };
 #define CB_FIT_STATE_DOUBLES ((int)((sizeof(FitState) + 7) / 8))
 enum { FIT_GO = 0, FIT_DONE = 1 };
@@ -131,9 +133,27 @@ CB_HD double fit_prior_penalty(const FitState *S, const double *x) {
     return c;
 }
 
+// Solver coordinates.  The misfit valley of this model runs flat towards large dz like
+// f_inf + A exp(-2 k_0 dz) (only the lowest wavenumbers still feel the base of the layer): in dz a
+// Newton-type step on that tail has constant length 1/(2 k_0) and 30 % of the windows of a fractal
+// grid crawl for dozens of iterations.  In u = exp(-2 k_0 dz) the tail is linear, the Gauss-Newton
+// model is exact there and the step lands on the bound (the cosh wall) at once.  Bounds, priors and
+// results stay in dz; only the iteration runs in (beta, zt, u, C).
+CB_HD void fit_to_physical(FitState *S, const double *y, double *p) {
+    p[0] = y[0]; p[1] = y[1]; p[3] = y[3];
+    p[2] = S->cu > 0.0 ? -cb_log(y[2]) / S->cu : y[2];
+}
+
+CB_HD void fit_set_trial(FitState *S) {
+    fit_to_physical(S, S->xt, S->pt);
+    S->sdz = S->cu > 0.0 ? -1.0 / (S->cu * S->xt[2]) : 1.0;
+    S->hb = 1e-6 * fmax(1.0, fabs(S->pt[0]));
+    S->pen_t = fit_prior_penalty(S, S->pt);
+}
+
 // ---- lane-0 phases ------------------------------------------------------------------------------
 // Start: clip x0 into the bounds (scipy does, _lbfgsb_py.py:359) and into the cosh wall.
-CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const double *x0, double kmax) {
+CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const double *x0, double kmin, double kmax) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         S->lb[j] = o->lb[j];
@@ -147,11 +167,25 @@ CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const doubl
         while (kmax * wall > CB_COSH_OVERFLOW) wall = nextafter(wall, 0.0);
         S->ub[2] = fmin(S->ub[2], wall);
     }
+    double p[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) S->xt[j] = clampd(x0[j], S->lb[j], S->ub[j]);
-    S->hb = 1e-6 * fmax(1.0, fabs(S->xt[0]));
-    S->pen_t = fit_prior_penalty(S, S->xt);
-    S->fresh = 1; S->stall = 0; S->status = FIT_MAXITER; S->action = FIT_GO; S->it = 0; S->nfev = 0; S->pad_ = 0;
+    for (int j = 0; j < 4; ++j) p[j] = clampd(x0[j], S->lb[j], S->ub[j]);
+    // u = exp(-cu dz) needs a finite upper bound on dz (the wall) and ascending positive k
+    S->cu = (kmin > 0.0 && kmax > 0.0 && S->ub[2] < 1e300 && !(o->flags & CB_FIT_FLAG_LINEAR_DZ)) ? 2.0 * kmin : 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S->xt[j] = p[j];
+    if (S->cu > 0.0) {
+        const double dlo = S->lb[2], dhi = S->ub[2];
+        double ulo = exp(-S->cu * dhi);                       // dz = dhi  <->  smallest u
+        while (-log(ulo) / S->cu > dhi) ulo = nextafter(ulo, 1.0);
+        double uhi = dlo > -1e300 ? exp(-S->cu * dlo) : (double)INFINITY;
+        if (uhi < (double)INFINITY) while (-log(uhi) / S->cu < dlo) uhi = nextafter(uhi, 0.0);
+        S->lb[2] = ulo;
+        S->ub[2] = uhi;
+        S->xt[2] = clampd(exp(-S->cu * p[2]), ulo, uhi);
+    }
+    fit_set_trial(S);
+    S->fresh = 1; S->stall = 0; S->status = FIT_MAXITER; S->action = FIT_GO; S->it = 0; S->nfev = 0; S->mask = 0;
 }
 
 // Make the evaluated trial point the current iterate (first evaluation: B = Gauss-Newton metric).
@@ -171,24 +205,39 @@ CB_NOINLINE_BODY void fit_direction(FitState *S, double gtol) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         frozen[j] = (S->x[j] <= S->lb[j] && S->g[j] > 0.0) || (S->x[j] >= S->ub[j] && S->g[j] < 0.0);
+        // no slope and no curvature: the objective does not depend on this variable here (dz far out on
+        // the flat tail, where the Bessel term is below the rounding of the bracket) -- leave it alone
+        if (S->g[j] == 0.0 && S->H[tri(j, j)] == 0.0) frozen[j] = true;
         if (!frozen[j]) pgn = fmax(pgn, fabs(S->g[j]));
     }
     if (pgn <= gtol) { S->status = FIT_CONVERGED_PG; S->action = FIT_DONE; return; }
-#ifdef CB_FIT_TRACE
-    printf("it %3d f %.15g pgn %.3e x %.6f %.6f %.6f %.6f fresh %d nfev %d\n", S->it, S->f, pgn, S->x[0], S->x[1],
-           S->x[2], S->x[3], S->fresh, S->nfev);
-#endif
-    double d[4], gd = 0.0;
-    bool have = solve_free(S->B, S->g, frozen, d);
-    if (have) {
+    // the secant pairs were collected on another face of the box: when the active set changes, restart
+    // the metric from the Gauss-Newton matrix of this point
+    int mask = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gd += S->g[j] * d[j];
-        have = (gd < 0.0) && isfinite(gd);
+    for (int j = 0; j < 4; ++j) mask |= frozen[j] ? (1 << j) : 0;
+    if (mask != S->mask) {
+        S->mask = mask;
+        if (!S->fresh) {
+#pragma unroll
+            for (int q = 0; q < 10; ++q) S->B[q] = S->H[q];
+            S->fresh = 1;
+        }
     }
-    if (!have && !S->fresh) {        // fall back to the Gauss-Newton metric of this point
-#pragma unroll
-        for (int q = 0; q < 10; ++q) S->B[q] = S->H[q];
-        S->fresh = 1;
+#ifdef CB_FIT_TRACE
+    {
+        double pp_[4];
+        fit_to_physical(S, S->x, pp_);
+        printf("it %3d f %.15g pgn %.3e x %.6f %.6f %.6f %.6f fresh %d nfev %d\n", S->it, S->f, pgn, pp_[0], pp_[1],
+               pp_[2], pp_[3], S->fresh, S->nfev);
+    }
+#endif
+    // Direction from the quasi-Newton metric; a metric that fails (not positive definite, not a
+    // descent direction) or that predicts no measurable decrease is replaced ONCE by the
+    // Gauss-Newton matrix of this point before either conclusion is drawn.
+    double d[4], gd = 0.0;
+    bool have = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
         have = solve_free(S->B, S->g, frozen, d);
         gd = 0.0;
         if (have) {
@@ -196,6 +245,13 @@ CB_NOINLINE_BODY void fit_direction(FitState *S, double gtol) {
             for (int j = 0; j < 4; ++j) gd += S->g[j] * d[j];
             have = (gd < 0.0) && isfinite(gd);
         }
+        // Newton decrement: the model predicts a decrease of -gd/2; below the rounding noise of the
+        // objective no line search can confirm progress
+        const bool tiny = have && -gd <= 1e-13 * fmax(1.0, fabs(S->f));
+        if ((have && !tiny) || S->fresh) break;
+#pragma unroll
+        for (int q = 0; q < 10; ++q) S->B[q] = S->H[q];
+        S->fresh = 1;
     }
     if (!have) {                      // steepest descent, scaled by the diagonal
         gd = 0.0;
@@ -209,8 +265,10 @@ CB_NOINLINE_BODY void fit_direction(FitState *S, double gtol) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) S->d[j] = d[j];
     S->gd = gd;
-    // Newton decrement: the model predicts a decrease of -gd/2; below the rounding noise of the
-    // objective no line search can confirm progress, so this is convergence.
+#ifdef CB_FIT_TRACE
+    printf("      g %.3e %.3e %.3e %.3e  d %.3e %.3e %.3e %.3e  gd %.3e mask %d Hdiag %.3e %.3e %.3e %.3e Bdiag %.3e %.3e %.3e %.3e\n", S->g[0], S->g[1], S->g[2], S->g[3], d[0], d[1], d[2], d[3], gd, S->mask,
+           S->H[0], S->H[4], S->H[7], S->H[9], S->B[0], S->B[4], S->B[7], S->B[9]);
+#endif
     if (-gd <= 1e-13 * fmax(1.0, fabs(S->f))) { S->status = FIT_CONVERGED_F; S->action = FIT_DONE; }
 }
 
@@ -225,8 +283,7 @@ CB_NOINLINE_BODY void fit_trial(FitState *S, double alpha) {
     }
     S->dec = dec;
     S->move = move;
-    S->hb = 1e-6 * fmax(1.0, fabs(S->xt[0]));
-    S->pen_t = fit_prior_penalty(S, S->xt);
+    fit_set_trial(S);
 }
 
 // The line search failed: retry once from the Gauss-Newton metric, else give up.
@@ -361,10 +418,16 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
             for (int q = 0; q < 10; ++q) S->Hn[q] = 0.0;
         } else {
             S->fn += S->pen_t;
+            // chain rule for the solver coordinate of dz, then the priors (Gaussian in the physical parameters)
+            const double sd = S->sdz;
+            S->gn[2] *= sd;
+            S->Hn[tri(0, 2)] *= sd; S->Hn[tri(1, 2)] *= sd; S->Hn[tri(2, 3)] *= sd;
+            S->Hn[tri(2, 2)] *= sd * sd;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                S->gn[a] = fma(S->xt[a] - S->pmu[a], S->pw[a], S->gn[a]);
-                S->Hn[tri(a, a)] += S->pw[a];
+                const double ja = a == 2 ? sd : 1.0;
+                S->gn[a] = fma((S->pt[a] - S->pmu[a]) * ja, S->pw[a], S->gn[a]);
+                S->Hn[tri(a, a)] = fma(ja * ja, S->pw[a], S->Hn[tri(a, a)]);
             }
         }
     }
@@ -397,11 +460,12 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     const double gtol = o->gtol > 0.0 ? o->gtol : 1e-9;
     const double ftol = o->ftol > 0.0 ? o->ftol : 1e-15;
 
-    if (lane == 0) fit_init(S, o, P.x0_dev ? P.x0_dev + w * 4 : o->x0, W.sorted ? W.kmax : 0.0);
+    if (lane == 0) fit_init(S, o, P.x0_dev ? P.x0_dev + w * 4 : o->x0, W.sorted ? W.kmin : 0.0, W.sorted ? W.kmax : 0.0);
     cx.sync_warp();
+    W.cu = S->cu;
 
     // full evaluation at the start
-    model_coefs_warp(cx, W, S->xt, S->hb, 0, 3, lane);
+    model_coefs_warp(cx, W, S->pt, S->hb, 0, 3, lane);
     model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
     model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
     model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
@@ -424,7 +488,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
             cx.sync_warp();
             const double dec = S->dec;
             if (S->move == 0.0) break;
-            model_coefs_warp(cx, W, S->xt, 0.0, 0, 1, lane);
+            model_coefs_warp(cx, W, S->pt, 0.0, 0, 1, lane);
             model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
             ++nls;
             double ft = slab_half_ssq(cx, W, lane);
@@ -445,15 +509,17 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
             continue;
         }
         // derivatives at the accepted point: beta +- hb (p0 and dPhi/ddz are already staged)
-        model_coefs_warp(cx, W, S->xt, S->hb, 1, 2, lane);
+        model_coefs_warp(cx, W, S->pt, S->hb, 1, 2, lane);
         model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
         model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
         fit_reduce_full(cx, W, S, lane);
         if (lane == 0) { S->nfev += nls + 2; fit_update(S, ftol, max_iter); }
     }
     if (lane == 0) {
+        double pf[4];
+        fit_to_physical(S, S->x, pf);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) P.x_out[w * 4 + j] = S->x[j];
+        for (int j = 0; j < 4; ++j) P.x_out[w * 4 + j] = pf[j];
         if (P.f_out) P.f_out[w] = S->f;
         if (P.niter) P.niter[w] = S->it;
         if (P.status) P.status[w] = S->status;

@@ -68,7 +68,8 @@ struct WarpSlab {          // views into one warp's shared-memory slab
     double *scratch;                    // solver state (fit) behind the tables
     int nk;
     bool sorted;
-    double kmax;
+    double kmin, kmax;
+    double cu;                          // fit: solver coordinate u = exp(-cu dz) (0 = none), see fit_body.cuh
 };
 
 #define CB_SLAB_COEF_DOUBLES ((int)((sizeof(EvalCoef) + 7) / 8))
@@ -95,6 +96,8 @@ CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit) {
     W.scratch = t;
     W.sorted = false;
     W.kmax = 0.0;
+    W.kmin = 0.0;
+    W.cu = 0.0;
     return W;
 }
 
@@ -103,7 +106,7 @@ template <class Ctx>
 CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *kh, const double *phi_row, int lane) {
     const int L = cx.team_lanes();
     bool asc = true;
-    double kmax = 0.0;
+    double kmax = 0.0, kmin = INFINITY;
 #pragma unroll 1
     for (int i = lane; i < W.nk; i += L) {
         const double k = kh[i];
@@ -115,11 +118,16 @@ CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *kh, const 
         if (i + 1 < W.nk && !(kh[i + 1] > k)) asc = false;
         if (!(k > 0.0)) asc = false;
         kmax = fmax(kmax, k);
+        kmin = fmin(kmin, k);
     }
 #pragma unroll 1
     for (int n = lane; n <= CB_MILLER_NMAX; n += L) W.rn[n] = n ? 1.0 / (double)n : 0.0;
-    for (int o = 16; o > 0; o >>= 1) kmax = fmax(kmax, cx.shfl_xor(kmax, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        kmax = fmax(kmax, cx.shfl_xor(kmax, o));
+        kmin = fmin(kmin, cx.shfl_xor(kmin, o));
+    }
     W.kmax = kmax;
+    W.kmin = kmin;
     W.sorted = cx.all(asc);
     cx.sync_warp();
 }
@@ -182,11 +190,15 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
 
     // ---- classes: [0,nT) Temme, [nT,nS) Miller, [nS,nk) K negligible ---------------------------
     int lastT = -1, lastC = -1;
+    const double cudz = out_ddz ? W.cu * dz : 0.0;
 #pragma unroll 1
     for (int i = lane; i < nk; i += L) {
         const double xi = W.k[i] * dz;
         if (xi <= 2.0) lastT = i;
-        const bool skip = xi > 2.0 && (2.0 * xi - m.nu * (W.logk[i] + m.lhalfdz) + e.lgnu > CB_SKIP_LOG);
+        // the K term relative to the cosh term is ~ exp(-(2x - nu ln(x/2) + ln Gamma(nu))).  When the caller
+        // iterates in u = exp(-cu dz) the derivative d/du = -(1/(cu u)) d/ddz magnifies it by exp(cu dz):
+        // W.cu dz is taken off the exponent so that dPhi/du keeps its relative accuracy on the flat tail
+        const bool skip = xi > 2.0 && (2.0 * xi - cudz - m.nu * (W.logk[i] + m.lhalfdz) + e.lgnu > CB_SKIP_LOG);
         if (!skip) lastC = i;
     }
     const int nT = cx.warp_max_i(lastT) + 1;
@@ -320,7 +332,8 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
             const double hx = cb_exp(m.nu * (lk + m.lhalfdz));
             const double br = fma(qg, 1.0 + e2, -b * hx);
             out_phi[i] = fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * lk + cb_log(m.lead * br);
-            if (out_ddz) out_ddz[i] = k * (fma(qg, 1.0 - e2, hx * a) / br - 1.0);
+            // k [ (Gamma/4 (1 - e2) + hx K_{nu-1} e^-x) / br - 1 ] with the subtraction done analytically
+            if (out_ddz) out_ddz[i] = k * fma(hx, a + b, -2.0 * qg * e2) / br;
         }
     }
 
