@@ -112,6 +112,31 @@ int cb_spectrum_batch(const cb_spectrum_plan *plan,
                       void *workspace_dev, int64_t workspace_bytes,
                       void *stream);
 
+/*
+ * Same result as cb_spectrum_batch for windows that sit on a lattice (create_centroid_list,
+ * grid.py:159-197): windows that start at the same column ix0 share the x-transforms of the grid
+ * rows they overlap (the row taper and the detrending plane commute with that transform), so those
+ * are computed once per (distinct ix0, grid row) into `rowspec_dev` and each window only runs its
+ * column transforms and the binning.  The host supplies the grouping:
+ *   group_of_win_dev[w]   index into group_ix0_dev of window w (ix0[w] == group_ix0[group_of_win[w]])
+ *   group_ix0_dev[g]      the distinct ix0 values, ngroups of them
+ *   [row_lo, row_hi)      grid rows to transform for every group; every window needs
+ *                         row_lo <= iy0[w] and iy0[w] + nw <= row_hi
+ *   rowspec_dev           cb_spectrum_rowspec_bytes(plan, ngroups, row_lo, row_hi) bytes of scratch
+ * Worth it when nwin * nw is well above ngroups * (row_hi - row_lo), i.e. when rows are reused.
+ */
+int64_t cb_spectrum_rowspec_bytes(const cb_spectrum_plan *plan, int ngroups, int row_lo, int row_hi);
+int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan,
+                                  const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
+                                  const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin,
+                                  const int32_t *group_of_win_dev, const int32_t *group_ix0_dev, int ngroups,
+                                  int row_lo, int row_hi,
+                                  int detrend, double power,
+                                  double *phi_dev, double *sigma_dev,
+                                  void *rowspec_dev, int64_t rowspec_bytes,
+                                  void *workspace_dev, int64_t workspace_bytes,
+                                  void *stream);
+
 /* Detrended windows themselves: out[w] = window - plane  (CurieGrid.remove_trend_linear). */
 int cb_detrend_batch(const double *grid_dev, int64_t ny, int64_t nx, int64_t ld, int nw,
                      const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin,

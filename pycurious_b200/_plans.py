@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import warnings
+import os
 import weakref
 
 import numpy as np
@@ -117,6 +118,8 @@ class SpectrumPlan:
         nbytes = int(lib.cb_spectrum_workspace_bytes(handle))
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         self.device = torch.cuda.current_device()
+        self._rowspec = None
+        self.last_path = "direct"
 
     def info(self):
         info = _lib.SpectrumPlanInfo()
@@ -130,17 +133,82 @@ class SpectrumPlan:
         _lib.check(_lib.load().cb_spectrum_plan_get_bins(self.handle, ptr.ctypes.data, idx.ctypes.data))
         return ptr, idx
 
-    def run(self, grid_t, iy0_t, ix0_t, detrend, power):
-        """grid_t: 2-D float64 cuda tensor; iy0_t/ix0_t: int32 cuda tensors -> (Phi, sigma) cuda [n, nbins]."""
+    # windows * nw rows would be transformed without sharing; the shared path transforms groups * rows
+    SHARE_MIN_REUSE = 2.0
+
+    def run(self, grid_t, iy0_t, ix0_t, detrend, power, share_rows=None):
+        """grid_t: 2-D float64 cuda tensor; iy0_t/ix0_t: int32 cuda tensors -> (Phi, sigma) cuda [n, nbins].
+
+        Windows on a lattice (many windows per distinct ix0, overlapping in y) go through
+        cb_spectrum_batch_shared_rows, which transforms every needed grid row once per distinct ix0;
+        scattered windows go through cb_spectrum_batch.  `share_rows` forces the choice (tests)."""
         torch = _lib.require_cuda()
+        lib = _lib.load()
         n = int(iy0_t.numel())
         phi = torch.empty((n, self.nbins), dtype=torch.float64, device="cuda")
         sig = torch.empty((n, self.nbins), dtype=torch.float64, device="cuda")
+        if n == 0:
+            return phi, sig
         ny, nx = grid_t.shape
-        _lib.check(_lib.load().cb_spectrum_batch(
-            self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0), iy0_t.data_ptr(), ix0_t.data_ptr(), n,
-            1 if detrend else 0, float(power), phi.data_ptr(), sig.data_ptr(),
-            self.workspace.data_ptr(), self.workspace.numel(), _lib.stream_ptr(torch)))
+        stream = _lib.stream_ptr(torch)
+        if share_rows is None:
+            share_rows = os.environ.get("CB_SPEC_SHARE_ROWS", "auto")
+            share_rows = None if share_rows == "auto" else share_rows not in ("0", "off", "no")
+        groups = None
+        if share_rows is not False and n > 1:
+            iy0_h = getattr(iy0_t, "_cb_host", None)
+            ix0_h = getattr(ix0_t, "_cb_host", None)
+            if iy0_h is None or ix0_h is None:
+                iy0_h, ix0_h = iy0_t.cpu().numpy(), ix0_t.cpu().numpy()
+            uniq, inv = np.unique(ix0_h, return_inverse=True)
+            row_lo, row_hi = int(iy0_h.min()), int(iy0_h.max()) + self.nw
+            reuse = float(n) * self.nw / (float(uniq.size) * (row_hi - row_lo))
+            if share_rows or reuse >= self.SHARE_MIN_REUSE:
+                groups = (uniq.astype(np.int32), inv.astype(np.int32), iy0_h)
+        if groups is None:
+            _lib.check(lib.cb_spectrum_batch(
+                self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0), iy0_t.data_ptr(), ix0_t.data_ptr(), n,
+                1 if detrend else 0, float(power), phi.data_ptr(), sig.data_ptr(),
+                self.workspace.data_ptr(), self.workspace.numel(), stream))
+            self.last_path = "direct"
+            return phi, sig
+
+        uniq, inv, iy0_h = groups
+        budget = int(float(os.environ.get("CB_SPEC_ROWSPEC_MAX_GB", "24")) * 2 ** 30)
+        per_group = int(lib.cb_spectrum_rowspec_bytes(self.handle, 1, int(iy0_h.min()), int(iy0_h.max()) + self.nw))
+        gmax = max(1, budget // max(per_group, 1))
+        if uniq.size <= gmax:
+            chunks = [(0, uniq.size, None)]
+        else:                                 # too many column groups for one scratch buffer: sort by group, go in slices
+            order = np.argsort(inv, kind="stable")
+            bounds = np.searchsorted(inv[order], np.arange(0, uniq.size + gmax, gmax))
+            chunks = [(g0, min(g0 + gmax, uniq.size), order[bounds[i]:bounds[i + 1]])
+                      for i, g0 in enumerate(range(0, uniq.size, gmax))]
+        for g0, g1, sel in chunks:
+            if sel is None:
+                iy_c, ix_c, gof, out_phi, out_sig, iy_hc = iy0_t, ix0_t, inv, phi, sig, iy0_h
+            else:
+                sel_t = torch.from_numpy(sel).cuda()
+                iy_c, ix_c = iy0_t.index_select(0, sel_t), ix0_t.index_select(0, sel_t)
+                gof, iy_hc = inv[sel] - g0, iy0_h[sel]
+                out_phi = torch.empty((sel.size, self.nbins), dtype=torch.float64, device="cuda")
+                out_sig = torch.empty_like(out_phi)
+            lo, hi = int(iy_hc.min()), int(iy_hc.max()) + self.nw
+            need = int(lib.cb_spectrum_rowspec_bytes(self.handle, g1 - g0, lo, hi))
+            if self._rowspec is None or self._rowspec.numel() < need:
+                self._rowspec = None
+                self._rowspec = torch.empty(need, dtype=torch.uint8, device="cuda")
+            gof_t = torch.from_numpy(np.ascontiguousarray(gof, dtype=np.int32)).cuda()
+            gix_t = torch.from_numpy(np.ascontiguousarray(uniq[g0:g1])).cuda()
+            _lib.check(lib.cb_spectrum_batch_shared_rows(
+                self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0), iy_c.data_ptr(), ix_c.data_ptr(),
+                int(iy_c.numel()), gof_t.data_ptr(), gix_t.data_ptr(), g1 - g0, lo, hi, 1 if detrend else 0,
+                float(power), out_phi.data_ptr(), out_sig.data_ptr(), self._rowspec.data_ptr(), self._rowspec.numel(),
+                self.workspace.data_ptr(), self.workspace.numel(), stream))
+            if sel is not None:
+                phi.index_copy_(0, sel_t, out_phi)
+                sig.index_copy_(0, sel_t, out_sig)
+        self.last_path = "shared_rows"
         return phi, sig
 
 

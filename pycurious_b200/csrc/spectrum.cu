@@ -13,7 +13,8 @@ struct cb_spectrum_plan {
     double2 *d_tw = nullptr, *d_chirp = nullptr, *d_filt = nullptr;
     int32_t *d_slot = nullptr, *d_bin_ptr = nullptr, *d_bin_idx = nullptr;
     double *d_taper_r = nullptr, *d_taper_c = nullptr;
-    spectrum_kernel_fn kernel = nullptr;
+    double2 *d_plane_t0 = nullptr, *d_plane_t1 = nullptr;
+    spectrum_kernel_fn kernel = nullptr, row_kernel = nullptr, col_kernel = nullptr;
     const char *engine = "generic";
 };
 
@@ -26,23 +27,26 @@ spectrum_kernel(const __grid_constant__ SpectrumParams P) {
     spectrum_body<Engine>(cx, P);
 }
 
+template <class Engine>
+__global__ void __launch_bounds__(CB_SPEC_MAX_TEAMS * CB_WARP, 1)
+rowspec_kernel(const __grid_constant__ SpectrumParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem)};
+    rowspec_body<Engine>(cx, P);
+}
+
+template <class Engine>
+__global__ void __launch_bounds__(CB_SPEC_MAX_TEAMS * CB_WARP, 1)
+colspec_kernel(const __grid_constant__ SpectrumParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem)};
+    colspec_body<Engine>(cx, P);
+}
+
 // FFT engines compiled in: static pass lists for the Bluestein lengths of the BASELINE window sizes,
 // the generic runtime-radix engine for everything else.
 typedef StaticFft<8, 8, 8> Fft512;      // nw 201 (and 129..256 that pad to 512)
 typedef StaticFft<8, 8, 4> Fft256;      // nw 101
 typedef StaticFft<8, 8, 5> Fft320;      // nw 129
 typedef StaticFft<5, 5, 5, 5> Fft625;   // nw 301
-
-static spectrum_kernel_fn pick_spectrum_kernel(const SpectrumHostPlan &hp, const char **name) {
-    if (hp.bluestein) {
-        if (Fft512::matches(hp.fft) && hp.n <= Fft512::FUSED_SPAN) { *name = "static 8.8.8"; return spectrum_kernel<Fft512>; }
-        if (Fft256::matches(hp.fft) && hp.n <= Fft256::FUSED_SPAN) { *name = "static 8.8.4"; return spectrum_kernel<Fft256>; }
-        if (Fft320::matches(hp.fft) && hp.n <= Fft320::FUSED_SPAN) { *name = "static 8.8.5"; return spectrum_kernel<Fft320>; }
-        if (Fft625::matches(hp.fft) && hp.n <= Fft625::FUSED_SPAN) { *name = "static 5.5.5.5"; return spectrum_kernel<Fft625>; }
-    }
-    *name = "generic";
-    return spectrum_kernel<GenericFft>;
-}
 
 __global__ void __launch_bounds__(256) detrend_kernel(const __grid_constant__ DetrendParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem)};
@@ -58,12 +62,32 @@ static int upload(T **dst, const std::vector<T> &src) {
     return CB_OK;
 }
 
+template <class Engine>
+static void set_kernels(cb_spectrum_plan *pl, const char *name) {
+    pl->kernel = spectrum_kernel<Engine>;
+    pl->row_kernel = rowspec_kernel<Engine>;
+    pl->col_kernel = colspec_kernel<Engine>;
+    pl->engine = name;
+}
+
+static void pick_spectrum_kernels(cb_spectrum_plan *pl) {
+    const SpectrumHostPlan &hp = pl->hp;
+    if (hp.bluestein && !getenv("CB_SPEC_GENERIC")) {
+        if (Fft512::matches(hp.fft) && hp.n <= Fft512::FUSED_SPAN) return set_kernels<Fft512>(pl, "static 8.8.8");
+        if (Fft256::matches(hp.fft) && hp.n <= Fft256::FUSED_SPAN) return set_kernels<Fft256>(pl, "static 8.8.4");
+        if (Fft320::matches(hp.fft) && hp.n <= Fft320::FUSED_SPAN) return set_kernels<Fft320>(pl, "static 8.8.5");
+        if (Fft625::matches(hp.fft) && hp.n <= Fft625::FUSED_SPAN) return set_kernels<Fft625>(pl, "static 5.5.5.5");
+    }
+    set_kernels<GenericFft>(pl, "generic");
+}
+
 extern "C" {
 
 int cb_spectrum_plan_destroy(cb_spectrum_plan *plan) {
     if (!plan) return CB_OK;
     cudaFree(plan->d_tw); cudaFree(plan->d_chirp); cudaFree(plan->d_filt); cudaFree(plan->d_slot);
     cudaFree(plan->d_bin_ptr); cudaFree(plan->d_bin_idx); cudaFree(plan->d_taper_r); cudaFree(plan->d_taper_c);
+    cudaFree(plan->d_plane_t0); cudaFree(plan->d_plane_t1);
     delete plan;
     return CB_OK;
 }
@@ -99,13 +123,16 @@ int cb_spectrum_plan_create(int nw, int nbins, const double *taper_r, const doub
 #define UP(dst, src) if ((rc = upload(&pl->dst, hp.src)) != CB_OK) { cb_spectrum_plan_destroy(pl); return rc; }
     UP(d_tw, tw) UP(d_chirp, chirp) UP(d_filt, filt) UP(d_slot, slot)
     UP(d_bin_ptr, bin_ptr) UP(d_bin_idx, bin_idx) UP(d_taper_r, taper_r) UP(d_taper_c, taper_c)
+    UP(d_plane_t0, plane_t0) UP(d_plane_t1, plane_t1)
 #undef UP
     // the attribute belongs to the kernel, not to the plan: raise it once to the device limit so that
     // plans with different line lengths can coexist
-    pl->kernel = pick_spectrum_kernel(hp, &pl->engine);
-    if (getenv("CB_SPEC_GENERIC")) { pl->kernel = spectrum_kernel<GenericFft>; pl->engine = "generic"; }
-    cudaError_t e = cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)prop.sharedMemPerBlockOptin);
+    pick_spectrum_kernels(pl);
+    cudaError_t e = cudaSuccess;
+    for (spectrum_kernel_fn fn : {pl->kernel, pl->row_kernel, pl->col_kernel}) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+        if (e != cudaSuccess) break;
+    }
     if (e != cudaSuccess) {
         cb_set_error("cudaFuncSetAttribute(smem=%lld): %s", (long long)prop.sharedMemPerBlockOptin, cudaGetErrorString(e));
         cb_spectrum_plan_destroy(pl);
@@ -177,6 +204,54 @@ int cb_spectrum_batch(const cb_spectrum_plan *plan, const double *grid_dev, int6
     P.gt = reinterpret_cast<double2 *>(base);
     P.lh = reinterpret_cast<double *>(base + (uintptr_t)grid * (uintptr_t)hp.gt_stride * 16);
     plan->kernel<<<grid, hp.threads, (size_t)hp.smem_bytes, (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int64_t cb_spectrum_rowspec_bytes(const cb_spectrum_plan *plan, int ngroups, int row_lo, int row_hi) {
+    if (!plan || ngroups < 0 || row_hi < row_lo) return 0;
+    const int64_t nrows = ((int64_t)(row_hi - row_lo) + 1) & ~1LL;
+    return (int64_t)ngroups * plan->hp.nvh * nrows * 16 + 256;
+}
+
+int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan, const double *grid_dev, int64_t ny, int64_t nx,
+                                  int64_t ld, const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin,
+                                  const int32_t *group_of_win_dev, const int32_t *group_ix0_dev, int ngroups,
+                                  int row_lo, int row_hi, int detrend, double power, double *phi_dev,
+                                  double *sigma_dev, void *rowspec_dev, int64_t rowspec_bytes, void *workspace_dev,
+                                  int64_t workspace_bytes, void *stream) {
+    CB_REQUIRE(plan != nullptr, "plan is NULL");
+    CB_REQUIRE(nwin >= 0, "nwin < 0");
+    if (nwin == 0) return CB_OK;
+    CB_REQUIRE(grid_dev && iy0_dev && ix0_dev && phi_dev && sigma_dev && workspace_dev && rowspec_dev, "NULL buffer");
+    CB_REQUIRE(group_of_win_dev && group_ix0_dev && ngroups > 0, "missing window groups");
+    const SpectrumHostPlan &hp = plan->hp;
+    CB_REQUIRE(ny >= hp.n && nx >= hp.n && ld >= nx, "grid smaller than the window");
+    CB_REQUIRE(row_lo >= 0 && row_hi <= ny && row_hi - row_lo >= hp.n, "row range must hold a whole window inside the grid");
+    CB_REQUIRE(rowspec_bytes >= cb_spectrum_rowspec_bytes(plan, ngroups, row_lo, row_hi),
+               "row-spectra buffer too small (see cb_spectrum_rowspec_bytes)");
+    const int grid = (int)std::min<int64_t>(nwin, plan->grid_max);
+    uintptr_t base = ((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255;
+    CB_REQUIRE((int64_t)(base - (uintptr_t)workspace_dev) + (int64_t)grid * hp.ws_per_cta <= workspace_bytes,
+               "workspace too small (see cb_spectrum_workspace_bytes)");
+    SpectrumParams P;
+    memset(&P, 0, sizeof(P));
+    spectrum_fill_params(hp, P, plan->d_tw, plan->d_chirp, plan->d_filt, plan->d_slot, plan->d_taper_r,
+                         plan->d_taper_c, plan->d_bin_ptr, plan->d_bin_idx);
+    P.grid = grid_dev; P.ld = ld; P.iy0 = iy0_dev; P.ix0 = ix0_dev; P.nwin = nwin;
+    P.detrend = detrend ? 1 : 0; P.power = power;
+    P.phi = phi_dev; P.sigma = sigma_dev;
+    P.lh = reinterpret_cast<double *>(base);          // the G^T part of the slab is not used on this path
+    P.lh_stride = hp.ws_per_cta / 8;
+    P.group_of_win = group_of_win_dev; P.group_ix0 = group_ix0_dev; P.ngroups = ngroups;
+    P.row_lo = row_lo; P.nrows_valid = row_hi - row_lo; P.nrows = (P.nrows_valid + 1) & ~1;
+    P.rt = reinterpret_cast<double2 *>(((uintptr_t)rowspec_dev + 255) & ~(uintptr_t)255);
+    P.plane_t0 = plan->d_plane_t0; P.plane_t1 = plan->d_plane_t1;
+    const int64_t items = (int64_t)ngroups * (P.nrows / 2);
+    const int row_grid = (int)std::min<int64_t>((items + hp.teams - 1) / hp.teams, plan->grid_max);
+    plan->row_kernel<<<row_grid, hp.threads, (size_t)hp.smem_bytes, (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    plan->col_kernel<<<grid, hp.threads, (size_t)hp.smem_bytes, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }

@@ -47,11 +47,96 @@ struct SpectrumParams {
     int64_t gt_stride, lh_stride;   // elements per CTA
     // shared-memory carve-up (in double2 slots)
     int32_t sm_tw, sm_filt, sm_chirp, sm_cw, sm_buf, line_slots;
+    // shared-row-spectra path (rowspec_body / colspec_body): windows with the same ix0 share the
+    // x-transforms of the grid rows they overlap
+    const int32_t *group_of_win;   // [nwin] group (= distinct ix0) of each window
+    const int32_t *group_ix0;      // [ngroups]
+    int32_t ngroups;
+    int32_t row_lo;                // first grid row held in rt
+    int32_t nrows;                 // rows per (group, v) line of rt, even
+    int32_t nrows_valid;           // rows [row_lo, row_lo + nrows_valid) exist in the grid
+    double2 *rt;                   // [ngroups][nvh][nrows] half spectra of (grid row x column taper)
+    const double2 *plane_t0, *plane_t1;   // [nvh] x-transforms of taper_c and (x - ctr) taper_c (detrend)
 };
 
 CB_HD double2 bluestein_out(const double2 *buf, const double2 *chirp, int k) {
     // X[k] = chirp[k] * (a (*) b)[k]; the line holds the conjugate of the convolution
     return cmul(chirp[k], cconj(buf[CB_PAD(k)]));
+}
+
+// Least-squares plane of one window in closed form (grid.py:199-216): c0 + cx1 (x - ctr) + cy1 (y - ctr).
+// Block-wide; s_red = 96 doubles of shared scratch.
+template <class Ctx>
+CB_BODY void window_plane(const Ctx &cx, const SpectrumParams &P, const double *src, double *s_red, int warp, int lane,
+                          int nwarps, double &c0, double &cx1, double &cy1) {
+    const int n = P.n;
+    const double ctr = 0.5 * (double)(n - 1);
+    double s0 = 0.0, sx = 0.0, sy = 0.0;
+    for (int y = warp; y < n; y += nwarps) {
+        const double *row = src + (int64_t)y * P.ld;
+        double r0 = 0.0, rx = 0.0;
+        for (int x = lane; x < n; x += CB_WARP) {
+            double d = Ctx::ldg(row + x);
+            r0 += d;
+            rx = fma((double)x - ctr, d, rx);
+        }
+        s0 += r0;
+        sx += rx;
+        sy = fma((double)y - ctr, r0, sy);
+    }
+    s0 = cx.warp_sum(s0);
+    sx = cx.warp_sum(sx);
+    sy = cx.warp_sum(sy);
+    if (lane == 0) { s_red[warp] = s0; s_red[32 + warp] = sx; s_red[64 + warp] = sy; }
+    cx.sync_block();
+    s0 = sx = sy = 0.0;
+    for (int i = 0; i < nwarps; ++i) { s0 += s_red[i]; sx += s_red[32 + i]; sy += s_red[64 + i]; }
+    const double nn = (double)n;
+    const double sxx = nn * nn * (nn * nn - 1.0) / 12.0;   // sum over the window of (x-ctr)^2
+    c0 = s0 / (nn * nn);
+    cx1 = sx / sxx;
+    cy1 = sy / sxx;
+    cx.sync_block();
+}
+
+// Phase C: radial bins (grid.py:281-286), mean / population std of the members of each bin, one
+// warp per bin over the folded CSR.
+template <class Ctx>
+CB_BODY void bin_phase(const Ctx &cx, const SpectrumParams &P, const double *Lh, int64_t w, int warp, int lane,
+                       int nwarps) {
+    for (int b = warp; b < P.nbins; b += nwarps) {
+        const int lo = Ctx::ldg(P.bin_ptr + b), hi = Ctx::ldg(P.bin_ptr + b + 1);
+        // one pass over the members: sum and sum of squares about a pivot member (the population
+        // variance is shift invariant; the pivot removes the mean^2 cancellation), 4 gathers in flight
+        double pivot = lo < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + lo)) : 0.0;
+        if (!isfinite(pivot)) pivot = 0.0;          // log(0) = -inf members: plain sums, numpy's -inf / nan result
+        double s = 0.0, q = 0.0;
+        for (int eb = lo; eb < hi; eb += 4 * CB_WARP) {
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = eb + j * CB_WARP + lane;
+                v[j] = e < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e)) : pivot;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double d = v[j] - pivot;      // padding lanes contribute exactly 0
+                s += d;
+                q = fma(d, d, q);
+            }
+        }
+        s = cx.warp_sum(s);
+        q = cx.warp_sum(q);
+        const double cnt = (double)(hi - lo);
+        const double md = s / cnt;                  // mean - pivot
+        const double mean = pivot + md;
+        q -= s * md;                                // sum (x - mean)^2
+        if (q < 0.0) q = 0.0;                       // (a nan stays a nan)
+        if (lane == 0) {
+            P.phi[w * P.nbins + b] = P.power * mean;
+            P.sigma[w * P.nbins + b] = fabs(P.power) * sqrt(q / cnt);
+        }
+    }
 }
 
 template <class Engine, class Ctx>
@@ -87,34 +172,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
 
         // ---- optional least-squares plane (centred regressors are orthogonal) -------------
         double c0 = 0.0, cx1 = 0.0, cy1 = 0.0;
-        if (P.detrend) {
-            double s0 = 0.0, sx = 0.0, sy = 0.0;
-            for (int y = warp; y < n; y += nwarps) {
-                const double *row = src + (int64_t)y * P.ld;
-                double r0 = 0.0, rx = 0.0;
-                for (int x = lane; x < n; x += CB_WARP) {
-                    double d = Ctx::ldg(row + x);
-                    r0 += d;
-                    rx = fma((double)x - ctr, d, rx);
-                }
-                s0 += r0;
-                sx += rx;
-                sy = fma((double)y - ctr, r0, sy);
-            }
-            s0 = cx.warp_sum(s0);
-            sx = cx.warp_sum(sx);
-            sy = cx.warp_sum(sy);
-            if (lane == 0) { s_red[warp] = s0; s_red[32 + warp] = sx; s_red[64 + warp] = sy; }
-            cx.sync_block();
-            s0 = sx = sy = 0.0;
-            for (int i = 0; i < nwarps; ++i) { s0 += s_red[i]; sx += s_red[32 + i]; sy += s_red[64 + i]; }
-            const double nn = (double)n;
-            const double sxx = nn * nn * (nn * nn - 1.0) / 12.0;   // sum over the window of (x-ctr)^2
-            c0 = s0 / (nn * nn);
-            cx1 = sx / sxx;
-            cy1 = sy / sxx;
-            cx.sync_block();
-        }
+        if (P.detrend) window_plane(cx, P, src, s_red, warp, lane, nwarps, c0, cx1, cy1);
 
         // ---- phase A: row pairs ---------------------------------------------------------------
         const int npairs = (n + 1) >> 1;
@@ -243,42 +301,167 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
         }
         cx.sync_block();
 
-        // ---- phase C: radial bins (grid.py:281-286), mean / population std --------------
-        for (int b = warp; b < P.nbins; b += nwarps) {
-            const int lo = Ctx::ldg(P.bin_ptr + b), hi = Ctx::ldg(P.bin_ptr + b + 1);
-            // one pass over the members: sum and sum of squares about a pivot member (the population
-            // variance is shift invariant; the pivot removes the mean^2 cancellation), 4 gathers in flight
-            double pivot = lo < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + lo)) : 0.0;
-            if (!isfinite(pivot)) pivot = 0.0;          // log(0) = -inf members: plain sums, numpy's -inf / nan result
-            double s = 0.0, q = 0.0;
-            for (int eb = lo; eb < hi; eb += 4 * CB_WARP) {
-                double v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int e = eb + j * CB_WARP + lane;
-                    v[j] = e < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e)) : pivot;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double d = v[j] - pivot;      // padding lanes contribute exactly 0
-                    s += d;
-                    q = fma(d, d, q);
-                }
-            }
-            s = cx.warp_sum(s);
-            q = cx.warp_sum(q);
-            const double cnt = (double)(hi - lo);
-            const double md = s / cnt;                  // mean - pivot
-            const double mean = pivot + md;
-            q -= s * md;                                // sum (x - mean)^2
-            if (q < 0.0) q = 0.0;                       // (a nan stays a nan)
-            if (lane == 0) {
-                P.phi[w * P.nbins + b] = P.power * mean;
-                P.sigma[w * P.nbins + b] = fabs(P.power) * sqrt(q / cnt);
-            }
-        }
+        // ---- phase C: radial bins ----------------------------------------------------------------
+        bin_phase(cx, P, Lh, w, warp, lane, nwarps);
         // phase C of this window may overlap phase A of the next: A writes only Gt, C reads only Lh;
         // the barrier after the next phase A orders C(w) before B(w+1).
+    }
+}
+
+
+// =====================================================================================
+// Shared row spectra.  On a centroid lattice every window that starts at the same column ix0
+// needs the x-transform of (grid row x column taper) for the rows it overlaps -- the row taper is a
+// per-row scalar and the detrending plane a rank-2 correction, so they commute with that transform.
+// A 201-node window on a 10-node stride shares each row with 20 other windows:
+//   rowspec_body  one warp per (group = distinct ix0, row pair): the phase-A transform, ONCE, into
+//                 rt[group][v][row]   (HBM resident: config 3 = 390 x 101 x 4096 x 16 B = 2.6 GB)
+//   colspec_body  one CTA per window: phase B reads its 201-row slice of rt[group][v] (contiguous),
+//                 applies row taper, chirp and the plane correction, transforms, bins (phase C)
+// Per window this halves the FFT work; the row pass costs 1/20 of the old phase A.
+// =====================================================================================
+template <class Ctx>
+CB_BODY void spectrum_stage_tables(const Ctx &cx, const SpectrumParams &P, double2 *s_tw, double2 *s_filt,
+                                   double2 *s_chirp, double2 *s_cw, const double *taper) {
+    const int tid = cx.tid(), nthr = cx.nthreads(), n = P.n;
+    for (int i = tid; i < P.fft.tw_count; i += nthr) s_tw[i] = P.tw[i];
+    if (P.bluestein) {
+        for (int i = tid; i < P.line_slots; i += nthr) s_filt[i] = P.filt[i];
+        for (int i = tid; i < n; i += nthr) s_chirp[i] = P.chirp[i];
+    }
+    for (int i = tid; i < n; i += nthr) {
+        const double t = taper ? taper[i] : 1.0;
+        s_cw[i] = P.bluestein ? cscale(P.chirp[i], t) : cplx(t, 0.0);
+    }
+    cx.sync_block();
+}
+
+template <class Engine, class Ctx>
+CB_BODY void rowspec_body(const Ctx &cx, const SpectrumParams &P) {
+    const int tid = cx.tid(), nthr = cx.nthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int n = P.n, nvh = P.nvh, M = P.fft.n;
+    double2 *sm = reinterpret_cast<double2 *>(cx.smem());
+    double2 *s_tw = sm + P.sm_tw, *s_filt = sm + P.sm_filt, *s_chirp = sm + P.sm_chirp, *s_cw = sm + P.sm_cw;
+    double2 *buf = sm + P.sm_buf + (int64_t)warp * P.line_slots;
+    spectrum_stage_tables(cx, P, s_tw, s_filt, s_chirp, s_cw, P.taper_c);
+
+    const int npairs = P.nrows >> 1;
+    const int64_t total = (int64_t)P.ngroups * npairs;
+    for (int64_t item = (int64_t)cx.bid() * nwarps + warp; item < total; item += (int64_t)cx.nblocks() * nwarps) {
+        const int g = (int)(item / npairs), p = (int)(item - (int64_t)g * npairs);
+        const bool has0 = 2 * p < P.nrows_valid, has1 = 2 * p + 1 < P.nrows_valid;
+        const double *r0 = P.grid + (int64_t)(P.row_lo + (has0 ? 2 * p : 0)) * P.ld + Ctx::ldg(P.group_ix0 + g);
+        const double *r1 = has1 ? r0 + P.ld : r0;
+        bool fused = false;
+        if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+            fused = true;
+            auto ld = [&](int x) -> double2 {
+                if (x >= n) return cplx(0.0, 0.0);
+                const double av = has0 ? Ctx::ldg(r0 + x) : 0.0, bv = has1 ? Ctx::ldg(r1 + x) : 0.0;
+                return cmul(cplx(av, bv), s_cw[x]);
+            };
+            auto sk = [&](int k, double2 z) {
+                if (k < n) buf[CB_PAD(k)] = z;
+            };
+            Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+            cx.sync_warp();
+        }
+        if (!fused) {
+            cx.sync_warp();
+            for (int x = lane; x < M; x += CB_WARP) {
+                double2 z = cplx(0.0, 0.0);
+                if (x < n) {
+                    const double av = has0 ? Ctx::ldg(r0 + x) : 0.0, bv = has1 ? Ctx::ldg(r1 + x) : 0.0;
+                    const double2 cw = s_cw[x];
+                    z = P.bluestein ? cmul(cplx(av, bv), cw) : cplx(av * cw.x, bv * cw.x);
+                }
+                buf[CB_PAD(x)] = z;
+            }
+            if (P.bluestein) Engine::convolve(cx, buf, s_tw, s_filt, P.fft, lane);
+            else Engine::forward(cx, buf, s_tw, P.fft, lane);
+        }
+        // untangle the two real rows; rt[g][v][2p], rt[g][v][2p+1] are adjacent (one 32-byte sector)
+        double2 *dst0 = P.rt + ((int64_t)g * nvh) * P.nrows + 2 * p;
+        for (int v = lane; v < nvh; v += CB_WARP) {
+            const int vm = v ? n - v : 0;
+            double2 zv, zm;
+            if (P.bluestein) {
+                zv = bluestein_out(buf, s_chirp, v);
+                zm = bluestein_out(buf, s_chirp, vm);
+            } else {
+                zv = buf[CB_PAD(Ctx::ldg(P.slot + v))];
+                zm = buf[CB_PAD(Ctx::ldg(P.slot + vm))];
+            }
+            double2 *dst = dst0 + (int64_t)v * P.nrows;
+            Ctx::stcg(dst, cplx(0.5 * (zv.x + zm.x), 0.5 * (zv.y - zm.y)));
+            Ctx::stcg(dst + 1, cplx(0.5 * (zv.y + zm.y), -0.5 * (zv.x - zm.x)));
+        }
+        cx.sync_warp();
+    }
+}
+
+template <class Engine, class Ctx>
+CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
+    const int tid = cx.tid(), nthr = cx.nthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int n = P.n, nvh = P.nvh, M = P.fft.n;
+    double2 *sm = reinterpret_cast<double2 *>(cx.smem());
+    double2 *s_tw = sm + P.sm_tw, *s_filt = sm + P.sm_filt, *s_chirp = sm + P.sm_chirp, *s_rw = sm + P.sm_cw;
+    double2 *buf = sm + P.sm_buf + (int64_t)warp * P.line_slots;
+    double *s_red = reinterpret_cast<double *>(sm);
+    spectrum_stage_tables(cx, P, s_tw, s_filt, s_chirp, s_rw, P.taper_r);     // s_rw = row taper (x chirp)
+
+    double *Lh = P.lh + (int64_t)cx.bid() * P.lh_stride;
+    const double ctr = 0.5 * (double)(n - 1);
+    for (int64_t w = cx.bid(); w < P.nwin; w += cx.nblocks()) {
+        const int iy0 = P.iy0[w], g = P.group_of_win[w];
+        double c0 = 0.0, cx1 = 0.0, cy1 = 0.0;
+        if (P.detrend)
+            window_plane(cx, P, P.grid + (int64_t)iy0 * P.ld + P.ix0[w], s_red, warp, lane, nwarps, c0, cx1, cy1);
+        const double2 *rt_w = P.rt + ((int64_t)g * nvh) * P.nrows + (iy0 - P.row_lo);
+        for (int v = warp; v < nvh; v += nwarps) {
+            const double2 *col = rt_w + (int64_t)v * P.nrows;
+            double *out = Lh + (int64_t)v * n;
+            double2 t0 = cplx(0.0, 0.0), t1 = cplx(0.0, 0.0);
+            if (P.detrend) {
+                t0 = Ctx::ldg(P.plane_t0 + v);
+                t1 = cscale(Ctx::ldg(P.plane_t1 + v), cx1);
+            }
+            // row y of the window, x-transformed, minus the transformed plane, times the row taper
+            auto element = [&](int y) -> double2 {
+                double2 z = Ctx::ldcg(col + y);
+                if (P.detrend) {
+                    const double a = c0 + cy1 * ((double)y - ctr);
+                    z = cplx(z.x - fma(a, t0.x, t1.x), z.y - fma(a, t0.y, t1.y));
+                }
+                const double2 rw = s_rw[y];
+                return P.bluestein ? cmul(z, rw) : cscale(z, rw.x);
+            };
+            bool fused = false;
+            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+                fused = true;
+                auto ld = [&](int y) -> double2 { return y < n ? element(y) : cplx(0.0, 0.0); };
+                auto sk = [&](int u, double2 z) {
+                    if (u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                };
+                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+            }
+            if (!fused) {
+                cx.sync_warp();
+                for (int y = lane; y < M; y += CB_WARP) buf[CB_PAD(y)] = y < n ? element(y) : cplx(0.0, 0.0);
+                if (P.bluestein) Engine::convolve(cx, buf, s_tw, s_filt, P.fft, lane);
+                else Engine::forward(cx, buf, s_tw, P.fft, lane);
+                for (int u = lane; u < n; u += CB_WARP) {
+                    const double2 z = P.bluestein ? buf[CB_PAD(u)] : buf[CB_PAD(Ctx::ldg(P.slot + u))];
+                    Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                }
+            }
+            cx.sync_warp();
+        }
+        cx.sync_block();
+        bin_phase(cx, P, Lh, w, warp, lane, nwarps);
+        cx.sync_block();       // the next window's phase B overwrites Lh
     }
 }
 

@@ -13,6 +13,7 @@ struct SpectrumHostPlan {
     std::vector<double2> tw, chirp, filt;
     std::vector<int32_t> slot;
     std::vector<double> taper_r, taper_c;
+    std::vector<double2> plane_t0, plane_t1;   // x-transforms of taper_c and (x - ctr) taper_c, v < nvh
     bool has_taper = false;
     std::vector<int32_t> bin_ptr, bin_idx;
     int nnz_full = 0;
@@ -90,6 +91,22 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
     if (hp.has_taper) {
         hp.taper_r.assign(taper_r, taper_r + nw);
         hp.taper_c.assign(taper_c, taper_c + nw);
+    }
+    {   // detrending commutes with the row transform through these two vectors (colspec_body)
+        const long double ctr = 0.5L * (long double)(nw - 1);
+        hp.plane_t0.resize(hp.nvh);
+        hp.plane_t1.resize(hp.nvh);
+        for (int v = 0; v < hp.nvh; ++v) {
+            cbplan::lcplx a0(0, 0), a1(0, 0);
+            for (int x = 0; x < nw; ++x) {
+                const long double t = hp.has_taper ? (long double)taper_c[x] : 1.0L;
+                const cbplan::lcplx w = cbplan::cis_ratio((long long)v * x, nw);
+                a0 += t * w;
+                a1 += ((long double)x - ctr) * t * w;
+            }
+            hp.plane_t0[v] = cplx((double)a0.real(), (double)a0.imag());
+            hp.plane_t1[v] = cplx((double)a1.real(), (double)a1.imag());
+        }
     }
     for (int b = 0; b < nbins; ++b)
         if (bin_ptr[b + 1] < bin_ptr[b]) { hp.error = "bin_ptr not monotone"; return false; }

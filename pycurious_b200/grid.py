@@ -106,7 +106,9 @@ class CurieGrid(object):
     def _origins_device(self, window, xc_list, yc_list):
         torch = _lib.require_cuda()
         iy0, ix0, n = _plans.window_origins(self, window, xc_list, yc_list)
-        return (torch.from_numpy(iy0).cuda(), torch.from_numpy(ix0).cuda(), n)
+        iy0_t, ix0_t = torch.from_numpy(iy0).cuda(), torch.from_numpy(ix0).cuda()
+        iy0_t._cb_host, ix0_t._cb_host = iy0, ix0      # the spectrum plan groups windows by ix0 on the host
+        return (iy0_t, ix0_t, n)
 
     # ------------------------------------------------------------------ reference API
     def subgrid(self, window, xc, yc):

@@ -41,6 +41,14 @@ static void emu_launch(int nblocks, int nthreads, size_t smem_bytes, F body) {
     }
 }
 
+// Shared-row-spectra path (rowspec_body + colspec_body); groups are built here like the host side of
+// pycurious_b200/_plans.py does.  max_teams < 0 forces the generic engine.
+template <class Engine>
+static void emu_run_shared(int nblocks, const SpectrumHostPlan &hp, const SpectrumParams &P) {
+    emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { rowspec_body<Engine>(cx, P); });
+    emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { colspec_body<Engine>(cx, P); });
+}
+
 extern "C" {
 
 // plan introspection without a device: FFT length, radices, folded CSR size
@@ -128,6 +136,52 @@ int emu_spectrum(int nw, int nbins, const double *taper_r, const double *taper_c
         emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<5, 5, 5, 5>>(cx, P); });
     else
         emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<GenericFft>(cx, P); });
+    return 0;
+}
+
+int emu_spectrum_shared(int nw, int nbins, const double *taper_r, const double *taper_c, const int32_t *bin_ptr,
+                        const int32_t *bin_idx, const double *grid, int64_t ny, int64_t ld, const int32_t *iy0,
+                        const int32_t *ix0, int64_t nwin, int detrend, double power, double *phi, double *sigma,
+                        int nblocks, int max_teams) {
+    SpectrumHostPlan hp;
+    if (!spectrum_plan_build_host(hp, nw, nbins, taper_r, taper_c, bin_ptr, bin_idx, 232448)) {
+        fprintf(stderr, "emu_spectrum_shared: %s\n", hp.error.c_str());
+        return -1;
+    }
+    const int mt = max_teams < 0 ? -max_teams : max_teams;
+    if (mt > 0 && hp.teams > mt) {
+        hp.teams = mt;
+        hp.threads = 32 * mt;
+        hp.smem_bytes = 16 * ((int64_t)hp.sm_buf + (int64_t)hp.teams * hp.line_slots);
+    }
+    std::vector<int32_t> gix, gof(nwin);
+    int row_lo = 1 << 30, row_hi = 0;
+    for (int64_t w = 0; w < nwin; ++w) {
+        auto it = std::find(gix.begin(), gix.end(), ix0[w]);
+        if (it == gix.end()) { gix.push_back(ix0[w]); it = gix.end() - 1; }
+        gof[w] = (int32_t)(it - gix.begin());
+        row_lo = std::min(row_lo, (int)iy0[w]);
+        row_hi = std::max(row_hi, (int)iy0[w] + nw);
+    }
+    SpectrumParams P;
+    memset(&P, 0, sizeof(P));
+    spectrum_fill_params(hp, P, hp.tw.data(), hp.chirp.data(), hp.filt.data(), hp.slot.data(),
+                         hp.taper_r.data(), hp.taper_c.data(), hp.bin_ptr.data(), hp.bin_idx.data());
+    P.grid = grid; P.ld = ld; P.iy0 = iy0; P.ix0 = ix0; P.nwin = nwin;
+    P.detrend = detrend; P.power = power; P.phi = phi; P.sigma = sigma;
+    P.group_of_win = gof.data(); P.group_ix0 = gix.data(); P.ngroups = (int)gix.size();
+    P.row_lo = row_lo; P.nrows_valid = row_hi - row_lo; P.nrows = (P.nrows_valid + 1) & ~1;
+    std::vector<double2> rt((size_t)P.ngroups * hp.nvh * P.nrows);
+    std::vector<double> lh((size_t)nblocks * hp.lh_stride);
+    P.rt = rt.data(); P.lh = lh.data();
+    P.plane_t0 = hp.plane_t0.data(); P.plane_t1 = hp.plane_t1.data();
+    (void)ny;
+    const bool generic = max_teams < 0 || !hp.bluestein;
+    if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 8>>(nblocks, hp, P);
+    else if (!generic && StaticFft<8, 8, 4>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 4>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 4>>(nblocks, hp, P);
+    else if (!generic && StaticFft<8, 8, 5>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 5>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 5>>(nblocks, hp, P);
+    else if (!generic && StaticFft<5, 5, 5, 5>::matches(hp.fft) && hp.n <= StaticFft<5, 5, 5, 5>::FUSED_SPAN) emu_run_shared<StaticFft<5, 5, 5, 5>>(nblocks, hp, P);
+    else emu_run_shared<GenericFft>(nblocks, hp, P);
     return 0;
 }
 

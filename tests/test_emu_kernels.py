@@ -120,6 +120,36 @@ def test_spectrum_body_matches_oracle(emu, oracle, mag, nw, taper, det, power, o
         np.testing.assert_allclose(sig[w], s0, rtol=1e-9)
 
 
+@pytest.mark.parametrize("nw,taper,det,power,teams", [
+    (101, np.hanning, 0, 2.0, 4), (101, np.hamming, 1, 0.5, -4), (129, None, 1, 2.0, 4), (30, np.hanning, 1, 2.0, 4),
+    (201, np.hanning, 0, 2.0, 4)])
+def test_shared_row_spectra_path_matches_oracle(emu, oracle, mag, nw, taper, det, power, teams):
+    """rowspec_body + colspec_body: windows on a lattice share the x-transforms of the grid rows (odd and
+    even row offsets, two column groups, last row pair half empty), with and without the plane detrend."""
+    d = np.ascontiguousarray(mag[0])
+    ny = d.shape[0]
+    origins = [(3, 5), (10, 5), (ny - nw, 5), (4, 40)] if nw < 201 else [(3, 5), (ny - nw, 5)]
+    ptr, idx = _bins(oracle, nw)
+    nb = ptr.size - 1
+    tr = None if taper is None else np.ascontiguousarray(taper(nw), dtype=np.float64)
+    iy0 = np.array([o[0] for o in origins], dtype=np.int32)
+    ix0 = np.array([o[1] for o in origins], dtype=np.int32)
+    phi = np.zeros((len(origins), nb))
+    sig = np.zeros_like(phi)
+    emu.emu_spectrum_shared.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                                                                 C.c_int64, C.c_int, C.c_double, C.c_void_p,
+                                                                                 C.c_void_p, C.c_int, C.c_int]
+    assert emu.emu_spectrum_shared(nw, nb, P(tr), P(tr), P(ptr), P(idx), P(d), d.shape[0], d.shape[1], P(iy0), P(ix0),
+                                   len(origins), det, power, P(phi), P(sig), 2, teams) == 0
+    for w, (j0, i0) in enumerate(origins):
+        win = d[j0:j0 + nw, i0:i0 + nw]
+        if det:
+            win = oracle.detrend_plane(win)
+        _, p0, s0 = oracle.radial_spectrum(win, 1000.0, taper=taper, power=power)
+        np.testing.assert_allclose(phi[w], p0, rtol=1e-10, err_msg=str((w, j0, i0)))
+        np.testing.assert_allclose(sig[w], s0, rtol=1e-9)
+
+
 def test_spectrum_static_and_generic_engines_agree(emu, oracle, mag):
     """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 5.5.5.5) against the runtime-radix engine."""
     d = np.ascontiguousarray(mag[0])

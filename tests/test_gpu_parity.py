@@ -101,6 +101,40 @@ def test_spectrum_batch_equals_single_and_oracle(grid, oracle, mag):
         np.testing.assert_allclose(sig[i], s0, rtol=1e-9)
 
 
+@pytest.mark.parametrize("detrend", [False, True])
+def test_shared_row_spectra_path_equals_direct_path(pc, grid, oracle, mag, detrend, monkeypatch):
+    """cb_spectrum_batch_shared_rows (rows transformed once per distinct ix0) against cb_spectrum_batch and
+    the oracle on a centroid lattice, in one piece and with the column groups forced into several slices."""
+    import torch
+    from pycurious_b200 import _plans
+    d, ext = mag
+    spec = oracle.GridSpec(d, *ext)
+    xc, yc = grid.create_centroid_list(100e3, 9e3, 14e3)
+    iy0, ix0, n = grid._origins_device(100e3, xc, yc)
+    plan = _plans.spectrum_plan(n, grid.dx, _plans.taper_vector(np.hanning, n))
+    g = grid.device_grid()
+    p_dir, s_dir = plan.run(g, iy0, ix0, detrend, 2.0, share_rows=False)
+    assert plan.last_path == "direct"
+    plan.last_path = "direct"
+    p_sh, s_sh = plan.run(g, iy0, ix0, detrend, 2.0, share_rows=True)
+    assert plan.last_path == "shared_rows"
+    monkeypatch.setenv("CB_SPEC_ROWSPEC_MAX_GB", "%.6f" % (5.2 * 51 * 306 * 16 / 2 ** 30))   # ~5 groups per slice
+    p_ch, s_ch = plan.run(g, iy0, ix0, detrend, 2.0, share_rows=True)
+    torch.cuda.synchronize()
+    for a, b in ((p_sh, p_dir), (p_ch, p_dir)):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-11, atol=1e-11)
+    for a, b in ((s_sh, s_dir), (s_ch, s_dir)):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-9)
+    assert np.array_equal(p_sh.cpu().numpy(), p_ch.cpu().numpy())
+    ph = p_sh.cpu().numpy()
+    for i in range(0, xc.size, 37):
+        win = oracle.cut_window(spec, 100e3, xc[i], yc[i])
+        if detrend:
+            win = oracle.detrend_plane(win)
+        _, p0, _ = oracle.radial_spectrum(win, spec.dx)
+        np.testing.assert_allclose(ph[i], p0, rtol=1e-10)
+
+
 def test_spectrum_properties_full_size(pc):
     """Size-independent properties on a BASELINE-sized window set (4096-wide grid, 201-node windows):
     scaling the data by a shifts Phi by power*ln(a) and leaves sigma; identical windows give identical
