@@ -372,14 +372,24 @@ struct StaticFft {
     static constexpr int FUSED_SPAN = HALF * (N / R0);   // the engine serves windows with n <= FUSED_SPAN
 
     template <class Loader> CB_HD static void first_pass(double2 *buf, const double2 *tw, int lane, Loader ld) {
-        constexpr int R = R0, SUB = N / R0, NB = N / R;
+        constexpr int R = R0, SUB = N / R0, NB = N / R, NIT = (NB + CB_WARP - 1) / CB_WARP;
+        // every input of every butterfly of this lane is requested before the first one is used: the
+        // loads come from L2 / HBM (grid rows, shared row spectra) and their latency is paid once per line
+        double2 in[NIT][HALF];
 #pragma unroll
-        for (int b0 = 0; b0 < NB; b0 += CB_WARP) {
-            const int j = b0 + lane;                     // LEN == N: blk = 0
+        for (int it = 0; it < NIT; ++it) {
+            const int j = it * CB_WARP + lane;
+#pragma unroll
+            for (int t = 0; t < HALF; ++t)
+                in[it][t] = (NB % CB_WARP == 0 || j < NB) ? ld(j + t * SUB) : cplx(0.0, 0.0);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int j = it * CB_WARP + lane;                     // LEN == N: blk = 0
             if (NB % CB_WARP != 0 && j >= NB) break;
             double2 v[R];
 #pragma unroll
-            for (int t = 0; t < R; ++t) v[t] = t < HALF ? ld(j + t * SUB) : cplx(0.0, 0.0);
+            for (int t = 0; t < R; ++t) v[t] = t < HALF ? in[it][t] : cplx(0.0, 0.0);
             if (R == 8) dft8_half_in(v);
             else Dft<R>::run(v);
             double2 w[R];

@@ -11,7 +11,7 @@ struct cb_spectrum_plan {
     SpectrumHostPlan hp;
     int device = 0, sm_count = 0, occupancy = 1, grid_max = 0;
     double2 *d_tw = nullptr, *d_chirp = nullptr, *d_filt = nullptr;
-    int32_t *d_slot = nullptr, *d_bin_ptr = nullptr, *d_bin_idx = nullptr;
+    int32_t *d_slot = nullptr, *d_bin_ptr = nullptr, *d_bin_idx = nullptr, *d_col_span = nullptr;
     double *d_taper_r = nullptr, *d_taper_c = nullptr;
     double2 *d_plane_t0 = nullptr, *d_plane_t1 = nullptr;
     spectrum_kernel_fn kernel = nullptr, row_kernel = nullptr, col_kernel = nullptr;
@@ -87,7 +87,7 @@ int cb_spectrum_plan_destroy(cb_spectrum_plan *plan) {
     if (!plan) return CB_OK;
     cudaFree(plan->d_tw); cudaFree(plan->d_chirp); cudaFree(plan->d_filt); cudaFree(plan->d_slot);
     cudaFree(plan->d_bin_ptr); cudaFree(plan->d_bin_idx); cudaFree(plan->d_taper_r); cudaFree(plan->d_taper_c);
-    cudaFree(plan->d_plane_t0); cudaFree(plan->d_plane_t1);
+    cudaFree(plan->d_plane_t0); cudaFree(plan->d_plane_t1); cudaFree(plan->d_col_span);
     delete plan;
     return CB_OK;
 }
@@ -123,7 +123,7 @@ int cb_spectrum_plan_create(int nw, int nbins, const double *taper_r, const doub
 #define UP(dst, src) if ((rc = upload(&pl->dst, hp.src)) != CB_OK) { cb_spectrum_plan_destroy(pl); return rc; }
     UP(d_tw, tw) UP(d_chirp, chirp) UP(d_filt, filt) UP(d_slot, slot)
     UP(d_bin_ptr, bin_ptr) UP(d_bin_idx, bin_idx) UP(d_taper_r, taper_r) UP(d_taper_c, taper_c)
-    UP(d_plane_t0, plane_t0) UP(d_plane_t1, plane_t1)
+    UP(d_plane_t0, plane_t0) UP(d_plane_t1, plane_t1) UP(d_col_span, col_span)
 #undef UP
     // the attribute belongs to the kernel, not to the plan: raise it once to the device limit so that
     // plans with different line lengths can coexist
@@ -197,7 +197,7 @@ int cb_spectrum_batch(const cb_spectrum_plan *plan, const double *grid_dev, int6
     SpectrumParams P;
     memset(&P, 0, sizeof(P));
     spectrum_fill_params(hp, P, plan->d_tw, plan->d_chirp, plan->d_filt, plan->d_slot, plan->d_taper_r,
-                         plan->d_taper_c, plan->d_bin_ptr, plan->d_bin_idx);
+                         plan->d_taper_c, plan->d_bin_ptr, plan->d_bin_idx, plan->d_col_span);
     P.grid = grid_dev; P.ld = ld; P.iy0 = iy0_dev; P.ix0 = ix0_dev; P.nwin = nwin;
     P.detrend = detrend ? 1 : 0; P.power = power;
     P.phi = phi_dev; P.sigma = sigma_dev;
@@ -237,12 +237,13 @@ int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan, const double *gr
     SpectrumParams P;
     memset(&P, 0, sizeof(P));
     spectrum_fill_params(hp, P, plan->d_tw, plan->d_chirp, plan->d_filt, plan->d_slot, plan->d_taper_r,
-                         plan->d_taper_c, plan->d_bin_ptr, plan->d_bin_idx);
+                         plan->d_taper_c, plan->d_bin_ptr, plan->d_bin_idx, plan->d_col_span);
     P.grid = grid_dev; P.ld = ld; P.iy0 = iy0_dev; P.ix0 = ix0_dev; P.nwin = nwin;
     P.detrend = detrend ? 1 : 0; P.power = power;
     P.phi = phi_dev; P.sigma = sigma_dev;
     P.lh = reinterpret_cast<double *>(base);          // the G^T part of the slab is not used on this path
     P.lh_stride = hp.ws_per_cta / 8;
+    P.lh_half = hp.lh_stride;                         // second slab (phase C of w overlaps phase B of w+1)
     P.group_of_win = group_of_win_dev; P.group_ix0 = group_ix0_dev; P.ngroups = ngroups;
     P.row_lo = row_lo; P.nrows_valid = row_hi - row_lo; P.nrows = (P.nrows_valid + 1) & ~1;
     P.rt = reinterpret_cast<double2 *>(((uintptr_t)rowspec_dev + 255) & ~(uintptr_t)255);

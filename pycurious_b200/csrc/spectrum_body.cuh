@@ -36,6 +36,7 @@ struct SpectrumParams {
     const int32_t *slot;      // n: slot of X[k] after DIF (direct mode)
     const double *taper_r, *taper_c;   // n each, or NULL
     const int32_t *bin_ptr, *bin_idx;  // folded CSR, ids v*n+u
+    const int32_t *col_span;           // [nvh] (lo | hi << 16): only u in [lo, hi] of column v belong to a bin
     int32_t nbins;
     int32_t detrend;
     double power;
@@ -45,6 +46,7 @@ struct SpectrumParams {
     double2 *gt;              // [nvh][npad]
     double *lh;               // [nvh][n]
     int64_t gt_stride, lh_stride;   // elements per CTA
+    int64_t lh_half;                // colspec_body: offset of the CTA's second log-modulus slab
     // shared-memory carve-up (in double2 slots)
     int32_t sm_tw, sm_filt, sm_chirp, sm_cw, sm_buf, line_slots;
     // shared-row-spectra path (rowspec_body / colspec_body): windows with the same ix0 share the
@@ -268,9 +270,11 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                     if (y >= n) return cplx(0.0, 0.0);
                     return cmul(Ctx::ldcg(col + y), s_chirp[y]);
                 };
-                // |chirp| = 1, so the modulus needs no post-multiply; outputs go straight to the slab
+                // |chirp| = 1, so the modulus needs no post-multiply; outputs go straight to the slab.
+                // The log is only taken where a radial bin will read it (the corners of the plane lie outside).
+                const int span = Ctx::ldg(P.col_span + v), ulo = span & 0xffff, uhi = span >> 16;
                 auto sk = [&](int u, double2 z) {
-                    if (u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    if (u >= ulo && u <= uhi) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
                 };
                 Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
             }
@@ -412,9 +416,14 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
     double *s_red = reinterpret_cast<double *>(sm);
     spectrum_stage_tables(cx, P, s_tw, s_filt, s_chirp, s_rw, P.taper_r);     // s_rw = row taper (x chirp)
 
-    double *Lh = P.lh + (int64_t)cx.bid() * P.lh_stride;
+    // two log-modulus slabs per CTA: the bins of window w (phase C) are read from one while the columns
+    // of window w+1 (phase B) already fill the other -- one block barrier per window, and the gather
+    // latency of phase C hides behind the transforms of the warps that are already ahead
+    double *Lh2[2] = {P.lh + (int64_t)cx.bid() * P.lh_stride, P.lh + (int64_t)cx.bid() * P.lh_stride + P.lh_half};
     const double ctr = 0.5 * (double)(n - 1);
-    for (int64_t w = cx.bid(); w < P.nwin; w += cx.nblocks()) {
+    int parity = 0;
+    for (int64_t w = cx.bid(); w < P.nwin; w += cx.nblocks(), parity ^= 1) {
+        double *Lh = Lh2[parity];
         const int iy0 = P.iy0[w], g = P.group_of_win[w];
         double c0 = 0.0, cx1 = 0.0, cy1 = 0.0;
         if (P.detrend)
@@ -442,8 +451,9 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
             if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
                 fused = true;
                 auto ld = [&](int y) -> double2 { return y < n ? element(y) : cplx(0.0, 0.0); };
+                const int span = Ctx::ldg(P.col_span + v), ulo = span & 0xffff, uhi = span >> 16;
                 auto sk = [&](int u, double2 z) {
-                    if (u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    if (u >= ulo && u <= uhi) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
                 };
                 Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
             }
@@ -459,9 +469,8 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
             }
             cx.sync_warp();
         }
-        cx.sync_block();
+        cx.sync_block();       // all columns of w are in Lh; every warp has left phase C of w-1 (other slab)
         bin_phase(cx, P, Lh, w, warp, lane, nwarps);
-        cx.sync_block();       // the next window's phase B overwrites Lh
     }
 }
 

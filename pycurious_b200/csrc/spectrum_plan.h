@@ -15,7 +15,7 @@ struct SpectrumHostPlan {
     std::vector<double> taper_r, taper_c;
     std::vector<double2> plane_t0, plane_t1;   // x-transforms of taper_c and (x - ctr) taper_c, v < nvh
     bool has_taper = false;
-    std::vector<int32_t> bin_ptr, bin_idx;
+    std::vector<int32_t> bin_ptr, bin_idx, col_span;
     int nnz_full = 0;
     // shared memory layout (double2 slots) and launch shape
     int sm_tw = 0, sm_filt = 0, sm_chirp = 0, sm_cw = 0, sm_buf = 0, line_slots = 0;
@@ -114,6 +114,16 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
     for (int e = bin_ptr[0]; e < bin_ptr[nbins]; ++e)
         if (bin_idx[e] < 0 || bin_idx[e] >= nw * nw) { hp.error = "bin_idx out of range"; return false; }
     fold_bins(nw, nbins, bin_ptr, bin_idx, hp.bin_ptr, hp.bin_idx);
+    {   // per half-plane column the range of u that any bin reads (lo > hi: none)
+        std::vector<int> lo(hp.nvh, 0xffff), hi(hp.nvh, -1);
+        for (int32_t id : hp.bin_idx) {
+            const int v = id / nw, u = id % nw;
+            lo[v] = std::min(lo[v], u);
+            hi[v] = std::max(hi[v], u);
+        }
+        hp.col_span.resize(hp.nvh);
+        for (int v = 0; v < hp.nvh; ++v) hp.col_span[v] = hi[v] < 0 ? 0x0000ffff : (lo[v] | (hi[v] << 16));
+    }
 
     hp.line_slots = (fft_line_slots(hp.fft.n) + 1) & ~1;
     hp.sm_tw = CB_SPEC_RED_SLOTS;
@@ -125,6 +135,12 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
     int teams = (int)std::min<int64_t>(max_teams, slots_avail / hp.line_slots);
     if (teams < 1) { hp.error = "window too large for the shared-memory FFT line"; return false; }
     teams = std::min(teams, std::max(1, hp.nvh));
+    // Two CTAs of 8 teams per SM beat one of 16 (r01h: 84.0 vs 86.5 ms): the CTAs drift apart, so one
+    // transforms while the other waits on its block barrier or on the bin gathers.  228 KB of shared
+    // memory per SM, 1 KB reserved per CTA.
+    if (teams == CB_SPEC_MAX_TEAMS && max_teams == CB_SPEC_MAX_TEAMS &&
+        16 * ((int64_t)hp.sm_buf + 8 * (int64_t)hp.line_slots) <= (228 / 2 - 1) * 1024)
+        teams = 8;
     hp.teams = teams;
     hp.threads = teams * CB_WARP;
     hp.smem_bytes = 16 * ((int64_t)hp.sm_buf + (int64_t)teams * hp.line_slots);
@@ -139,12 +155,13 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
 static inline void spectrum_fill_params(const SpectrumHostPlan &hp, SpectrumParams &P, const double2 *tw,
                                         const double2 *chirp, const double2 *filt, const int32_t *slot,
                                         const double *taper_r, const double *taper_c,
-                                        const int32_t *bin_ptr, const int32_t *bin_idx) {
+                                        const int32_t *bin_ptr, const int32_t *bin_idx,
+                                        const int32_t *col_span) {
     P.n = hp.n; P.nvh = hp.nvh; P.npad = hp.npad; P.bluestein = hp.bluestein; P.fft = hp.fft;
     P.tw = tw; P.chirp = chirp; P.filt = filt; P.slot = slot;
     P.taper_r = hp.has_taper ? taper_r : nullptr;
     P.taper_c = hp.has_taper ? taper_c : nullptr;
-    P.bin_ptr = bin_ptr; P.bin_idx = bin_idx; P.nbins = hp.nbins;
+    P.bin_ptr = bin_ptr; P.bin_idx = bin_idx; P.nbins = hp.nbins; P.col_span = col_span;
     P.gt_stride = hp.gt_stride; P.lh_stride = hp.lh_stride;
     P.sm_tw = hp.sm_tw; P.sm_filt = hp.sm_filt; P.sm_chirp = hp.sm_chirp; P.sm_cw = hp.sm_cw; P.sm_buf = hp.sm_buf;
     P.line_slots = hp.line_slots;

@@ -118,7 +118,7 @@ int emu_spectrum(int nw, int nbins, const double *taper_r, const double *taper_c
     SpectrumParams P;
     memset(&P, 0, sizeof(P));
     spectrum_fill_params(hp, P, hp.tw.data(), hp.chirp.data(), hp.filt.data(), hp.slot.data(),
-                         hp.taper_r.data(), hp.taper_c.data(), hp.bin_ptr.data(), hp.bin_idx.data());
+                         hp.taper_r.data(), hp.taper_c.data(), hp.bin_ptr.data(), hp.bin_idx.data(), hp.col_span.data());
     P.grid = grid; P.ld = ld; P.iy0 = iy0; P.ix0 = ix0; P.nwin = nwin;
     P.detrend = detrend; P.power = power; P.phi = phi; P.sigma = sigma;
     std::vector<double2> gt((size_t)nblocks * hp.gt_stride);
@@ -166,14 +166,14 @@ int emu_spectrum_shared(int nw, int nbins, const double *taper_r, const double *
     SpectrumParams P;
     memset(&P, 0, sizeof(P));
     spectrum_fill_params(hp, P, hp.tw.data(), hp.chirp.data(), hp.filt.data(), hp.slot.data(),
-                         hp.taper_r.data(), hp.taper_c.data(), hp.bin_ptr.data(), hp.bin_idx.data());
+                         hp.taper_r.data(), hp.taper_c.data(), hp.bin_ptr.data(), hp.bin_idx.data(), hp.col_span.data());
     P.grid = grid; P.ld = ld; P.iy0 = iy0; P.ix0 = ix0; P.nwin = nwin;
     P.detrend = detrend; P.power = power; P.phi = phi; P.sigma = sigma;
     P.group_of_win = gof.data(); P.group_ix0 = gix.data(); P.ngroups = (int)gix.size();
     P.row_lo = row_lo; P.nrows_valid = row_hi - row_lo; P.nrows = (P.nrows_valid + 1) & ~1;
     std::vector<double2> rt((size_t)P.ngroups * hp.nvh * P.nrows);
-    std::vector<double> lh((size_t)nblocks * hp.lh_stride);
-    P.rt = rt.data(); P.lh = lh.data();
+    std::vector<double> lh((size_t)nblocks * 2 * hp.lh_stride);
+    P.rt = rt.data(); P.lh = lh.data(); P.lh_stride = 2 * hp.lh_stride; P.lh_half = hp.lh_stride;
     P.plane_t0 = hp.plane_t0.data(); P.plane_t1 = hp.plane_t1.data();
     (void)ny;
     const bool generic = max_teams < 0 || !hp.bluestein;

@@ -11,6 +11,6 @@ for l in sys.stdin:
     else: print(l.rstrip()[-300:])
 "
 }
-run CB_SPEC_GENERIC=1
 run CB_SPEC_TEAMS=16
 run CB_SPEC_TEAMS=8
+run CB_SPEC_TEAMS=12

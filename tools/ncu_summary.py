@@ -85,7 +85,7 @@ def line_map(func):
 
 
 for kn in dict.fromkeys(names):
-    short = kn.split("(")[0]
+    short = re.split(r"[(<]", kn.replace("void ", ""))[0].strip()
     src = list(csv.reader(io.StringIO(run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + short]))))
     try:
         h = next(i for i, r in enumerate(src) if len(r) > 5 and r[0] == "Address")
