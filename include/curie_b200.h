@@ -185,6 +185,23 @@ int cb_fit_batch(const double *kh_dev, int nk,
                  int32_t *nfev_dev /* [nwin] or NULL: model evaluations of nk points each */,
                  void *stream);
 
+/* Same fit with per-row prior means: prior_mu_dev[w, j] (NaN = keep opt->prior_mu[j]) replaces the
+ * mean of the prior on parameter j for row w; a prior exists iff opt->prior_mu[j] is not NaN.  This is
+ * the inner loop of CurieOptimise.sensitivity (optimise.py:705-716): each row is one simulation with its
+ * own perturbed spectrum and its own draw of the prior means. */
+int cb_fit_batch_rows(const double *kh_dev, int nk,
+                      const double *phi_dev /* [nrow, nk] */, int64_t nrow,
+                      const cb_fit_options *opt_host,
+                      const double *x0_dev /* [nrow,4] or NULL */,
+                      const double *prior_mu_dev /* [nrow,4] or NULL */,
+                      double *x_out_dev, double *f_out_dev, int32_t *niter_dev, int32_t *status_dev,
+                      int32_t *nfev_dev, void *stream);
+
+/* out[(w*nsim + s), j] = phi[w, j] + sigma[w, j] * z,  z ~ N(0,1) from Philox4x32-10 keyed by
+ * (seed, window_offset + w): the spectra perturbation of sensitivity (optimise.py:714), nsim rows per window. */
+int cb_perturb_spectra(const double *phi_dev, const double *sigma_dev, int64_t nwin, int nk, int64_t nsim,
+                       uint64_t seed, uint64_t window_offset, double *out_dev /* [nwin*nsim, nk] */, void *stream);
+
 /* ------------------------------------------------------------------------
  * Metropolis-Hastings:  CurieOptimise.metropolis_hastings (optimise.py:511-633)
  * One chain per warp, Philox4x32-10 counter-based stream keyed by (seed, chain id).

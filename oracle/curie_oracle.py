@@ -243,6 +243,13 @@ def polished_fit(kh, phi, x_start, bounds=DEFAULT_BOUNDS,
     return x, f
 
 
+def sensitivity_rows(kh, phi_rows, prior_mu_rows, prior_sigma, x0=(3.0, 1.0, 10.0, 5.0), bounds=DEFAULT_BOUNDS):
+    """The loop body of CurieOptimise.sensitivity (optimise.py:705-716) for given draws: row s is one
+    simulation with its perturbed spectrum phi_rows[s] and its redrawn prior means prior_mu_rows[s]."""
+    return np.array([map_fit(kh, phi_rows[s], x0, bounds, prior_mu_rows[s], prior_sigma)
+                     for s in range(len(phi_rows))])
+
+
 def window_fit(g: GridSpec, window, xc, yc, x0=(3.0, 1.0, 10.0, 5.0), taper=np.hanning,
                detrend=False, bounds=DEFAULT_BOUNDS, prior_mu=NO_PRIOR[0],
                prior_sigma=NO_PRIOR[1], **kw):
@@ -363,6 +370,30 @@ class PhiloxStream:
 
     def uniform(self):
         return self._pending_uniform
+
+
+def perturbed_spectra_philox(phi, sigma, nsim, seed, window=0):
+    """Replica of the device's cb_perturb_spectra stream for one window: rows (nsim, nbins) of
+    phi + sigma * z with z from Philox4x32-10, key (seed ^ window), counter (sim*nq + q, hi, j, phase 2)."""
+    phi, sigma = np.asarray(phi, dtype=float), np.asarray(sigma, dtype=float)
+    nk = phi.size
+    nq = (nk + 3) // 4
+    rng = PhiloxStream(seed, window)
+    rng.phase = 2
+    out = np.empty((nsim, nk))
+    for sim in range(nsim):
+        for q in range(nq):
+            rng.t = sim * nq + q
+            a, b = rng._block(0), rng._block(1)
+            u = [_u53(a[0], a[1]), _u53(a[2], a[3]), _u53(b[0], b[1]), _u53(b[2], b[3])]
+            for p in range(2):
+                r = np.sqrt(-2.0 * np.log(u[2 * p]))
+                ang = 2.0 * np.pi * u[2 * p + 1]
+                for t, zz in ((2 * p, r * np.cos(ang)), (2 * p + 1, r * np.sin(ang))):
+                    j = 4 * q + t
+                    if j < nk:
+                        out[sim, j] = phi[j] + sigma[j] * zz
+    return out
 
 
 def mh_chain_philox(kh, phi, nsim, burnin, seed, chain, **kw):

@@ -30,6 +30,7 @@ struct FitParams {
     int64_t nwin;
     cb_fit_options opt;
     const double *x0_dev;   // [nwin,4] or NULL
+    const double *prior_mu_dev;   // [nwin,4] or NULL: per-row prior means (sensitivity), NaN = opt.prior_mu[j]
     double *x_out;          // [nwin,4]
     double *f_out;          // [nwin] or NULL
     int32_t *niter;         // [nwin] or NULL
@@ -153,13 +154,15 @@ CB_HD void fit_set_trial(FitState *S) {
 
 // ---- lane-0 phases ------------------------------------------------------------------------------
 // Start: clip x0 into the bounds (scipy does, _lbfgsb_py.py:359) and into the cosh wall.
-CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const double *x0, double kmin, double kmax) {
+CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const double *x0, const double *row_mu,
+                               double kmin, double kmax) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         S->lb[j] = o->lb[j];
         S->ub[j] = o->ub[j];
-        const bool has = !isnan(o->prior_mu[j]);
-        S->pmu[j] = has ? o->prior_mu[j] : 0.0;
+        const bool has = !isnan(o->prior_mu[j]);           // a prior exists iff the options carry one
+        const double mu = (row_mu && !isnan(row_mu[j])) ? row_mu[j] : o->prior_mu[j];
+        S->pmu[j] = has ? mu : 0.0;
         S->pw[j] = has ? 1.0 / (o->prior_sigma[j] * o->prior_sigma[j]) : 0.0;
     }
     if (kmax > 0.0) {
@@ -460,7 +463,9 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     const double gtol = o->gtol > 0.0 ? o->gtol : 1e-9;
     const double ftol = o->ftol > 0.0 ? o->ftol : 1e-15;
 
-    if (lane == 0) fit_init(S, o, P.x0_dev ? P.x0_dev + w * 4 : o->x0, W.sorted ? W.kmin : 0.0, W.sorted ? W.kmax : 0.0);
+    if (lane == 0)
+        fit_init(S, o, P.x0_dev ? P.x0_dev + w * 4 : o->x0, P.prior_mu_dev ? P.prior_mu_dev + w * 4 : nullptr,
+                 W.sorted ? W.kmin : 0.0, W.sorted ? W.kmax : 0.0);
     cx.sync_warp();
     W.cu = S->cu;
 

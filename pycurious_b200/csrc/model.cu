@@ -74,6 +74,28 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) mh
     mh_body(cx, P);
 }
 
+// rPhi = Phi + sigma_Phi * N(0,1) (optimise.py:714): row (w, s) of the output is simulation s of window w.
+// Philox4x32-10 keyed by (seed, global window index), counter = (simulation, quad of bins, 0, phase 2).
+__global__ void __launch_bounds__(256)
+perturb_kernel(const double *phi, const double *sigma, int64_t nwin, int nk, int64_t nsim, uint64_t seed,
+               uint64_t window_offset, double *out) {
+    const int nq = (nk + 3) / 4;
+    const int64_t total = nwin * nsim * nq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % nq);
+        const int64_t row = i / nq, w = row / nsim, sim = row - w * nsim;
+        const uint64_t chain = window_offset + (uint64_t)w;
+        const uint32_t k0 = (uint32_t)(seed ^ chain), k1 = (uint32_t)((seed >> 32) ^ (chain >> 32));
+        double z[4];
+        philox_normal4((uint64_t)sim * (uint64_t)nq + (uint64_t)q, 2u, k0, k1, z);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = 4 * q + t;
+            if (j < nk) out[row * nk + j] = fma(sigma[w * nk + j], z[t], phi[w * nk + j]);
+        }
+    }
+}
+
 static int elementwise_grid(int64_t n) {
     int64_t g = (n + 255) / 256;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -147,9 +169,10 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
     return CB_OK;
 }
 
-int cb_fit_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwin, const cb_fit_options *opt_host,
-                 const double *x0_dev, double *x_out_dev, double *f_out_dev, int32_t *niter_dev,
-                 int32_t *status_dev, int32_t *nfev_dev, void *stream) {
+int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64_t nwin,
+                      const cb_fit_options *opt_host, const double *x0_dev, const double *prior_mu_dev,
+                      double *x_out_dev, double *f_out_dev, int32_t *niter_dev, int32_t *status_dev,
+                      int32_t *nfev_dev, void *stream) {
     CB_REQUIRE(nwin >= 0, "nwin < 0");
     if (nwin == 0) return CB_OK;
     CB_REQUIRE(kh_dev && phi_dev && opt_host && x_out_dev, "NULL buffer");
@@ -165,10 +188,32 @@ int cb_fit_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nw
     FitParams P;
     memset(&P, 0, sizeof(P));
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
+    P.prior_mu_dev = prior_mu_dev;
     P.x_out = x_out_dev; P.f_out = f_out_dev; P.niter = niter_dev; P.status = status_dev; P.nfev = nfev_dev;
     P.warps_per_block = CB_FIT_WARPS;
     if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     fit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_fit_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwin, const cb_fit_options *opt_host,
+                 const double *x0_dev, double *x_out_dev, double *f_out_dev, int32_t *niter_dev,
+                 int32_t *status_dev, int32_t *nfev_dev, void *stream) {
+    return cb_fit_batch_rows(kh_dev, nk, phi_dev, nwin, opt_host, x0_dev, nullptr, x_out_dev, f_out_dev, niter_dev,
+                             status_dev, nfev_dev, stream);
+}
+
+int cb_perturb_spectra(const double *phi_dev, const double *sigma_dev, int64_t nwin, int nk, int64_t nsim,
+                       uint64_t seed, uint64_t window_offset, double *out_dev, void *stream) {
+    CB_REQUIRE(nwin >= 0 && nsim >= 0 && nk > 0, "bad sizes");
+    if (nwin == 0 || nsim == 0) return CB_OK;
+    CB_REQUIRE(phi_dev && sigma_dev && out_dev, "NULL buffer");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    const int64_t quads = nwin * nsim * (((int64_t)nk + 3) / 4);
+    perturb_kernel<<<elementwise_grid(quads), 256, 0, (cudaStream_t)stream>>>(phi_dev, sigma_dev, nwin, nk, nsim, seed,
+                                                                              window_offset, out_dev);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }

@@ -224,6 +224,15 @@ class CurieOptimise(CurieGrid):
                 reduce="chains", **a["kwargs"])
             return [[chains[i, j] for i in range(n)] for j in range(4)]
 
+        if self._is_own(func, "sensitivity"):
+            b = inspect.signature(CurieOptimise.sensitivity).bind(self, window, 0.0, 0.0, *args, **kwargs)
+            b.apply_defaults()
+            a = b.arguments
+            x = self.sensitivity_batch(window, xc_list, yc_list, a["nsim"], beta=a["beta"], zt=a["zt"], dz=a["dz"],
+                                       C=a["C"], taper=a["taper"], process_subgrid=a["process_subgrid"],
+                                       seed=a["seed"], **a["kwargs"])
+            return [[x[i, :, j] for i in range(n)] for j in range(4)]
+
         res = None
         xOpt = [[] for _ in range(n)]
         for i in range(n):
@@ -295,6 +304,63 @@ class CurieOptimise(CurieGrid):
         self.last_accepted = acc
         return out.cpu().numpy() if as_numpy else out
 
-    def sensitivity(self, *args, **kwargs):
-        raise NotImplementedError("sensitivity() is the next item after the hot path (SURVEY.md 8f item 1); "
-                                  "it will reuse the batched fit kernel")
+    # ------------------------------------------------------------------ sensitivity (optimise.py:635-725)
+    def _sensitivity_device(self, k, phi_t, sig_t, nsim, x0, seed, chain_offset=0):
+        """nsim perturbed re-fits for every row of phi_t: returns a cuda tensor (n, nsim, 4).
+        Spectra are perturbed on the device (cb_perturb_spectra); the prior means are redrawn on the host
+        with the priors' own `rvs` so that any scipy.stats distribution works (optimise.py:709-711)."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        n, nk = int(phi_t.shape[0]), int(phi_t.shape[1])
+        nsim = int(nsim)
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
+        rows = torch.empty((n * nsim, nk), dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_perturb_spectra(phi_t.data_ptr(), sig_t.data_ptr(), n, nk, nsim, int(seed) & (2 ** 64 - 1),
+                                          int(chain_offset), rows.data_ptr(), _lib.stream_ptr(torch)))
+        mu_rows = None
+        if any(self.prior_pdf[key] is not None for key in _KEYS):
+            mu = np.full((n * nsim, 4), np.nan)
+            for j, key in enumerate(_KEYS):
+                pdf = self.prior_pdf[key]
+                if pdf is not None:
+                    mu[:, j] = np.asarray(pdf.rvs(size=n * nsim), dtype=np.float64)
+            mu_rows = torch.from_numpy(mu).cuda()
+        opt = _lib.FitOptions()
+        lb, ub = self._bound_arrays()
+        pm, ps = self._prior_arrays()
+        for j in range(4):
+            opt.x0[j], opt.lb[j], opt.ub[j] = float(x0[j]), lb[j], ub[j]
+            opt.prior_mu[j], opt.prior_sigma[j] = pm[j], ps[j]
+        k_t = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float64)).cuda()
+        x_t = torch.empty((n * nsim, 4), dtype=torch.float64, device="cuda")
+        _lib.check(lib.cb_fit_batch_rows(k_t.data_ptr(), k_t.numel(), rows.data_ptr(), n * nsim, C.byref(opt), None,
+                                         _lib.ptr(mu_rows), x_t.data_ptr(), None, None, None, None,
+                                         _lib.stream_ptr(torch)))
+        return x_t.view(n, nsim, 4)
+
+    def sensitivity(self, window, xc, yc, nsim, beta=3.0, zt=1.0, dz=10.0, C=5.0, taper=np.hanning,
+                    process_subgrid=None, seed=None, **kwargs):
+        """Monte-Carlo sensitivity of (beta, zt, dz, C) for one centroid: `nsim` re-fits with the spectrum
+        drawn from N(Phi, sigma_Phi) and the prior means redrawn from their distributions
+        (optimise.py:635-725).  Returns [beta(nsim,), zt(nsim,), dz(nsim,), C(nsim,)]; all nsim fits run
+        in one launch.  `seed=None` takes the seed from numpy's global RNG."""
+        k, phi, sig = self._batch_spectra(window, [xc], [yc], taper, process_subgrid, kwargs)
+        x = self._sensitivity_device(k, phi, sig, nsim, (beta, zt, dz, C), seed)
+        return list(np.ascontiguousarray(x[0].cpu().numpy().T))
+
+    def sensitivity_batch(self, window, xc_list, yc_list, nsim, *, beta=3.0, zt=1.0, dz=10.0, C=5.0,
+                          taper=np.hanning, process_subgrid=None, seed=None, reduce="samples", chain_offset=0,
+                          as_numpy=True, **kwargs):
+        """sensitivity for every centroid in one launch of n*nsim fits.
+        reduce='samples' -> (n, nsim, 4);  reduce='moments' -> (n, 8): mean then std (population) of
+        (beta, zt, dz, C) over the simulations -- the uncertainty maps of the reference's notebooks."""
+        self._check_lists(xc_list, yc_list)
+        if reduce not in ("samples", "moments"):
+            raise ValueError("reduce must be 'samples' or 'moments'")
+        k, phi, sig = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
+        x = self._sensitivity_device(k, phi, sig, nsim, (beta, zt, dz, C), seed, chain_offset)
+        if reduce == "moments":
+            import torch
+            x = torch.cat([x.mean(dim=1), x.std(dim=1, unbiased=False)], dim=1)
+        return x.cpu().numpy() if as_numpy else x

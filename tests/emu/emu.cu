@@ -249,6 +249,22 @@ int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_
     return 0;
 }
 
+// fit with per-row prior means (the inner loop of CurieOptimise.sensitivity)
+int emu_fit_rows(const double *kh, int nk, const double *phi, int64_t nwin, const cb_fit_options *opt,
+                 const double *prior_mu_rows, double *x_out, double *f_out) {
+    FitParams P;
+    memset(&P, 0, sizeof(P));
+    P.kh = kh; P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.prior_mu_dev = prior_mu_rows;
+    P.x_out = x_out; P.f_out = f_out;
+    P.warps_per_block = 1;
+    std::vector<double> sm(fit_slab_doubles(nk));
+    for (int64_t w = 0; w < nwin; ++w) {
+        SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
+        fit_body(cx, P);
+    }
+    return 0;
+}
+
 int emu_mh(const double *kh, int nk, const double *phi, int64_t nwin, const cb_mh_options *opt, const double *x0,
            double *out, int64_t *accepted, int mode) {
     MhParams P;

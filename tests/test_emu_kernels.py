@@ -403,6 +403,30 @@ def test_radon_bodies_bit_exact(emu, oracle, mag):
         np.testing.assert_allclose(S[0], g["n%d_az_S" % nw], rtol=1e-11)
 
 
+def test_fit_rows_with_per_row_priors_match_oracle(emu, oracle):
+    """cb_fit_batch_rows semantics (the inner loop of CurieOptimise.sensitivity, optimise.py:705-716): every
+    row has its own perturbed spectrum and its own prior means; priors without a row value keep the default."""
+    g = load_golden("fit.npz")
+    k, phi = g["w200_k"], g["w200_phi"][0]
+    rng = np.random.default_rng(3)
+    ns = 6
+    rows = np.ascontiguousarray(phi[None, :] + 0.3 * rng.standard_normal((ns, phi.size)))
+    mu = np.full((ns, 4), np.nan)
+    mu[:, 0], mu[:3, 1] = rng.normal(3.0, 0.5, ns), rng.normal(0.5, 0.25, 3)     # rows 3.. keep the default zt mean
+    sg = np.array([0.5, 0.25, np.nan, np.nan])
+    o = FitOpt()
+    for j in range(4):
+        o.x0[j], o.lb[j], o.ub[j] = [3, 1, 10, 5][j], [0, 0, 0, -np.inf][j], np.inf
+        o.prior_mu[j], o.prior_sigma[j] = [3.0, 0.5, np.nan, np.nan][j], sg[j]
+    x, f = np.empty((ns, 4)), np.empty(ns)
+    emu.emu_fit_rows(P(k), k.size, P(rows), C.c_int64(ns), C.byref(o), P(np.ascontiguousarray(mu)), P(x), P(f))
+    mu_eff = np.where(np.isnan(mu), np.array([3.0, 0.5, np.nan, np.nan]), mu)
+    ref = oracle.sensitivity_rows(k, rows, mu_eff, sg)
+    assert np.max(np.abs(x - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-4
+    for s in range(ns):
+        np.testing.assert_allclose(f[s], oracle.misfit(x[s], k, rows[s], mu_eff[s], sg), rtol=1e-11)
+
+
 def test_fit_is_insensitive_to_rounding_level_perturbations():
     """tools/emu_fit_stress.py: every golden case refitted from spectra perturbed at the 1e-13 level (the
     CUDA-vs-glibc math difference) must reach the polished minimum -- no rounding-dependent stalls."""

@@ -262,6 +262,52 @@ def test_fit_custom_process_subgrid_and_single(grid, oracle, mag):
     np.testing.assert_allclose(x_dev, xp, rtol=2e-5)
 
 
+def test_sensitivity_matches_reference_loop(grid, oracle, mag):
+    """CurieOptimise.sensitivity (optimise.py:635-725): the device draws N(Phi, sigma_Phi) with its Philox
+    stream; the oracle replays the same stream and runs the reference's loop body (L-BFGS-B) on the same
+    rows.  No priors here, so the rows are the only randomness."""
+    d, ext = mag
+    spec = oracle.GridSpec(d, *ext)
+    xc, yc = 152.5e3, 140.5e3
+    nsim, seed = 12, 424242
+    res = grid.sensitivity(200e3, xc, yc, nsim, seed=seed)
+    assert isinstance(res, list) and len(res) == 4 and all(r.shape == (nsim,) for r in res)
+    k, phi, sig = oracle.radial_spectrum(oracle.cut_window(spec, 200e3, xc, yc), spec.dx)
+    rows = oracle.perturbed_spectra_philox(phi, sig, nsim, seed, 0)
+    nan4 = np.full(4, np.nan)
+    ref = oracle.sensitivity_rows(k, rows, np.tile(nan4, (nsim, 1)), nan4)
+    ours = np.stack(res, axis=1)
+    good = 0
+    for s in range(nsim):
+        xp, fp = oracle.polished_fit(k, rows[s], ref[s])
+        conv = np.max(np.abs(ref[s] - xp) / np.maximum(np.abs(xp), 1e-3)) < 3e-5
+        f_ours = oracle.misfit(ours[s], k, rows[s])
+        assert f_ours <= oracle.misfit(ref[s], k, rows[s]) * (1 + 1e-9) + 1e-12
+        if conv:
+            good += 1
+            assert np.max(np.abs(ours[s] - ref[s]) / np.maximum(np.abs(ref[s]), 1e-3)) < 1e-4, (s, ours[s], ref[s])
+    assert good >= nsim // 2
+
+
+def test_sensitivity_priors_and_batch_containers(grid):
+    """Prior means are redrawn per simulation (optimise.py:709-711): with a tight prior on beta the spread of
+    the fitted beta follows the prior's width; parallelise_routine(self.sensitivity) keeps the reference's
+    nested containers; the batched call streams moments."""
+    grid.reset_priors()
+    grid.add_prior(beta=(3.0, 0.05))
+    try:
+        np.random.seed(7)
+        b, zt, dz, C = grid.sensitivity(200e3, 152.5e3, 140.5e3, 400)
+        assert abs(np.mean(b) - 3.0) < 0.03 and 0.02 < np.std(b) < 0.12
+        out = grid.parallelise_routine(200e3, [152.5e3, 150.5e3], [140.5e3, 149.5e3], grid.sensitivity, 16)
+        assert len(out) == 4 and len(out[0]) == 2 and out[0][0].shape == (16,)
+        mom = grid.sensitivity_batch(200e3, [152.5e3, 150.5e3], [140.5e3, 149.5e3], 64, reduce="moments", seed=3)
+        assert mom.shape == (2, 8) and np.all(mom[:, 4:] >= 0)
+    finally:
+        grid.reset_priors()
+    assert grid.prior["beta"] is None
+
+
 # --------------------------------------------------------------------------- Metropolis-Hastings
 def test_mh_chain_matches_reference_stream(grid):
     """Same Philox stream as the monkey-patched reference run: chains coincide step by step."""

@@ -81,6 +81,8 @@ def test_api_surface_matches_reference_signatures(pc):
     assert sig(O.parallelise_routine) == ["self", "window", "xc_list", "yc_list", "func", "args", "kwargs"]
     assert sig(O.metropolis_hastings)[:14] == ["self", "window", "xc", "yc", "nsim", "burnin", "x_scale", "beta", "zt",
                                                "dz", "C", "taper", "process_subgrid", "seed"]
+    assert sig(O.sensitivity)[:12] == ["self", "window", "xc", "yc", "nsim", "beta", "zt", "dz", "C", "taper",
+                                       "process_subgrid", "seed"]           # optimise.py:635-648 (+ keyword seed)
     assert sig(O.min_func) == ["self", "x", "kh", "Phi", "sigma_Phi"]
     d = inspect.signature(O.optimise).parameters
     assert (d["beta"].default, d["zt"].default, d["dz"].default, d["C"].default) == (3.0, 1.0, 10.0, 5.0)
