@@ -226,6 +226,16 @@ int cb_mh_batch(const double *kh_dev, int nk,
                 void *stream);
 
 /* ------------------------------------------------------------------------
+ * Tanaka et al. (1999):  tanaka1999 + ComputeTanaka (pycurious/grid.py:603-699) for a batch of
+ * radial spectra taken with power = 0.5.  out[w, 0..7] = Ztr, btr, dZtr, Zor, bor, dZor, Zb, eZb;
+ * (kmin_lo, kmin_hi) / (kmax_lo, kmax_hi) are the reference's kmin_range / kmax_range.
+ * ---------------------------------------------------------------------- */
+int cb_tanaka_batch(const double *k_dev, int nk,
+                    const double *lnphi_dev /* [nwin, nk] */, const double *sigma_dev /* [nwin, nk] */,
+                    int64_t nwin, double kmin_lo, double kmin_hi, double kmax_lo, double kmax_hi,
+                    double *out_dev /* [nwin, 8] */, void *stream);
+
+/* ------------------------------------------------------------------------
  * Radon transform:  src/cradon.c:4-246 + src/radon.pyx:12-120
  * ---------------------------------------------------------------------- */
 typedef struct cb_radon_plan cb_radon_plan;

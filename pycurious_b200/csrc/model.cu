@@ -3,6 +3,7 @@
 #include <cstring>
 #include "fit_body.cuh"
 #include "mh_body.cuh"
+#include "tanaka_body.cuh"
 
 extern __shared__ double cb_dyn_smem_d[];
 
@@ -94,6 +95,11 @@ perturb_kernel(const double *phi, const double *sigma, int64_t nwin, int nk, int
             if (j < nk) out[row * nk + j] = fma(sigma[w * nk + j], z[t], phi[w * nk + j]);
         }
     }
+}
+
+__global__ void __launch_bounds__(128) tanaka_kernel(const __grid_constant__ TanakaParams P) {
+    DevCtx cx{nullptr};
+    tanaka_body(cx, P);
 }
 
 static int elementwise_grid(int64_t n) {
@@ -214,6 +220,24 @@ int cb_perturb_spectra(const double *phi_dev, const double *sigma_dev, int64_t n
     const int64_t quads = nwin * nsim * (((int64_t)nk + 3) / 4);
     perturb_kernel<<<elementwise_grid(quads), 256, 0, (cudaStream_t)stream>>>(phi_dev, sigma_dev, nwin, nk, nsim, seed,
                                                                               window_offset, out_dev);
+    CB_CUDA_TRY(cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_tanaka_batch(const double *k_dev, int nk, const double *lnphi_dev, const double *sigma_dev, int64_t nwin,
+                    double kmin_lo, double kmin_hi, double kmax_lo, double kmax_hi, double *out_dev, void *stream) {
+    CB_REQUIRE(nwin >= 0 && nk > 0, "bad sizes");
+    if (nwin == 0) return CB_OK;
+    CB_REQUIRE(k_dev && lnphi_dev && sigma_dev && out_dev, "NULL buffer");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    TanakaParams P;
+    P.k = k_dev; P.nk = nk; P.lnphi = lnphi_dev; P.sigma = sigma_dev; P.nwin = nwin;
+    P.top_lo = kmin_lo; P.top_hi = kmin_hi; P.cen_lo = kmax_lo; P.cen_hi = kmax_hi;
+    P.out = out_dev; P.warps_per_block = 4;
+    const int64_t g = (nwin + 3) / 4;
+    CB_REQUIRE(g <= 2147483647LL, "too many windows for one launch");
+    tanaka_kernel<<<(int)g, 128, 0, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }

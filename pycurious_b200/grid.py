@@ -217,6 +217,23 @@ class CurieGrid(object):
         kbins, S, dtheta = self._azimuthal_device(self.device_grid(), iy0, ix0, n, taper, power, theta, **kwargs)
         return kbins, S.cpu().numpy(), dtheta
 
+    def tanaka_batch(self, window, xc_list, yc_list, *, kmin_range=(0.05, 0.2), kmax_range=(0.05, 0.2),
+                     taper=np.hanning, detrend=False, as_numpy=True, **kwargs):
+        """Tanaka et al. (1999) for every centroid: radial_spectrum(power=0.5) -> tanaka1999 -> ComputeTanaka
+        (grid.py:603-699), all on the device.  Returns an (n, 8) array with columns
+        Ztr, btr, dZtr, Zor, bor, dZor, Zb, eZb."""
+        torch = _lib.require_cuda()
+        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+        plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
+        phi, sig = plan.run(self.device_grid(), iy0, ix0, detrend, 0.5)
+        k_t = torch.from_numpy(np.ascontiguousarray(plan.k)).cuda()
+        out = torch.empty((phi.shape[0], 8), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().cb_tanaka_batch(k_t.data_ptr(), k_t.numel(), phi.data_ptr(), sig.data_ptr(),
+                                               phi.shape[0], float(kmin_range[0]), float(kmin_range[1]),
+                                               float(kmax_range[0]), float(kmax_range[1]), out.data_ptr(),
+                                               _lib.stream_ptr(torch)))
+        return out.cpu().numpy() if as_numpy else out
+
     def remove_trend_linear_batch(self, window, xc_list, yc_list):
         torch = _lib.require_cuda()
         iy0, ix0, n = self._origins_device(window, xc_list, yc_list)

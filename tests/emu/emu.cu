@@ -11,6 +11,7 @@
 #include "spectrum_plan.h"
 #include "fit_body.cuh"
 #include "mh_body.cuh"
+#include "tanaka_body.cuh"
 #include "radon_body.cuh"
 
 void cb_set_error(const char *fmt, ...) { (void)fmt; }
@@ -247,6 +248,14 @@ int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_
         emu_launch((int)((nwin + 1) / 2), 64, 2 * fit_slab_doubles(nk) * sizeof(double), [&](const HostCtx &cx) { fit_body(cx, P); });
     }
     return 0;
+}
+
+void emu_tanaka(const double *k, int nk, const double *lnphi, const double *sigma, int64_t nwin, double a0, double a1,
+                double b0, double b1, double *out) {
+    TanakaParams P;
+    P.k = k; P.nk = nk; P.lnphi = lnphi; P.sigma = sigma; P.nwin = nwin;
+    P.top_lo = a0; P.top_hi = a1; P.cen_lo = b0; P.cen_hi = b1; P.out = out; P.warps_per_block = 2;
+    emu_launch((int)((nwin + 1) / 2), 64, 64, [&](const HostCtx &cx) { tanaka_body(cx, P); });
 }
 
 // fit with per-row prior means (the inner loop of CurieOptimise.sensitivity)

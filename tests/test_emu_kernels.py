@@ -403,6 +403,25 @@ def test_radon_bodies_bit_exact(emu, oracle, mag):
         np.testing.assert_allclose(S[0], g["n%d_az_S" % nw], rtol=1e-11)
 
 
+def test_tanaka_body_matches_reference_formulas(emu, oracle):
+    """tanaka1999 + ComputeTanaka (grid.py:603-699) batched, one window per warp, against the oracle and the
+    reference's golden value."""
+    g = load_golden("spectrum.npz")
+    m = load_golden("misc.npz")
+    rng = np.random.default_rng(11)
+    k = load_golden("fit.npz")["w200_k"]
+    n = 5
+    lnphi = np.ascontiguousarray(10.0 - 8.0 * k[None, :] + 0.2 * rng.standard_normal((n, k.size)))
+    sig = np.ascontiguousarray(0.6 + 0.2 * rng.random((n, k.size)))
+    out = np.empty((n, 8))
+    emu.emu_tanaka.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_double] * 4 + [C.c_void_p]
+    emu.emu_tanaka(P(k), k.size, P(lnphi), P(sig), n, 0.005, 0.03, 0.03, 0.7, P(out))
+    for i in range(n):
+        top, cen = oracle.tanaka1999(k, lnphi[i], sig[i], (0.005, 0.03), (0.03, 0.7))
+        zb, ezb = oracle.compute_tanaka(top[0], top[2], cen[0], cen[2])
+        np.testing.assert_allclose(out[i], [*top, *cen, zb, ezb], rtol=1e-8)
+
+
 def test_fit_rows_with_per_row_priors_match_oracle(emu, oracle):
     """cb_fit_batch_rows semantics (the inner loop of CurieOptimise.sensitivity, optimise.py:705-716): every
     row has its own perturbed spectrum and its own prior means; priors without a row value keep the default."""

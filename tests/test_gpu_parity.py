@@ -135,6 +135,38 @@ def test_shared_row_spectra_path_equals_direct_path(pc, grid, oracle, mag, detre
         np.testing.assert_allclose(ph[i], p0, rtol=1e-10)
 
 
+def test_emag2_shaped_grid_far_corner(pc, oracle):
+    """BASELINE config 5 geometry: a 21600 x 10800 node grid (1.87 GB).  Windows in the far corner address
+    elements beyond 2^31 bytes; all three window sizes (101 / 201 / 301 nodes -> Bluestein 256 / 512 / 625),
+    scattered (direct path) and on a small lattice (shared row spectra)."""
+    ny, nx = 10800, 21600
+    rng = np.random.default_rng(99)
+    data = rng.standard_normal((ny, nx))
+    ext = pc.synth.grid_extent(ny, nx)
+    G = pc.CurieOptimise(data, *ext)
+    spec = oracle.GridSpec(data, *ext)
+    for window in (100e3, 200e3, 300e3):
+        half = (int(round(window / 1000.0)) // 2) * 1000.0
+        xs = np.array([ext[1] - half, ext[1] - half - 20e3, half, ext[1] - half])
+        ys = np.array([ext[3] - half, ext[3] - half - 20e3, ext[3] - half, half])
+        k, phi, sig = G.radial_spectrum_batch(window, xs, ys)
+        for i in range(xs.size):
+            k0, p0, s0 = oracle.radial_spectrum(oracle.cut_window(spec, window, xs[i], ys[i]), spec.dx)
+            assert np.array_equal(k, k0)
+            np.testing.assert_allclose(phi[i], p0, rtol=1e-10)
+            np.testing.assert_allclose(sig[i], s0, rtol=1e-9)
+    # lattice in the corner: 6 x 6 windows of 201 nodes, 20-node stride -> shared path (reuse >= 2)
+    xq, yq = np.meshgrid(ext[1] - 100e3 - 20e3 * np.arange(6), ext[3] - 100e3 - 20e3 * np.arange(6))
+    from pycurious_b200 import _plans
+    k, phi, sig = G.radial_spectrum_batch(200e3, xq.ravel(), yq.ravel())
+    assert _plans.spectrum_plan(201, G.dx, _plans.taper_vector(np.hanning, 201)).last_path == "shared_rows"
+    for i in (0, 7, 35):
+        _, p0, _ = oracle.radial_spectrum(oracle.cut_window(spec, 200e3, xq.ravel()[i], yq.ravel()[i]), spec.dx)
+        np.testing.assert_allclose(phi[i], p0, rtol=1e-10)
+    x = G.optimise_batch(200e3, xq.ravel()[:4], yq.ravel()[:4])
+    assert x.shape == (4, 4) and np.all(np.isfinite(x))
+
+
 def test_spectrum_properties_full_size(pc):
     """Size-independent properties on a BASELINE-sized window set (4096-wide grid, 201-node windows):
     scaling the data by a shifts Phi by power*ln(a) and leaves sigma; identical windows give identical
@@ -260,6 +292,20 @@ def test_fit_custom_process_subgrid_and_single(grid, oracle, mag):
     k, phi, _ = oracle.radial_spectrum(win, spec.dx)
     xp, fp = oracle.polished_fit(k, phi, oracle.map_fit(k, phi))
     np.testing.assert_allclose(x_dev, xp, rtol=2e-5)
+
+
+def test_tanaka_batch_matches_reference(pc, grid, oracle, mag):
+    """CurieGrid.tanaka_batch = radial_spectrum(power=0.5) -> tanaka1999 -> ComputeTanaka per centroid."""
+    d, ext = mag
+    spec = oracle.GridSpec(d, *ext)
+    xc, yc = grid.create_centroid_list(200e3, 40e3, 40e3)
+    out = grid.tanaka_batch(200e3, xc, yc, kmin_range=(0.005, 0.03), kmax_range=(0.03, 0.7))
+    assert out.shape == (xc.size, 8)
+    for i in range(0, xc.size, 3):
+        k, phi, sig = oracle.radial_spectrum(oracle.cut_window(spec, 200e3, xc[i], yc[i]), spec.dx, power=0.5)
+        top, cen = oracle.tanaka1999(k, phi, sig, (0.005, 0.03), (0.03, 0.7))
+        zb, ezb = oracle.compute_tanaka(top[0], top[2], cen[0], cen[2])
+        np.testing.assert_allclose(out[i], [*top, *cen, zb, ezb], rtol=1e-7)
 
 
 def test_sensitivity_matches_reference_loop(grid, oracle, mag):
