@@ -29,6 +29,7 @@
 // of the fit kernel inlined them at every call site, grew to 770 KB of SASS and spent 75 % of its
 // issue slots waiting on the instruction cache (profiles/r01_fit_icache.md).
 #pragma once
+#include <string.h>
 #include "bouligand.cuh"
 
 #define CB_MILLER_NMAX 97                     /* tables hold n = 0..97 */
@@ -158,6 +159,18 @@ CB_NOINLINE_BODY void model_coefs_warp(const Ctx &cx, const WarpSlab &W, const d
         W.coef[idx] = e;
     }
     cx.sync_warp();
+}
+
+// 2^-e for |v| = m 2^e, m in [1, 2) (1.0 for zero, subnormal, inf or nan): an exact scale factor.
+CB_HD double cb_pow2_inverse_of(double v) {
+    unsigned long long b;
+    memcpy(&b, &v, sizeof(b));
+    const unsigned long long ex = (b >> 52) & 0x7ffull;
+    if (ex == 0ull || ex >= 0x7feull) return 1.0;
+    const unsigned long long r = (0x7feull - ex) << 52;          // biased exponent of 2^-(ex-1023) is 2046 - ex
+    double o;
+    memcpy(&o, &r, sizeof(o));
+    return o;
 }
 
 // Reference-order arithmetic for one point (the slow, always-valid path).
@@ -303,9 +316,13 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
         }
         if (i < nS) {
             const double invx = W.rk[ii] * e.rdz;
-            const double cS = W.sq[ii] * e.rsdz / S;               // sqrt(pi/(2x)) / S
-            W.ka[i] = cS * y;
-            W.kb[i] = cS * fma(mu + xi + 0.5, y, -a1 * yp) * invx;
+            // y, yp and S have grown together to ~1e100+: take S's exponent off all three (exact) so that
+            // the division stays on the hardware's fast path instead of the out-of-range slow path
+            const double sc = cb_pow2_inverse_of(S);
+            const double cS = W.sq[ii] * e.rsdz / (S * sc);        // sqrt(pi/(2x)) / S, scaled
+            const double ys = y * sc, yps = yp * sc;
+            W.ka[i] = cS * ys;
+            W.kb[i] = cS * fma(mu + xi + 0.5, ys, -a1 * yps) * invx;
         }
     }
     cx.sync_warp();
