@@ -120,6 +120,8 @@ int cb_spectrum_batch(const cb_spectrum_plan *plan,
  * column transforms and the binning.  The host supplies the grouping:
  *   group_of_win_dev[w]   index into group_ix0_dev of window w (ix0[w] == group_ix0[group_of_win[w]])
  *   group_ix0_dev[g]      the distinct ix0 values, ngroups of them
+ *   win_order_dev[i]      optional (NULL = 0..nwin-1): the order in which windows are processed; sorting by
+ *                         (group, iy0) makes concurrently resident CTAs read overlapping rows (L2 hits)
  *   [row_lo, row_hi)      grid rows to transform for every group; every window needs
  *                         row_lo <= iy0[w] and iy0[w] + nw <= row_hi
  *   rowspec_dev           cb_spectrum_rowspec_bytes(plan, ngroups, row_lo, row_hi) bytes of scratch
@@ -130,6 +132,7 @@ int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan,
                                   const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
                                   const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin,
                                   const int32_t *group_of_win_dev, const int32_t *group_ix0_dev, int ngroups,
+                                  const int32_t *win_order_dev,
                                   int row_lo, int row_hi,
                                   int detrend, double power,
                                   double *phi_dev, double *sigma_dev,

@@ -57,7 +57,7 @@ SIGNATURES = {
     "cb_spectrum_workspace_bytes": (_I64, [_VP]),
     "cb_spectrum_batch": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _I64, _VP]),
     "cb_spectrum_rowspec_bytes": (_I64, [_VP, _I, _I, _I]),
-    "cb_spectrum_batch_shared_rows": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _I64, _VP, _VP, _I, _I, _I, _I, _D,
+    "cb_spectrum_batch_shared_rows": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _I64, _VP, _VP, _I, _VP, _I, _I, _I, _D,
                                            _VP, _VP, _VP, _I64, _VP, _I64, _VP]),
     "cb_detrend_batch": (_I, [_VP, _I64, _I64, _I64, _I, _VP, _VP, _I64, _VP, _VP]),
     "cb_besselk": (_I, [_VP, _VP, _I64, _VP, _VP]),

@@ -200,9 +200,12 @@ class SpectrumPlan:
                 self._rowspec = torch.empty(need, dtype=torch.uint8, device="cuda")
             gof_t = torch.from_numpy(np.ascontiguousarray(gof, dtype=np.int32)).cuda()
             gix_t = torch.from_numpy(np.ascontiguousarray(uniq[g0:g1])).cuda()
+            # processing order: by (group, iy0), sorted on the device (plumbing, 0.1 ms for 152,100 keys)
+            order_t = torch.argsort(gof_t.to(torch.int64) * (1 << 20) + iy_c.to(torch.int64)).to(torch.int32)
             _lib.check(lib.cb_spectrum_batch_shared_rows(
                 self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0), iy_c.data_ptr(), ix_c.data_ptr(),
-                int(iy_c.numel()), gof_t.data_ptr(), gix_t.data_ptr(), g1 - g0, lo, hi, 1 if detrend else 0,
+                int(iy_c.numel()), gof_t.data_ptr(), gix_t.data_ptr(), g1 - g0, order_t.data_ptr(), lo, hi,
+                1 if detrend else 0,
                 float(power), out_phi.data_ptr(), out_sig.data_ptr(), self._rowspec.data_ptr(), self._rowspec.numel(),
                 self.workspace.data_ptr(), self.workspace.numel(), stream))
             if sel is not None:

@@ -217,6 +217,7 @@ int64_t cb_spectrum_rowspec_bytes(const cb_spectrum_plan *plan, int ngroups, int
 int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan, const double *grid_dev, int64_t ny, int64_t nx,
                                   int64_t ld, const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin,
                                   const int32_t *group_of_win_dev, const int32_t *group_ix0_dev, int ngroups,
+                                  const int32_t *win_order_dev,
                                   int row_lo, int row_hi, int detrend, double power, double *phi_dev,
                                   double *sigma_dev, void *rowspec_dev, int64_t rowspec_bytes, void *workspace_dev,
                                   int64_t workspace_bytes, void *stream) {
@@ -245,6 +246,7 @@ int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan, const double *gr
     P.lh_stride = hp.ws_per_cta / 8;
     P.lh_half = hp.lh_stride;                         // second slab (phase C of w overlaps phase B of w+1)
     P.group_of_win = group_of_win_dev; P.group_ix0 = group_ix0_dev; P.ngroups = ngroups;
+    P.win_order = win_order_dev;
     P.row_lo = row_lo; P.nrows_valid = row_hi - row_lo; P.nrows = (P.nrows_valid + 1) & ~1;
     P.rt = reinterpret_cast<double2 *>(((uintptr_t)rowspec_dev + 255) & ~(uintptr_t)255);
     P.plane_t0 = plan->d_plane_t0; P.plane_t1 = plan->d_plane_t1;

@@ -52,6 +52,7 @@ struct SpectrumParams {
     // shared-row-spectra path (rowspec_body / colspec_body): windows with the same ix0 share the
     // x-transforms of the grid rows they overlap
     const int32_t *group_of_win;   // [nwin] group (= distinct ix0) of each window
+    const int32_t *win_order;      // [nwin] or NULL: processing order (windows of one group together, by iy0)
     const int32_t *group_ix0;      // [ngroups]
     int32_t ngroups;
     int32_t row_lo;                // first grid row held in rt
@@ -422,7 +423,10 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
     double *Lh2[2] = {P.lh + (int64_t)cx.bid() * P.lh_stride, P.lh + (int64_t)cx.bid() * P.lh_stride + P.lh_half};
     const double ctr = 0.5 * (double)(n - 1);
     int parity = 0;
-    for (int64_t w = cx.bid(); w < P.nwin; w += cx.nblocks(), parity ^= 1) {
+    for (int64_t wi = cx.bid(); wi < P.nwin; wi += cx.nblocks(), parity ^= 1) {
+        // CTAs that run side by side take neighbouring windows of the SAME column group: their row slices of
+        // rt overlap by (nw - stride)/nw, so the slab is read from L2 instead of HBM
+        const int64_t w = P.win_order ? (int64_t)P.win_order[wi] : wi;
         double *Lh = Lh2[parity];
         const int iy0 = P.iy0[w], g = P.group_of_win[w];
         double c0 = 0.0, cx1 = 0.0, cy1 = 0.0;
