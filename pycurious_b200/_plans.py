@@ -33,6 +33,24 @@ def nearest_node(coords, q):
     return np.where(pick_lo, lo, hi).astype(np.int64)
 
 
+def _lattice_shape(xc, yc):
+    """(rows, cols) when (xc, yc) is a raveled meshgrid with x fastest (what create_centroid_list returns,
+    grid.py:196-197), else None.  O(n) comparisons instead of two searches per centroid."""
+    n = xc.size
+    if n < 4096 or yc.size != n:
+        return None
+    rep = np.flatnonzero(xc[1:] == xc[0])
+    cols = int(rep[0]) + 1 if rep.size else n
+    if n % cols:
+        return None
+    rows = n // cols
+    if not (xc.reshape(rows, cols) == xc[:cols]).all():
+        return None
+    if not (yc.reshape(rows, cols) == yc[::cols, None]).all():
+        return None
+    return rows, cols
+
+
 def window_nodes(window, dx):
     nw = int(round(window / dx))
     return nw, nw // 2
@@ -48,8 +66,14 @@ def window_origins(g, window, xc, yc):
         i = int(np.flatnonzero(outside)[0])
         raise ValueError("Point {} outside data range".format((xc[i], yc[i])))
     _, half = window_nodes(window, g.dx)
-    ix = nearest_node(g.xcoords, xc)
-    iy = nearest_node(g.ycoords, yc)
+    lat = _lattice_shape(xc, yc)
+    if lat is not None:                  # create_centroid_list output: resolve the distinct coordinates only
+        rows, cols = lat
+        ix = np.tile(nearest_node(g.xcoords, xc[:cols]), rows)
+        iy = np.repeat(nearest_node(g.ycoords, yc[::cols]), cols)
+    else:
+        ix = nearest_node(g.xcoords, xc)
+        iy = nearest_node(g.ycoords, yc)
     bad = (ix - half < 0) | (ix + half + 1 > g.nx) | (iy - half < 0) | (iy + half + 1 > g.ny)
     if bad.any():
         i = int(np.flatnonzero(bad)[0])
@@ -160,7 +184,11 @@ class SpectrumPlan:
             ix0_h = getattr(ix0_t, "_cb_host", None)
             if iy0_h is None or ix0_h is None:
                 iy0_h, ix0_h = iy0_t.cpu().numpy(), ix0_t.cpu().numpy()
-            uniq, inv = np.unique(ix0_h, return_inverse=True)
+            # distinct ix0 values and each window's index into them (counting sort: ix0 < nx)
+            present = np.zeros(int(nx) + 1, dtype=bool)
+            present[ix0_h] = True
+            uniq = np.flatnonzero(present)
+            inv = (np.cumsum(present) - 1)[ix0_h]
             row_lo, row_hi = int(iy0_h.min()), int(iy0_h.max()) + self.nw
             reuse = float(n) * self.nw / (float(uniq.size) * (row_hi - row_lo))
             if share_rows or reuse >= self.SHARE_MIN_REUSE:

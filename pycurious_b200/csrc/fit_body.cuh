@@ -59,9 +59,19 @@ struct FitState {
     double pt[4];                 // physical parameters (beta, zt, dz, C) of the trial point
     double cu, sdz;               // solver coordinate u = exp(-cu dz) (cu = 0: u = dz); sdz = d dz / d u at the trial point
     int32_t okn, fresh, stall, status, action, it, nfev, mask;
+    int32_t central;              // derivative evaluations use the central difference in beta from now on
+    int32_t gcentral;             // the gradient of the current iterate was taken with the central difference
+    int32_t use_pm;               // the evaluation being reduced staged Phi(beta - hb) (else forward difference)
+    int32_t buf_at_x;             // p0 / dPhi/ddz / Phi(beta + hb) in the slab belong to the current iterate
 };
 #define CB_FIT_STATE_DOUBLES ((int)((sizeof(FitState) + 7) / 8))
-enum { FIT_GO = 0, FIT_DONE = 1 };
+enum { FIT_GO = 0, FIT_DONE = 1, FIT_REFINE = 2 };
+// dPhi/dbeta is a difference quotient in the order of K_nu (no closed form).  Far from the minimum the
+// forward difference (one extra evaluation) is accurate enough -- its O(h) error is ~1e-6 of the
+// gradient; once the projected gradient falls below this fraction of max(1, f) the solver re-takes the
+// gradient of the current iterate with the central difference and keeps using it, so every convergence
+// decision is made on central-difference gradients.
+#define CB_FIT_CENTRAL_BELOW 1.0e-3
 CB_HD int fit_slab_doubles(int nk) { return warp_slab_doubles(nk, true, CB_FIT_STATE_DOUBLES); }
 
 // Solve B d = -g on the free variables (frozen ones get d = 0) by Cholesky; returns false when the
@@ -189,11 +199,14 @@ CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const doubl
     }
     fit_set_trial(S);
     S->fresh = 1; S->stall = 0; S->status = FIT_MAXITER; S->action = FIT_GO; S->it = 0; S->nfev = 0; S->mask = 0;
+    S->central = 0; S->gcentral = 0; S->use_pm = 0; S->buf_at_x = 0;
 }
 
 // Make the evaluated trial point the current iterate (first evaluation: B = Gauss-Newton metric).
 CB_NOINLINE_BODY void fit_accept_first(FitState *S) {
     if (!S->okn) { S->status = FIT_BAD_START; S->action = FIT_DONE; }
+    S->gcentral = S->use_pm;
+    S->buf_at_x = 1;
     S->f = S->fn;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { S->x[j] = S->xt[j]; S->g[j] = S->gn[j]; }
@@ -212,6 +225,11 @@ CB_NOINLINE_BODY void fit_direction(FitState *S, double gtol) {
         // the flat tail, where the Bessel term is below the rounding of the bracket) -- leave it alone
         if (S->g[j] == 0.0 && S->H[tri(j, j)] == 0.0) frozen[j] = true;
         if (!frozen[j]) pgn = fmax(pgn, fabs(S->g[j]));
+    }
+    if (!S->gcentral && pgn <= CB_FIT_CENTRAL_BELOW * fmax(1.0, fabs(S->f))) {
+        S->central = 1;
+        S->action = FIT_REFINE;          // re-take this iterate's gradient with the central difference first
+        return;
     }
     if (pgn <= gtol) { S->status = FIT_CONVERGED_PG; S->action = FIT_DONE; return; }
     // the secant pairs were collected on another face of the box: when the active set changes, restart
@@ -268,6 +286,7 @@ CB_NOINLINE_BODY void fit_direction(FitState *S, double gtol) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) S->d[j] = d[j];
     S->gd = gd;
+    if (!S->gcentral && -gd <= 1e-13 * fmax(1.0, fabs(S->f))) { S->central = 1; S->action = FIT_REFINE; return; }
 #ifdef CB_FIT_TRACE
     printf("      g %.3e %.3e %.3e %.3e  d %.3e %.3e %.3e %.3e  gd %.3e mask %d Hdiag %.3e %.3e %.3e %.3e Bdiag %.3e %.3e %.3e %.3e\n", S->g[0], S->g[1], S->g[2], S->g[3], d[0], d[1], d[2], d[3], gd, S->mask,
            S->H[0], S->H[4], S->H[7], S->H[9], S->B[0], S->B[4], S->B[7], S->B[9]);
@@ -340,6 +359,8 @@ CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
         for (int q = 0; q < 10; ++q) S->B[q] = S->Hn[q];
         S->fresh = 1;
     }
+    S->gcentral = S->use_pm;
+    S->buf_at_x = 1;
     const double fold = S->f;
     S->f = S->fn;
 #pragma unroll
@@ -365,10 +386,11 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
     const int L = cx.team_lanes(), nk = W.nk;
     const double hb = S->hb;
     const double rh = 1.0 / hb, rh2 = 0.5 * rh;
+    const bool use_pm = S->use_pm != 0;
 #pragma unroll 1
     for (int i = lane; i < nk; i += L) {
-        const double p0 = W.p0[i], pp = W.pp[i], pm = W.pm[i];
-        const bool fp = isfinite(pp), fm = isfinite(pm);
+        const double p0 = W.p0[i], pp = W.pp[i], pm = use_pm ? W.pm[i] : 0.0;
+        const bool fp = isfinite(pp), fm = use_pm && isfinite(pm);
         W.kb[i] = (fp && fm) ? (pp - pm) * rh2 : (fp ? (pp - p0) * rh : (fm ? (p0 - pm) * rh : 0.0));
         W.ka[i] = p0 - W.obs[i];
     }
@@ -438,11 +460,31 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
 }
 
 template <class Ctx>
-CB_BODY bool fit_poll(const Ctx &cx, const FitState *S) {
+CB_BODY int fit_poll(const Ctx &cx, const FitState *S) {
     cx.sync_warp();
-    const bool go = S->action == FIT_GO;
+    const int a = S->action;
     cx.sync_warp();
-    return go;
+    return a;
+}
+
+// Lane 0: the re-taken gradient replaces the iterate's (same point, same f up to rounding).
+CB_NOINLINE_BODY void fit_refined(FitState *S) {
+    if (!S->okn) { S->status = FIT_LINESEARCH; S->action = FIT_DONE; return; }
+    S->f = S->fn;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S->g[j] = S->gn[j];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) S->H[q] = S->Hn[q];
+    S->gcentral = 1;
+    S->buf_at_x = 1;
+    S->action = FIT_GO;
+}
+
+// Lane 0: make the current iterate the trial point again (refinement after a failed line search).
+CB_NOINLINE_BODY void fit_trial_at_x(FitState *S) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S->xt[j] = S->x[j];
+    fit_set_trial(S);
 }
 
 template <class Ctx>
@@ -469,19 +511,39 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
     cx.sync_warp();
     W.cu = S->cu;
 
-    // full evaluation at the start
-    model_coefs_warp(cx, W, S->pt, S->hb, 0, 3, lane);
+    // first evaluation: forward difference in beta (see CB_FIT_CENTRAL_BELOW)
+    model_coefs_warp(cx, W, S->pt, S->hb, 0, 2, lane);
     model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
     model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
-    model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
     fit_reduce_full(cx, W, S, lane);
-    if (lane == 0) { fit_accept_first(S); S->nfev = 3; }
+    if (lane == 0) { fit_accept_first(S); S->nfev = 2; }
 
     // S->action is written by lane 0 only; every read is fenced by a barrier on both sides so that
     // lane 0 cannot change it again before all lanes have seen the same value
-    while (fit_poll(cx, S)) {
+    while (fit_poll(cx, S) == FIT_GO) {
         if (lane == 0) fit_direction(S, gtol);
-        if (!fit_poll(cx, S)) break;
+        const int act = fit_poll(cx, S);
+        if (act == FIT_DONE) break;
+        if (act == FIT_REFINE) {
+            int extra = 1;
+            if (S->buf_at_x) {            // Phi, dPhi/ddz and Phi(beta + hb) of this iterate are still staged
+                model_coefs_warp(cx, W, S->pt, S->hb, 2, 1, lane);
+            } else {
+                cx.sync_warp();
+                if (lane == 0) fit_trial_at_x(S);
+                cx.sync_warp();
+                model_coefs_warp(cx, W, S->pt, S->hb, 0, 3, lane);
+                model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
+                model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
+                extra = 3;
+            }
+            model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
+            if (lane == 0) S->use_pm = 1;
+            cx.sync_warp();
+            fit_reduce_full(cx, W, S, lane);
+            if (lane == 0) { S->nfev += extra; fit_refined(S); }
+            continue;
+        }
 
         // projected Armijo backtracking
         const double f0 = S->f;
@@ -489,7 +551,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
         bool accepted = false;
         int nls = 0;
         for (int ls = 0; ls < 40; ++ls) {
-            if (lane == 0) fit_trial(S, alpha);
+            if (lane == 0) { fit_trial(S, alpha); S->buf_at_x = 0; }
             cx.sync_warp();
             const double dec = S->dec;
             if (S->move == 0.0) break;
@@ -513,12 +575,16 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
             if (lane == 0) { S->nfev += nls; fit_linesearch_failed(S); }
             continue;
         }
-        // derivatives at the accepted point: beta +- hb (p0 and dPhi/ddz are already staged)
-        model_coefs_warp(cx, W, S->pt, S->hb, 1, 2, lane);
+        // derivatives at the accepted point: beta + hb (and beta - hb once the central difference is on);
+        // p0 and dPhi/ddz are already staged
+        const int central = S->central;
+        model_coefs_warp(cx, W, S->pt, S->hb, 1, central ? 2 : 1, lane);
         model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
-        model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
+        if (central) model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
+        if (lane == 0) S->use_pm = central;
+        cx.sync_warp();
         fit_reduce_full(cx, W, S, lane);
-        if (lane == 0) { S->nfev += nls + 2; fit_update(S, ftol, max_iter); }
+        if (lane == 0) { S->nfev += nls + (central ? 2 : 1); fit_update(S, ftol, max_iter); }
     }
     if (lane == 0) {
         double pf[4];
