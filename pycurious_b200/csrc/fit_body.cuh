@@ -25,6 +25,7 @@
 
 struct FitParams {
     const double *kh;       // [nk]
+    const double *ktab;     // [ktable_doubles(nk)] window-independent tables (ktable_entry)
     int32_t nk;
     const double *phi;      // [nwin, nk]
     int64_t nwin;
@@ -392,7 +393,7 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
         const double p0 = W.p0[i], pp = W.pp[i], pm = use_pm ? W.pm[i] : 0.0;
         const bool fp = isfinite(pp), fm = use_pm && isfinite(pm);
         W.kb[i] = (fp && fm) ? (pp - pm) * rh2 : (fp ? (pp - p0) * rh : (fm ? (p0 - pm) * rh : 0.0));
-        W.ka[i] = p0 - W.obs[i];
+        W.res[i] = p0 - W.obs[i];
     }
     if (lane == 0) S->one = 1.0;
     cx.sync_warp();
@@ -411,8 +412,8 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
             va = a + 1;
             vb = t - (a * 4 - (a * (a - 1)) / 2) + a + 1;
         }
-        const double *pa = va == 0 ? W.ka : (va == 1 ? W.kb : (va == 2 ? W.k : (va == 3 ? W.dz : &S->one)));
-        const double *pb = vb == 0 ? W.ka : (vb == 1 ? W.kb : (vb == 2 ? W.k : (vb == 3 ? W.dz : &S->one)));
+        const double *pa = va == 0 ? W.res : (va == 1 ? W.kb : (va == 2 ? W.k : (va == 3 ? W.dz : &S->one)));
+        const double *pb = vb == 0 ? W.res : (vb == 1 ? W.kb : (vb == 2 ? W.k : (vb == 3 ? W.dz : &S->one)));
         const int sa = va == 4 ? 0 : 1, sb = vb == 4 ? 0 : 1;
         double acc = 0.0;
         if (q < 15) {
@@ -497,8 +498,8 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
 
     // per-warp slab in shared memory: wavenumber tables, model values, order tables, solver state
     WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) +
-                                     (int64_t)warp * fit_slab_doubles(nk), nk, true);
-    warp_slab_load(cx, W, P.kh, P.phi + w * nk, lane);
+                                     (int64_t)warp * fit_slab_doubles(nk), nk, true, P.kh, P.ktab);
+    warp_slab_load(cx, W, P.phi + w * nk, lane);
     FitState *S = reinterpret_cast<FitState *>(W.scratch);
     const cb_fit_options *o = &P.opt;
     const int max_iter = o->max_iter > 0 ? o->max_iter : 200;

@@ -11,6 +11,7 @@
 
 struct MhParams {
     const double *kh;
+    const double *ktab;     // [ktable_doubles(nk)] window-independent tables (ktable_entry)
     int32_t nk;
     const double *phi;      // [nwin, nk]
     int64_t nwin;
@@ -90,8 +91,8 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     if (w >= P.nwin) return;
 
     WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * warp_slab_doubles(nk, false),
-                                 nk, false);
-    warp_slab_load(cx, W, P.kh, P.phi + w * nk, lane);
+                                 nk, false, P.kh, P.ktab);
+    warp_slab_load(cx, W, P.phi + w * nk, lane);
 
     const cb_mh_options &o = P.opt;
     Priors pr;

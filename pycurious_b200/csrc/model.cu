@@ -8,10 +8,11 @@
 extern __shared__ double cb_dyn_smem_d[];
 
 // One warp (= one window / chain) per CTA: fit and chain lengths vary between windows, and with
-// single-warp CTAs the hardware block scheduler balances them; 16 CTAs per SM keep 4 warps per
-// scheduler in flight to hide the FP64 dependency chains of the Bessel recurrences.
+// single-warp CTAs the hardware block scheduler balances them.  The kernels are dependency-latency
+// bound (one long serial chain per window): throughput scales with resident warps, so the slab is kept
+// at ~9 KB (window-independent tables live in global memory) and registers at 80 for 24 CTAs per SM.
 #define CB_FIT_WARPS 1
-#define CB_FIT_CTAS_PER_SM 16
+#define CB_FIT_CTAS_PER_SM 24
 
 __global__ void __launch_bounds__(256) besselk_kernel(const double *nu, const double *x, int64_t n, double *out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -43,6 +44,7 @@ bouligand_points_kernel(const double *kh, const double *params, int64_t n, doubl
 
 struct MisfitParams {
     const double *kh;
+    const double *ktab;
     int32_t nk;
     const double *phi;
     int64_t phi_stride;
@@ -57,8 +59,8 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) mi
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * CB_FIT_WARPS + warp;
     if (row >= P.m) return;
-    WarpSlab W = warp_slab_carve(cb_dyn_smem_d + (int64_t)warp * warp_slab_doubles(P.nk, false), P.nk, false);
-    warp_slab_load(cx, W, P.kh, P.phi + row * P.phi_stride, lane);
+    WarpSlab W = warp_slab_carve(cb_dyn_smem_d + (int64_t)warp * warp_slab_doubles(P.nk, false), P.nk, false, P.kh, P.ktab);
+    warp_slab_load(cx, W, P.phi + row * P.phi_stride, lane);
     double x[4];
     for (int j = 0; j < 4; ++j) x[j] = P.params[row * 4 + j];
     const double f = misfit_slab(cx, W, x, P.pr, lane);
@@ -100,6 +102,43 @@ perturb_kernel(const double *phi, const double *sigma, int64_t nwin, int nk, int
 __global__ void __launch_bounds__(128) tanaka_kernel(const __grid_constant__ TanakaParams P) {
     DevCtx cx{nullptr};
     tanaka_body(cx, P);
+}
+
+__global__ void __launch_bounds__(256) ktable_kernel(const double *kh, int nk, double *out) {
+    const int n = ktable_doubles(nk);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = ktable_entry(kh, nk, i);
+}
+
+// Scratch for the window-independent tables: one small buffer per (device, stream), created on first use and
+// kept (launches of one stream are ordered, so the fill of the next call cannot overtake the kernel of the
+// previous one; different streams never share a buffer).  cudaMallocAsync per call was measured 4x slower
+// for back-to-back launches.
+#include <map>
+#include <mutex>
+#define CB_KTABLE_MAX_NK 2048
+static std::mutex g_ktab_mutex;
+static std::map<std::pair<int, cudaStream_t>, double *> g_ktab;
+
+static int ktable_make(const double *kh_dev, int nk, cudaStream_t st, double **out) {
+    *out = nullptr;
+    CB_REQUIRE(nk <= CB_KTABLE_MAX_NK, "nk too large");
+    int dev = 0;
+    CB_CUDA_TRY(cudaGetDevice(&dev));
+    double *buf = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_ktab_mutex);
+        auto it = g_ktab.find(std::make_pair(dev, st));
+        if (it != g_ktab.end()) buf = it->second;
+        else {
+            CB_CUDA_TRY(cudaMalloc((void **)&buf, (size_t)ktable_doubles(CB_KTABLE_MAX_NK) * sizeof(double)));
+            g_ktab[std::make_pair(dev, st)] = buf;
+        }
+    }
+    const int n = ktable_doubles(nk);
+    ktable_kernel<<<(n + 255) / 256, 256, 0, st>>>(kh_dev, nk, buf);
+    CB_CUDA_TRY(cudaGetLastError());
+    *out = buf;
+    return CB_OK;
 }
 
 static int elementwise_grid(int64_t n) {
@@ -170,6 +209,9 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
         P.pr.sigma[j] = prior_sigma_host ? prior_sigma_host[j] : NAN;
     }
     if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    double *ktab = nullptr;
+    if ((rc = ktable_make(kh_dev, nk, (cudaStream_t)stream, &ktab)) != CB_OK) return rc;
+    P.ktab = ktab;
     misfit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
@@ -198,6 +240,9 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     P.x_out = x_out_dev; P.f_out = f_out_dev; P.niter = niter_dev; P.status = status_dev; P.nfev = nfev_dev;
     P.warps_per_block = CB_FIT_WARPS;
     if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    double *ktab = nullptr;
+    if ((rc = ktable_make(kh_dev, nk, (cudaStream_t)stream, &ktab)) != CB_OK) return rc;
+    P.ktab = ktab;
     fit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
@@ -259,6 +304,9 @@ int cb_mh_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwi
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
     P.out = out_dev; P.accepted = accepted_dev; P.warps_per_block = CB_FIT_WARPS;
     if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(mh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    double *ktab = nullptr;
+    if ((rc = ktable_make(kh_dev, nk, (cudaStream_t)stream, &ktab)) != CB_OK) return rc;
+    P.ktab = ktab;
     mh_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;

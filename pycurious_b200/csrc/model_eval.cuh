@@ -59,10 +59,14 @@ struct EvalCoef {
 };
 
 struct WarpSlab {          // views into one warp's shared-memory slab
-    double *k, *logk, *rk, *sq, *obs;   // [nk] k, ln k, 1/k, sqrt(pi/(2k)), observed Phi
+    // window-independent tables, built once per launch in global memory (ktable_fill), read through L1
+    const double *k, *logk, *rk, *sq;   // [nk] k, ln k, 1/k, sqrt(pi/(2k))
+    const double *rn;                   // [CB_MILLER_NMAX + 1] 1/n
+    // per-window arrays in the warp's shared-memory slab
+    double *obs;                        // [nk] observed Phi
     double *p0, *pp, *pm, *dz;          // [nk] model values (p0) and, for the fit, Phi(beta+-h), dPhi/ddz
-    double *ka, *kb;                    // [nk] K_mu, K_mu+1 between the phases of one evaluation
-    double *rn;                         // [CB_MILLER_NMAX + 1] 1/n
+    double *kb;                         // [nk] K_mu+1 between the phases of one evaluation (K_mu sits in out_phi)
+    double *res;                        // [nk] fit only: residuals during the reduction
     double2 *CA;                        // [CB_MILLER_NMAX + 1] (C_n, a_{n+1}) of the order being evaluated
     double2 *rpq;                       // [CB_TEMME_TAB] (1/(j-mu), 1/(j+mu))
     EvalCoef *coef;                     // [CB_MAX_ORDERS]
@@ -76,60 +80,63 @@ struct WarpSlab {          // views into one warp's shared-memory slab
 #define CB_SLAB_COEF_DOUBLES ((int)((sizeof(EvalCoef) + 7) / 8))
 
 CB_HD int warp_slab_doubles(int nk, bool fit, int scratch_doubles = 0) {
-    int n = (fit ? 11 : 8) * nk + (CB_MILLER_NMAX + 1) + 2 * (CB_MILLER_NMAX + 1) + 2 * CB_TEMME_TAB +
+    int n = (fit ? 7 : 3) * nk + 2 * (CB_MILLER_NMAX + 1) + 2 * CB_TEMME_TAB +
             CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES + scratch_doubles;
     return (n + 1) & ~1;      // keep every slab 16-byte aligned
 }
 
-CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit) {
+// Window-independent tables of one launch: [0,nk) ln k, [nk,2nk) 1/k, [2nk,3nk) sqrt(pi/(2k)),
+// then CB_MILLER_NMAX+1 values 1/n, then (sorted flag, k_min, k_max).
+CB_HD int ktable_doubles(int nk) { return 3 * nk + (CB_MILLER_NMAX + 1) + 3; }
+
+// Entry i of the table (i < ktable_doubles(nk)); every entry is independent so that the fill is a
+// plain parallel loop on the device and a serial one in the CPU harness.
+CB_HD double ktable_entry(const double *kh, int nk, int i) {
+    if (i < nk) return cb_log(kh[i]);
+    if (i < 2 * nk) return 1.0 / kh[i - nk];
+    if (i < 3 * nk) return sqrt(0.5 * CB_PI / kh[i - 2 * nk]);
+    i -= 3 * nk;
+    if (i <= CB_MILLER_NMAX) return i ? 1.0 / (double)i : 0.0;
+    i -= CB_MILLER_NMAX + 1;
+    double kmin = INFINITY, kmax = 0.0;
+    bool asc = true;
+    for (int j = 0; j < nk; ++j) {
+        const double k = kh[j];
+        if (j + 1 < nk && !(kh[j + 1] > k)) asc = false;
+        if (!(k > 0.0)) asc = false;
+        kmin = fmin(kmin, k);
+        kmax = fmax(kmax, k);
+    }
+    return i == 0 ? (asc ? 1.0 : 0.0) : (i == 1 ? kmin : kmax);
+}
+
+CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh, const double *ktab) {
     WarpSlab W;
     W.nk = nk;
+    W.k = kh; W.logk = ktab; W.rk = ktab + nk; W.sq = ktab + 2 * nk; W.rn = ktab + 3 * nk;
+    const double *meta = ktab + 3 * nk + (CB_MILLER_NMAX + 1);
+    W.sorted = meta[0] != 0.0;
+    W.kmin = meta[1];
+    W.kmax = meta[2];
     double *t = base;
     W.CA = reinterpret_cast<double2 *>(t); t += 2 * (CB_MILLER_NMAX + 1);
     W.rpq = reinterpret_cast<double2 *>(t); t += 2 * CB_TEMME_TAB;
     W.coef = reinterpret_cast<EvalCoef *>(t); t += CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES;
-    W.rn = t; t += CB_MILLER_NMAX + 1;
-    W.k = t; W.logk = t + nk; W.rk = t + 2 * nk; W.sq = t + 3 * nk; W.obs = t + 4 * nk; W.p0 = t + 5 * nk;
-    W.ka = t + 6 * nk; W.kb = t + 7 * nk;
-    t += 8 * nk;
-    if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; t += 3 * nk; }
-    else { W.pp = W.pm = W.dz = nullptr; }
+    W.obs = t; W.p0 = t + nk; W.kb = t + 2 * nk;
+    t += 3 * nk;
+    if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; W.res = t + 3 * nk; t += 4 * nk; }
+    else { W.pp = W.pm = W.dz = W.res = nullptr; }
     W.scratch = t;
-    W.sorted = false;
-    W.kmax = 0.0;
-    W.kmin = 0.0;
     W.cu = 0.0;
     return W;
 }
 
-// Stage the per-window tables; detect ascending positive k.
+// Stage the window's spectrum.
 template <class Ctx>
-CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *kh, const double *phi_row, int lane) {
+CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *phi_row, int lane) {
     const int L = cx.team_lanes();
-    bool asc = true;
-    double kmax = 0.0, kmin = INFINITY;
 #pragma unroll 1
-    for (int i = lane; i < W.nk; i += L) {
-        const double k = kh[i];
-        W.k[i] = k;
-        W.logk[i] = cb_log(k);
-        W.rk[i] = 1.0 / k;
-        W.sq[i] = sqrt(0.5 * CB_PI / k);
-        W.obs[i] = phi_row[i];
-        if (i + 1 < W.nk && !(kh[i + 1] > k)) asc = false;
-        if (!(k > 0.0)) asc = false;
-        kmax = fmax(kmax, k);
-        kmin = fmin(kmin, k);
-    }
-#pragma unroll 1
-    for (int n = lane; n <= CB_MILLER_NMAX; n += L) W.rn[n] = n ? 1.0 / (double)n : 0.0;
-    for (int o = 16; o > 0; o >>= 1) {
-        kmax = fmax(kmax, cx.shfl_xor(kmax, o));
-        kmin = fmin(kmin, cx.shfl_xor(kmin, o));
-    }
-    W.kmax = kmax;
-    W.kmin = kmin;
-    W.sorted = cx.all(asc);
+    for (int i = lane; i < W.nk; i += L) W.obs[i] = phi_row[i];
     cx.sync_warp();
 }
 
@@ -195,7 +202,7 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     if (!(W.sorted && e.fast)) {                       // generic per-point path, reference nan/inf semantics
 #pragma unroll 1
         for (int i = lane; i < nk; i += L)
-            out_phi[i] = generic_point(&m, W.k[i], W.logk[i], out_ddz ? out_ddz + i : nullptr);
+            out_phi[i] = generic_point(&m, Ctx::ldg(W.k + (i)), Ctx::ldg(W.logk + (i)), out_ddz ? out_ddz + i : nullptr);
         cx.sync_warp();
         return;
     }
@@ -206,12 +213,12 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     const double cudz = out_ddz ? W.cu * dz : 0.0;
 #pragma unroll 1
     for (int i = lane; i < nk; i += L) {
-        const double xi = W.k[i] * dz;
+        const double xi = Ctx::ldg(W.k + (i)) * dz;
         if (xi <= 2.0) lastT = i;
         // the K term relative to the cosh term is ~ exp(-(2x - nu ln(x/2) + ln Gamma(nu))).  When the caller
         // iterates in u = exp(-cu dz) the derivative d/du = -(1/(cu u)) d/ddz magnifies it by exp(cu dz):
         // W.cu dz is taken off the exponent so that dPhi/du keeps its relative accuracy on the flat tail
-        const bool skip = xi > 2.0 && (2.0 * xi - cudz - m.nu * (W.logk[i] + m.lhalfdz) + e.lgnu > CB_SKIP_LOG);
+        const bool skip = xi > 2.0 && (2.0 * xi - cudz - m.nu * (Ctx::ldg(W.logk + (i)) + m.lhalfdz) + e.lgnu > CB_SKIP_LOG);
         if (!skip) lastC = i;
     }
     const int nT = cx.warp_max_i(lastT) + 1;
@@ -227,7 +234,7 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
             W.CA[0] = make_double2(1.0, -a1);
             W.CA[1] = make_double2(a1, -(a1 + 2.0));
             for (int n = 2; n <= CB_MILLER_NMAX; ++n) {
-                c *= fma(a1, W.rn[n], (double)(n - 1));
+                c *= fma(a1, Ctx::ldg(W.rn + (n)), (double)(n - 1));
                 W.CA[n] = make_double2(c, -(a1 + (double)n * (double)(n + 1)));
             }
         } else {
@@ -236,7 +243,7 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int n = 3 * lane + 2 + j;
-                const double g = n <= CB_MILLER_NMAX ? fma(a1, W.rn[n], (double)(n - 1)) : 1.0;
+                const double g = n <= CB_MILLER_NMAX ? fma(a1, Ctx::ldg(W.rn + (n)), (double)(n - 1)) : 1.0;
                 run *= g;
                 q[j] = run;
             }
@@ -270,21 +277,21 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     // ---- T: Temme's series ----------------------------------------------------------------------
 #pragma unroll 1
     for (int i = lane; i < nT; i += L) {
-        const double d = -(W.logk[i] + m.lhalfdz);      // ln(2/x)
+        const double d = -(Ctx::ldg(W.logk + (i)) + m.lhalfdz);      // ln(2/x)
         const double sg = mu * d;
         const double ee = cb_exp(sg), ei = 1.0 / ee;
         // sinh(sg)/sg * d = sinh(sg)/mu
         const double shd = fabs(sg) < 1e-4 ? d * (1.0 + sg * sg * (1.0 / 6.0)) : 0.5 * (ee - ei) * e.rmu;
         double ff = m.ord.sinc * (m.ord.gam1 * 0.5 * (ee + ei) + m.ord.gam2 * shd);
         double p = e.hp * ee, q = e.hq * ei, c = 1.0;
-        const double x2 = 0.5 * W.k[i] * dz, dd = x2 * x2;
+        const double x2 = 0.5 * Ctx::ldg(W.k + (i)) * dz, dd = x2 * x2;
         double sum = ff, sum1 = p;
 #pragma unroll 1
         for (int j = 1; j < CB_TEMME_TAB; ++j) {
             const double fj = (double)j;
             const double2 r = W.rpq[j];
             ff = (fj * ff + p + q) * (r.x * r.y);
-            c *= dd * W.rn[j];
+            c *= dd * Ctx::ldg(W.rn + (j));
             p *= r.x;
             q *= r.y;
             const double del = c * ff;
@@ -292,8 +299,8 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
             sum1 = fma(c, p - fj * ff, sum1);
             if (fabs(del) < fabs(sum) * CB_KNU_EPS) break;
         }
-        W.ka[i] = sum;
-        W.kb[i] = sum1 * (2.0 * W.rk[i] * e.rdz);
+        out_phi[i] = sum;                       // K_mu; phase F turns it into Phi in place
+        W.kb[i] = sum1 * (2.0 * Ctx::ldg(W.rk + (i)) * e.rdz);
     }
 
     // ---- M: Miller backward recurrence, uniform trip count per pass ----------------------------
@@ -301,8 +308,8 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     for (int base = nT; base < nS; base += L) {
         const int i = base + lane;
         const int ii = i < nS ? i : nS - 1;
-        const double xi = W.k[ii] * dz;
-        int N = (int)(12.0 + 140.0 * (W.rk[base] * e.rdz)) + 1;     // from the smallest x of this pass (k ascending)
+        const double xi = Ctx::ldg(W.k + (ii)) * dz;
+        int N = (int)(12.0 + 140.0 * (Ctx::ldg(W.rk + (base)) * e.rdz)) + 1;     // from the smallest x of this pass (k ascending)
         if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
         double yp = 0.0, y = 1.0, S = W.CA[N].x;
         double bn = 2.0 * ((double)N + xi);
@@ -315,13 +322,13 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
             bn -= 2.0;
         }
         if (i < nS) {
-            const double invx = W.rk[ii] * e.rdz;
+            const double invx = Ctx::ldg(W.rk + (ii)) * e.rdz;
             // y, yp and S have grown together to ~1e100+: take S's exponent off all three (exact) so that
             // the division stays on the hardware's fast path instead of the out-of-range slow path
             const double sc = cb_pow2_inverse_of(S);
-            const double cS = W.sq[ii] * e.rsdz / (S * sc);        // sqrt(pi/(2x)) / S, scaled
+            const double cS = Ctx::ldg(W.sq + (ii)) * e.rsdz / (S * sc);        // sqrt(pi/(2x)) / S, scaled
             const double ys = y * sc, yps = yp * sc;
-            W.ka[i] = cS * ys;
+            out_phi[i] = cS * ys;
             W.kb[i] = cS * fma(mu + xi + 0.5, ys, -a1 * yps) * invx;
         }
     }
@@ -334,12 +341,12 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
         const int nl = m.ord.nl;
 #pragma unroll 1
         for (int i = lane; i < nS; i += L) {
-            const double k = W.k[i], lk = W.logk[i], xi = k * dz;
+            const double k = Ctx::ldg(W.k + (i)), lk = Ctx::ldg(W.logk + (i)), xi = k * dz;
             const bool temme = i < nT;
             const double ex = cb_exp(temme ? -xi : -2.0 * xi);     // scales ka, kb to K e^-x in both classes
             const double e2 = temme ? ex * ex : ex;
-            double a = W.ka[i] * ex, b = W.kb[i] * ex;
-            const double tox = 2.0 * W.rk[i] * e.rdz;
+            double a = out_phi[i] * ex, b = W.kb[i] * ex;
+            const double tox = 2.0 * Ctx::ldg(W.rk + (i)) * e.rdz;
 #pragma unroll 1
             for (int j = 1; j < nl; ++j) {
                 const double c = fma((mu + (double)j) * tox, b, a);
@@ -357,9 +364,9 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     // ---- S: the Bessel term cannot change the rounded bracket ------------------------------------
 #pragma unroll 1
     for (int i = nS + lane; i < nk; i += L) {
-        const double k = W.k[i];
+        const double k = Ctx::ldg(W.k + (i));
         const bool over = k * dz > CB_COSH_OVERFLOW;
-        out_phi[i] = over ? INFINITY : fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * W.logk[i] + e.lgc;
+        out_phi[i] = over ? INFINITY : fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * Ctx::ldg(W.logk + (i)) + e.lgc;
         if (out_ddz) out_ddz[i] = over ? NAN : 0.0;
     }
     cx.sync_warp();

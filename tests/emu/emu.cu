@@ -50,6 +50,12 @@ static void emu_run_shared(int nblocks, const SpectrumHostPlan &hp, const Spectr
     emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { colspec_body<Engine>(cx, P); });
 }
 
+static std::vector<double> emu_ktable(const double *kh, int nk) {
+    std::vector<double> t(ktable_doubles(nk));
+    for (int i = 0; i < (int)t.size(); ++i) t[i] = ktable_entry(kh, nk, i);
+    return t;
+}
+
 extern "C" {
 
 // plan introspection without a device: FFT length, radices, folded CSR size
@@ -221,10 +227,11 @@ void emu_misfit(const double *kh, int nk, const double *phi, int64_t phi_stride,
     Priors pr;
     for (int j = 0; j < 4; ++j) { pr.mu[j] = prior_mu ? prior_mu[j] : NAN; pr.sigma[j] = prior_sigma ? prior_sigma[j] : NAN; }
     std::vector<double> sm(warp_slab_doubles(nk, false));
+    const std::vector<double> ktab = emu_ktable(kh, nk);
     SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
     for (int64_t r = 0; r < m; ++r) {
-        WarpSlab W = warp_slab_carve(sm.data(), nk, false);
-        warp_slab_load(cx, W, kh, phi + r * phi_stride, 0);
+        WarpSlab W = warp_slab_carve(sm.data(), nk, false, kh, ktab.data());
+        warp_slab_load(cx, W, phi + r * phi_stride, 0);
         out[r] = misfit_slab(cx, W, params + 4 * r, pr, 0);
     }
 }
@@ -234,7 +241,8 @@ int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_
             double *x_out, double *f_out, int32_t *niter, int32_t *status, int32_t *nfev, int mode) {
     FitParams P;
     memset(&P, 0, sizeof(P));
-    P.kh = kh; P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0;
+    const std::vector<double> ktab = emu_ktable(kh, nk);
+    P.kh = kh; P.ktab = ktab.data(); P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0;
     P.x_out = x_out; P.f_out = f_out; P.niter = niter; P.status = status; P.nfev = nfev;
     if (mode == 0) {
         P.warps_per_block = 1;
@@ -263,7 +271,8 @@ int emu_fit_rows(const double *kh, int nk, const double *phi, int64_t nwin, cons
                  const double *prior_mu_rows, double *x_out, double *f_out) {
     FitParams P;
     memset(&P, 0, sizeof(P));
-    P.kh = kh; P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.prior_mu_dev = prior_mu_rows;
+    const std::vector<double> ktab = emu_ktable(kh, nk);
+    P.kh = kh; P.ktab = ktab.data(); P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.prior_mu_dev = prior_mu_rows;
     P.x_out = x_out; P.f_out = f_out;
     P.warps_per_block = 1;
     std::vector<double> sm(fit_slab_doubles(nk));
@@ -278,7 +287,8 @@ int emu_mh(const double *kh, int nk, const double *phi, int64_t nwin, const cb_m
            double *out, int64_t *accepted, int mode) {
     MhParams P;
     memset(&P, 0, sizeof(P));
-    P.kh = kh; P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0; P.out = out; P.accepted = accepted;
+    const std::vector<double> ktab = emu_ktable(kh, nk);
+    P.kh = kh; P.ktab = ktab.data(); P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0; P.out = out; P.accepted = accepted;
     if (mode == 0) {
         P.warps_per_block = 1;
         std::vector<double> sm(warp_slab_doubles(nk, false));
@@ -327,18 +337,19 @@ int emu_az_tail(const double *sino, int nw, int ntheta, int64_t nwin, const doub
 // Warp-cooperative model evaluation (fast path) for direct comparison with bouligand2009: mode 0 serial, 1 = 32 lanes
 void emu_model_eval(const double *kh, int nk, const double *x, double *phi, double *ddz, int mode) {
     std::vector<double> zero(nk, 0.0);
+    const std::vector<double> ktab = emu_ktable(kh, nk);
     if (mode == 0) {
         std::vector<double> sm(warp_slab_doubles(nk, true));
         SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
-        WarpSlab W = warp_slab_carve(sm.data(), nk, true);
-        warp_slab_load(cx, W, kh, zero.data(), 0);
+        WarpSlab W = warp_slab_carve(sm.data(), nk, true, kh, ktab.data());
+        warp_slab_load(cx, W, zero.data(), 0);
         model_coefs_warp(cx, W, x, 0.0, 0, 1, 0);
         model_eval_warp(cx, W, 0, 0, W.p0, W.dz);
         for (int i = 0; i < nk; ++i) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
     } else {
         emu_launch(1, 32, warp_slab_doubles(nk, true) * sizeof(double), [&](const HostCtx &cx) {
-            WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()), nk, true);
-            warp_slab_load(cx, W, kh, zero.data(), cx.tid());
+            WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()), nk, true, kh, ktab.data());
+            warp_slab_load(cx, W, zero.data(), cx.tid());
             model_coefs_warp(cx, W, x, 0.0, 0, 1, cx.tid());
             model_eval_warp(cx, W, 0, cx.tid(), W.p0, W.dz);
             for (int i = cx.tid(); i < nk; i += 32) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
