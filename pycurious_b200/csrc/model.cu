@@ -13,6 +13,9 @@ extern __shared__ double cb_dyn_smem_d[];
 // at ~9 KB (window-independent tables live in global memory) and registers at 80 for 24 CTAs per SM.
 #define CB_FIT_WARPS 1
 #define CB_FIT_CTAS_PER_SM 24
+#ifndef CB_MH_CTAS_PER_SM
+#define CB_MH_CTAS_PER_SM 32
+#endif
 
 __global__ void __launch_bounds__(256) besselk_kernel(const double *nu, const double *x, int64_t n, double *out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -72,7 +75,7 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) fi
     fit_body(cx, P);
 }
 
-__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) mh_kernel(const __grid_constant__ MhParams P) {
+__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_MH_CTAS_PER_SM) mh_kernel(const __grid_constant__ MhParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
     mh_body(cx, P);
 }
