@@ -126,6 +126,7 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
     }
 
     hp.line_slots = (fft_line_slots(hp.fft.n) + 1) & ~1;
+    if (hp.bluestein) hp.filt.resize(hp.line_slots, cplx(0.0, 0.0));   // the kernels stage line_slots entries
     hp.sm_tw = CB_SPEC_RED_SLOTS;
     hp.sm_filt = hp.sm_tw + hp.fft.tw_count;
     hp.sm_chirp = hp.sm_filt + (hp.bluestein ? hp.line_slots : 0);

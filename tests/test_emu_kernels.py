@@ -17,6 +17,9 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 
 @pytest.fixture(scope="module")
 def emu():
+    lib = os.environ.get("CB_EMU_LIB")          # tests/test_emu_asan.py points this at the ASan build
+    if lib:
+        return C.CDLL(lib)
     subprocess.check_call(["make", "-s", "-C", EMU_DIR])
     return C.CDLL(os.path.join(EMU_DIR, "libcurie_emu.so"))
 

@@ -9,7 +9,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_emu_kernels import FitOpt, P
-emu = C.CDLL(os.path.join(ROOT, "tests/emu/libcurie_emu.so"))
+emu = C.CDLL(os.environ.get("CB_EMU_LIB") or os.path.join(ROOT, "tests/emu/libcurie_emu.so"))
 g = np.load(os.path.join(ROOT, "tests/golden/fit.npz"))
 nrep = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 rng = np.random.default_rng(1)
