@@ -107,22 +107,32 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     const uint64_t chain = o.chain_offset + (uint64_t)w;
     const uint32_t k0 = (uint32_t)(o.seed ^ chain), k1 = (uint32_t)((o.seed >> 32) ^ (chain >> 32));
 
-    // ---- burn-in (optimise.py:598-611) ----
-    double P0 = exp(-misfit_slab(cx, W, x, pr, lane) / 1000.0);
+    // Early rejection: min_func = 0.5 sum r^2 + priors only grows while the points are evaluated, so a
+    // proposal whose partial misfit already exceeds what acceptance would need is rejected without
+    // finishing the model (misfit_slab_bounded).  The bound carries a 1e-6 relative margin; inside the
+    // margin the evaluation is completed and the reference's own test decides, so every accept / reject
+    // decision -- and therefore the chain -- is the one the full evaluation gives.
+    // ---- burn-in (optimise.py:598-611): accept iff exp(-f1/1000) > exp(-f0/1000) ----
+    double f0 = misfit_slab(cx, W, x, pr, lane);
+    double P0 = exp(-f0 / 1000.0);
     for (int64_t t = 0; t < o.burnin; ++t) {
         double z[4], x1[4];
         philox_normal4((uint64_t)t, 0u, k0, k1, z);
 #pragma unroll
         for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
-        const double P1 = exp(-misfit_slab(cx, W, x1, pr, lane) / 1000.0);
+        const double bound = f0 + 1e-6 * fmax(1.0, fabs(f0));
+        const double f1 = misfit_slab_bounded(cx, W, x1, pr, lane, bound);
+        if (f1 > bound) continue;
+        const double P1 = exp(-f1 / 1000.0);
         if (P1 > P0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = x1[j];
             P0 = P1;
+            f0 = f1;
         }
     }
 
-    // ---- sampling (optimise.py:613-631) ----
+    // ---- sampling (optimise.py:613-631): accept iff u <= min(exp(-f1) / max(P0, 1e-99), 1) ----
     P0 = exp(-misfit_slab(cx, W, x, pr, lane));
     int64_t nacc = 0;
     double mean[5] = {0, 0, 0, 0, 0}, m2[5] = {0, 0, 0, 0, 0};   // Welford accumulators (mode 1)
@@ -134,9 +144,16 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
         P0 = fmax(P0, 1e-99);
-        const double P1 = exp(-misfit_slab(cx, W, x1, pr, lane));
-        const double ratio = fmin(P1 / P0, 1.0);
-        if (u <= ratio) {
+        const double need = -log(u * P0);                 // exp(-f1)/P0 >= u  <=>  f1 <= -ln(u P0)
+        const double bound = need + 1e-6 * fmax(1.0, fabs(need));
+        const double f1 = misfit_slab_bounded(cx, W, x1, pr, lane, bound);
+        bool take = false;
+        double P1 = 0.0;
+        if (!(f1 > bound)) {
+            P1 = exp(-f1);
+            take = u <= fmin(P1 / P0, 1.0);
+        }
+        if (take) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = x1[j];
             P0 = P1;

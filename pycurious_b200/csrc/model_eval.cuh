@@ -188,23 +188,30 @@ CB_NOINLINE_BODY double generic_point(const ModelCoef *m, double k, double logk,
 
 // Phi(k_i) of parameter vector `idx` (coefficients prepared by model_coefs_warp) for every
 // wavenumber of the slab -> out_phi[i] (and dPhi/ddz -> out_ddz[i] if not NULL).
-// Four phases, each a single copy of its code (exp / log / division sites are not duplicated):
-//   T  x <= 2           Temme series          -> ka = K_mu,      kb = K_mu+1        (unscaled)
-//   M  2 < x < x_skip   Miller recurrence     -> ka = K_mu e^x,  kb = K_mu+1 e^x
-//   F  all of the above: scale by e^-x resp. e^-2x, upward recurrence in the order, bracket, log
-//   S  x >= x_skip      closed form
+// Phases, each a single copy of its code (exp / log / division sites are not duplicated):
+//   S  x >= x_skip      closed form (first: it needs no Bessel function)
+//   then per chunk of <= 32 points of one class
+//   T  x <= 2           Temme series          -> K_mu,      K_mu+1        (unscaled)
+//   M  2 < x < x_skip   Miller recurrence     -> K_mu e^x,  K_mu+1 e^x
+//   F  scale by e^-x resp. e^-2x, upward recurrence in the order, bracket, log
+// Returns 0.5 sum_i (Phi_i - obs_i)^2 when `obs` is given (0 otherwise); with a finite `bound` the
+// evaluation may stop early and return a partial sum that already exceeds the bound.
 template <class Ctx>
-CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int lane, double *out_phi,
-                                      double *out_ddz) {
+CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int lane, double *out_phi,
+                                        double *out_ddz, const double *obs = nullptr, double bound = INFINITY) {
     const EvalCoef &e = W.coef[idx];
     const ModelCoef &m = e.m;
     const int nk = W.nk, L = cx.team_lanes();
     if (!(W.sorted && e.fast)) {                       // generic per-point path, reference nan/inf semantics
+        double accg = 0.0;
 #pragma unroll 1
-        for (int i = lane; i < nk; i += L)
-            out_phi[i] = generic_point(&m, Ctx::ldg(W.k + (i)), Ctx::ldg(W.logk + (i)), out_ddz ? out_ddz + i : nullptr);
+        for (int i = lane; i < nk; i += L) {
+            const double ph = generic_point(&m, Ctx::ldg(W.k + (i)), Ctx::ldg(W.logk + (i)), out_ddz ? out_ddz + i : nullptr);
+            out_phi[i] = ph;
+            if (obs) { const double r = ph - obs[i]; accg = fma(r, r, accg); }
+        }
         cx.sync_warp();
-        return;
+        return obs ? 0.5 * cx.warp_sum(accg) : 0.0;
     }
     const double mu = m.ord.mu, a1 = e.a1, dz = m.dz;
 
@@ -224,6 +231,28 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     const int nT = cx.warp_max_i(lastT) + 1;
     int nS = cx.warp_max_i(lastC) + 1;
     if (nS < nT) nS = nT;
+
+    // Residuals against `obs` are accumulated as the values appear (acc: this lane's share of sum r^2) and,
+    // when the caller gave a finite `bound`, the partial misfit is checked after the cheap class and after
+    // every chunk: 0.5 sum r^2 only grows, so a proposal whose partial misfit is already above the bound is
+    // rejected without the Bessel work of the remaining points (Metropolis-Hastings rejects ~90 %).
+    double acc = 0.0;
+    const bool bounded = obs != nullptr && bound < 1e300;
+
+    // ---- S: the Bessel term cannot change the rounded bracket (no K_nu needed: done first) --------
+#pragma unroll 1
+    for (int i = nS + lane; i < nk; i += L) {
+        const double k = Ctx::ldg(W.k + (i));
+        const bool over = k * dz > CB_COSH_OVERFLOW;
+        const double ph = over ? INFINITY : fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * Ctx::ldg(W.logk + (i)) + e.lgc;
+        out_phi[i] = ph;
+        if (out_ddz) out_ddz[i] = over ? NAN : 0.0;
+        if (obs) { const double r = ph - obs[i]; acc = fma(r, r, acc); }
+    }
+    if (bounded && nS < nk) {
+        const double part = 0.5 * cx.warp_sum(acc);
+        if (!(part <= bound)) { cx.sync_warp(); return part; }       // also leaves on nan / inf
+    }
 
     // ---- order-only tables, built lane-parallel ------------------------------------------------
     if (nS > nT) {
@@ -274,76 +303,73 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
     }
     cx.sync_warp();
 
-    // ---- T: Temme's series ----------------------------------------------------------------------
+    // ---- chunks of up to L points, each entirely in the Temme class [0,nT) or the Miller class [nT,nS):
+    //      K_mu, K_mu+1 (phase T or M), then scale / raise the order / bracket (phase F) ----------------
+    const double qg = 0.25 * m.gnu;
+    const int nl = m.ord.nl;
 #pragma unroll 1
-    for (int i = lane; i < nT; i += L) {
-        const double d = -(Ctx::ldg(W.logk + (i)) + m.lhalfdz);      // ln(2/x)
-        const double sg = mu * d;
-        const double ee = cb_exp(sg), ei = 1.0 / ee;
-        // sinh(sg)/sg * d = sinh(sg)/mu
-        const double shd = fabs(sg) < 1e-4 ? d * (1.0 + sg * sg * (1.0 / 6.0)) : 0.5 * (ee - ei) * e.rmu;
-        double ff = m.ord.sinc * (m.ord.gam1 * 0.5 * (ee + ei) + m.ord.gam2 * shd);
-        double p = e.hp * ee, q = e.hq * ei, c = 1.0;
-        const double x2 = 0.5 * Ctx::ldg(W.k + (i)) * dz, dd = x2 * x2;
-        double sum = ff, sum1 = p;
+    for (int c0 = 0; c0 < nS;) {
+        const bool temme = c0 < nT;
+        const int c1 = temme ? (c0 + L < nT ? c0 + L : nT) : (c0 + L < nS ? c0 + L : nS);
+        const int i = c0 + lane;
+        if (temme) {
+            if (i < c1) {
+                const double d = -(Ctx::ldg(W.logk + (i)) + m.lhalfdz);      // ln(2/x)
+                const double sg = mu * d;
+                const double ee = cb_exp(sg), ei = 1.0 / ee;
+                // sinh(sg)/sg * d = sinh(sg)/mu
+                const double shd = fabs(sg) < 1e-4 ? d * (1.0 + sg * sg * (1.0 / 6.0)) : 0.5 * (ee - ei) * e.rmu;
+                double ff = m.ord.sinc * (m.ord.gam1 * 0.5 * (ee + ei) + m.ord.gam2 * shd);
+                double p = e.hp * ee, q = e.hq * ei, c = 1.0;
+                const double x2 = 0.5 * Ctx::ldg(W.k + (i)) * dz, dd = x2 * x2;
+                double sum = ff, sum1 = p;
 #pragma unroll 1
-        for (int j = 1; j < CB_TEMME_TAB; ++j) {
-            const double fj = (double)j;
-            const double2 r = W.rpq[j];
-            ff = (fj * ff + p + q) * (r.x * r.y);
-            c *= dd * Ctx::ldg(W.rn + (j));
-            p *= r.x;
-            q *= r.y;
-            const double del = c * ff;
-            sum += del;
-            sum1 = fma(c, p - fj * ff, sum1);
-            if (fabs(del) < fabs(sum) * CB_KNU_EPS) break;
-        }
-        out_phi[i] = sum;                       // K_mu; phase F turns it into Phi in place
-        W.kb[i] = sum1 * (2.0 * Ctx::ldg(W.rk + (i)) * e.rdz);
-    }
-
-    // ---- M: Miller backward recurrence, uniform trip count per pass ----------------------------
-#pragma unroll 1
-    for (int base = nT; base < nS; base += L) {
-        const int i = base + lane;
-        const int ii = i < nS ? i : nS - 1;
-        const double xi = Ctx::ldg(W.k + (ii)) * dz;
-        int N = (int)(12.0 + 140.0 * (Ctx::ldg(W.rk + (base)) * e.rdz)) + 1;     // from the smallest x of this pass (k ascending)
-        if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
-        double yp = 0.0, y = 1.0, S = W.CA[N].x;
-        double bn = 2.0 * ((double)N + xi);
+                for (int j = 1; j < CB_TEMME_TAB; ++j) {
+                    const double fj = (double)j;
+                    const double2 r = W.rpq[j];
+                    ff = (fj * ff + p + q) * (r.x * r.y);
+                    c *= dd * Ctx::ldg(W.rn + (j));
+                    p *= r.x;
+                    q *= r.y;
+                    const double del = c * ff;
+                    sum += del;
+                    sum1 = fma(c, p - fj * ff, sum1);
+                    if (fabs(del) < fabs(sum) * CB_KNU_EPS) break;
+                }
+                out_phi[i] = sum;                       // K_mu; phase F turns it into Phi in place
+                W.kb[i] = sum1 * (2.0 * Ctx::ldg(W.rk + (i)) * e.rdz);
+            }
+        } else {
+            // Miller backward recurrence, trip count uniform over the chunk (from its smallest x: k ascending)
+            const int ii = i < c1 ? i : c1 - 1;
+            const double xi = Ctx::ldg(W.k + (ii)) * dz;
+            int N = (int)(12.0 + 140.0 * (Ctx::ldg(W.rk + (c0)) * e.rdz)) + 1;
+            if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
+            double yp = 0.0, y = 1.0, S = W.CA[N].x;
+            double bn = 2.0 * ((double)N + xi);
 #pragma unroll 2
-        for (int n = N; n >= 1; --n) {
-            const double ym = fma(bn, y, W.CA[n].y * yp);
-            yp = y;
-            y = ym;
-            S = fma(W.CA[n - 1].x, y, S);
-            bn -= 2.0;
+            for (int n = N; n >= 1; --n) {
+                const double ym = fma(bn, y, W.CA[n].y * yp);
+                yp = y;
+                y = ym;
+                S = fma(W.CA[n - 1].x, y, S);
+                bn -= 2.0;
+            }
+            if (i < c1) {
+                const double invx = Ctx::ldg(W.rk + (ii)) * e.rdz;
+                // y, yp and S have grown together to ~1e100+: take S's exponent off all three (exact) so that
+                // the division stays on the hardware's fast path instead of the out-of-range slow path
+                const double sc = cb_pow2_inverse_of(S);
+                const double cS = Ctx::ldg(W.sq + (ii)) * e.rsdz / (S * sc);        // sqrt(pi/(2x)) / S, scaled
+                const double ys = y * sc, yps = yp * sc;
+                out_phi[i] = cS * ys;
+                W.kb[i] = cS * fma(mu + xi + 0.5, ys, -a1 * yps) * invx;
+            }
         }
-        if (i < nS) {
-            const double invx = Ctx::ldg(W.rk + (ii)) * e.rdz;
-            // y, yp and S have grown together to ~1e100+: take S's exponent off all three (exact) so that
-            // the division stays on the hardware's fast path instead of the out-of-range slow path
-            const double sc = cb_pow2_inverse_of(S);
-            const double cS = Ctx::ldg(W.sq + (ii)) * e.rsdz / (S * sc);        // sqrt(pi/(2x)) / S, scaled
-            const double ys = y * sc, yps = yp * sc;
-            out_phi[i] = cS * ys;
-            W.kb[i] = cS * fma(mu + xi + 0.5, ys, -a1 * yps) * invx;
-        }
-    }
-    cx.sync_warp();
-
-    // ---- F: scale, raise the order, bracket ------------------------------------------------------
-    //   bracket e^-x = Gamma(nu)/4 (1 + e^-2x) - hx (K_nu e^-x)
-    {
-        const double qg = 0.25 * m.gnu;
-        const int nl = m.ord.nl;
-#pragma unroll 1
-        for (int i = lane; i < nS; i += L) {
+        // ---- F (same lane, same point: no barrier needed): bracket e^-x = Gamma(nu)/4 (1 + e^-2x) - hx (K_nu e^-x)
+        if (i < c1) {
             const double k = Ctx::ldg(W.k + (i)), lk = Ctx::ldg(W.logk + (i)), xi = k * dz;
-            const bool temme = i < nT;
-            const double ex = cb_exp(temme ? -xi : -2.0 * xi);     // scales ka, kb to K e^-x in both classes
+            const double ex = cb_exp(temme ? -xi : -2.0 * xi);     // scales K_mu, K_mu+1 to K e^-x in both classes
             const double e2 = temme ? ex * ex : ex;
             double a = out_phi[i] * ex, b = W.kb[i] * ex;
             const double tox = 2.0 * Ctx::ldg(W.rk + (i)) * e.rdz;
@@ -355,21 +381,20 @@ CB_NOINLINE_BODY void model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx,
             }
             const double hx = cb_exp(m.nu * (lk + m.lhalfdz));
             const double br = fma(qg, 1.0 + e2, -b * hx);
-            out_phi[i] = fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * lk + cb_log(m.lead * br);
+            const double ph = fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * lk + cb_log(m.lead * br);
+            out_phi[i] = ph;
             // k [ (Gamma/4 (1 - e2) + hx K_{nu-1} e^-x) / br - 1 ] with the subtraction done analytically
             if (out_ddz) out_ddz[i] = k * fma(hx, a + b, -2.0 * qg * e2) / br;
+            if (obs) { const double r = ph - obs[i]; acc = fma(r, r, acc); }
+        }
+        c0 = c1;
+        if (bounded && c0 < nS) {
+            const double part = 0.5 * cx.warp_sum(acc);
+            if (!(part <= bound)) { cx.sync_warp(); return part; }
         }
     }
-
-    // ---- S: the Bessel term cannot change the rounded bracket ------------------------------------
-#pragma unroll 1
-    for (int i = nS + lane; i < nk; i += L) {
-        const double k = Ctx::ldg(W.k + (i));
-        const bool over = k * dz > CB_COSH_OVERFLOW;
-        out_phi[i] = over ? INFINITY : fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * Ctx::ldg(W.logk + (i)) + e.lgc;
-        if (out_ddz) out_ddz[i] = over ? NAN : 0.0;
-    }
     cx.sync_warp();
+    return obs ? 0.5 * cx.warp_sum(acc) : 0.0;
 }
 
 // 0.5 sum (p0 - obs)^2 over the slab (every lane returns the total).
@@ -388,9 +413,19 @@ CB_BODY double slab_half_ssq(const Ctx &cx, const WarpSlab &W, int lane) {
 template <class Ctx>
 CB_BODY double misfit_slab(const Ctx &cx, const WarpSlab &W, const double *x, const Priors &pr, int lane) {
     model_coefs_warp(cx, W, x, 0.0, 0, 1, lane);
-    model_eval_warp(cx, W, 0, lane, W.p0, nullptr);
-    const double f = slab_half_ssq(cx, W, lane);
-    cx.sync_warp();
+    const double f = model_eval_warp(cx, W, 0, lane, W.p0, nullptr, W.obs);
     if (!isfinite(f)) return CB_BIG_MISFIT;
     return f + prior_penalty(pr, x);
+}
+
+// min_func when only "is it <= bound?" matters: the return value is exact when it is <= bound, and some
+// value > bound (a partial sum, or 1e99 for a non-finite model) otherwise.
+template <class Ctx>
+CB_BODY double misfit_slab_bounded(const Ctx &cx, const WarpSlab &W, const double *x, const Priors &pr, int lane,
+                                   double bound) {
+    const double pen = prior_penalty(pr, x);
+    model_coefs_warp(cx, W, x, 0.0, 0, 1, lane);
+    const double f = model_eval_warp(cx, W, 0, lane, W.p0, nullptr, W.obs, bound - pen);
+    if (!isfinite(f)) return CB_BIG_MISFIT;
+    return f + pen;
 }
