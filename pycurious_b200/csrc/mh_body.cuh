@@ -82,6 +82,9 @@ CB_HD double philox_uniform(uint64_t t, uint32_t ph, uint32_t k0, uint32_t k1) {
     return u52(c.v[0], c.v[1]);
 }
 
+// slab of one chain: model arrays, CB_MH_BLOCK coefficient slots, the block's proposals / uniforms / penalties
+CB_HD int mh_slab_doubles(int nk) { return warp_slab_doubles(nk, false, 6 * CB_MH_BLOCK, CB_MH_BLOCK); }
+
 template <class Ctx>
 CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     const int tid = cx.tid();
@@ -90,9 +93,13 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     const int64_t w = (int64_t)cx.bid() * P.warps_per_block + warp;
     if (w >= P.nwin) return;
 
-    WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * warp_slab_doubles(nk, false),
-                                 nk, false, P.kh, P.ktab);
+    WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * mh_slab_doubles(nk), nk, false,
+                                 P.kh, P.ktab, CB_MH_BLOCK);
     warp_slab_load(cx, W, P.phi + w * nk, lane);
+    const int L = cx.team_lanes();
+    double *props = W.scratch;                  // [CB_MH_BLOCK][4] proposals of the current block
+    double *us = props + 4 * CB_MH_BLOCK;       // [CB_MH_BLOCK] acceptance uniforms
+    double *pens = us + CB_MH_BLOCK;            // [CB_MH_BLOCK] prior penalties of the proposals
 
     const cb_mh_options &o = P.opt;
     Priors pr;
@@ -107,29 +114,58 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     const uint64_t chain = o.chain_offset + (uint64_t)w;
     const uint32_t k0 = (uint32_t)(o.seed ^ chain), k1 = (uint32_t)((o.seed >> 32) ^ (chain >> 32));
 
+    // Blocks of proposals.  Until a proposal is accepted every step proposes from the SAME state, so the
+    // random draws, the proposals and their order-only coefficients (Gamma functions, 1/Gamma(1+-mu), logs:
+    // the scalar third of a step) of the next CB_MH_BLOCK steps are prepared together, one lane each.  The
+    // steps are then decided in order; an acceptance invalidates the rest of the block, which is simply
+    // prepared again from the new state (acceptance is ~5-10 %).  Draws are keyed by the step index, so the
+    // chain is exactly the sequential one.
     // Early rejection: min_func = 0.5 sum r^2 + priors only grows while the points are evaluated, so a
     // proposal whose partial misfit already exceeds what acceptance would need is rejected without
-    // finishing the model (misfit_slab_bounded).  The bound carries a 1e-6 relative margin; inside the
-    // margin the evaluation is completed and the reference's own test decides, so every accept / reject
-    // decision -- and therefore the chain -- is the one the full evaluation gives.
+    // finishing the model.  The bound carries a 1e-6 relative margin; inside the margin the evaluation is
+    // completed and the reference's own test decides.
+    auto prepare = [&](int64_t t0, int n, uint32_t phase) {
+        cx.sync_warp();                         // nobody still reads the previous block
+        for (int l = lane; l < n; l += L) {
+            double z[4], x1[4];
+            philox_normal4((uint64_t)(t0 + l), phase, k0, k1, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { x1[j] = x[j] + z[j] * scale[j]; props[4 * l + j] = x1[j]; }
+            pens[l] = prior_penalty(pr, x1);
+            us[l] = phase ? philox_uniform((uint64_t)(t0 + l), phase, k0, k1) : 0.0;
+        }
+        cx.sync_warp();
+        model_coefs_lanes(cx, W, props, n, lane);
+    };
+    // min_func of proposal l of the block, exact when <= bound (see model_eval_warp)
+    auto misfit_of = [&](int l, double bound) -> double {
+        const double pen = pens[l];
+        const double f = model_eval_warp(cx, W, l, lane, W.p0, nullptr, W.obs, bound - pen);
+        return isfinite(f) ? f + pen : CB_BIG_MISFIT;
+    };
+
     // ---- burn-in (optimise.py:598-611): accept iff exp(-f1/1000) > exp(-f0/1000) ----
     double f0 = misfit_slab(cx, W, x, pr, lane);
     double P0 = exp(-f0 / 1000.0);
-    for (int64_t t = 0; t < o.burnin; ++t) {
-        double z[4], x1[4];
-        philox_normal4((uint64_t)t, 0u, k0, k1, z);
+    for (int64_t t = 0; t < o.burnin;) {
+        const int n = (int)(o.burnin - t < CB_MH_BLOCK ? o.burnin - t : CB_MH_BLOCK);
+        prepare(t, n, 0u);
+        int used = n;
+        for (int l = 0; l < n; ++l) {
+            const double bound = f0 + 1e-6 * fmax(1.0, fabs(f0));
+            const double f1 = misfit_of(l, bound);
+            if (f1 > bound) continue;
+            const double P1 = exp(-f1 / 1000.0);
+            if (P1 > P0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
-        const double bound = f0 + 1e-6 * fmax(1.0, fabs(f0));
-        const double f1 = misfit_slab_bounded(cx, W, x1, pr, lane, bound);
-        if (f1 > bound) continue;
-        const double P1 = exp(-f1 / 1000.0);
-        if (P1 > P0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = x1[j];
-            P0 = P1;
-            f0 = f1;
+                for (int j = 0; j < 4; ++j) x[j] = props[4 * l + j];
+                P0 = P1;
+                f0 = f1;
+                used = l + 1;
+                break;
+            }
         }
+        t += used;
     }
 
     // ---- sampling (optimise.py:613-631): accept iff u <= min(exp(-f1) / max(P0, 1e-99), 1) ----
@@ -137,43 +173,47 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     int64_t nacc = 0;
     double mean[5] = {0, 0, 0, 0, 0}, m2[5] = {0, 0, 0, 0, 0};   // Welford accumulators (mode 1)
     double *chain_out = P.out + w * 4 * o.nsim;
-    for (int64_t t = 0; t < o.nsim; ++t) {
-        double z[4], x1[4];
-        philox_normal4((uint64_t)t, 1u, k0, k1, z);
-        const double u = philox_uniform((uint64_t)t, 1u, k0, k1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x1[j] = x[j] + z[j] * scale[j];
-        P0 = fmax(P0, 1e-99);
-        const double need = -log(u * P0);                 // exp(-f1)/P0 >= u  <=>  f1 <= -ln(u P0)
-        const double bound = need + 1e-6 * fmax(1.0, fabs(need));
-        const double f1 = misfit_slab_bounded(cx, W, x1, pr, lane, bound);
-        bool take = false;
-        double P1 = 0.0;
-        if (!(f1 > bound)) {
-            P1 = exp(-f1);
-            take = u <= fmin(P1 / P0, 1.0);
-        }
-        if (take) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = x1[j];
-            P0 = P1;
-            ++nacc;
-        }
-        if (o.reduce_mode == 0) {
-            if (lane == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) chain_out[j * o.nsim + t] = x[j];
+    for (int64_t t0 = 0; t0 < o.nsim;) {
+        const int n = (int)(o.nsim - t0 < CB_MH_BLOCK ? o.nsim - t0 : CB_MH_BLOCK);
+        prepare(t0, n, 1u);
+        int used = n;
+        for (int l = 0; l < n; ++l) {
+            const int64_t t = t0 + l;
+            const double u = us[l];
+            P0 = fmax(P0, 1e-99);
+            const double need = -log(u * P0);                 // exp(-f1)/P0 >= u  <=>  f1 <= -ln(u P0)
+            const double bound = need + 1e-6 * fmax(1.0, fabs(need));
+            const double f1 = misfit_of(l, bound);
+            bool take = false;
+            double P1 = 0.0;
+            if (!(f1 > bound)) {
+                P1 = exp(-f1);
+                take = u <= fmin(P1 / P0, 1.0);
             }
-        } else {
-            const double v[5] = {x[0], x[1], x[2], x[3], x[1] + x[2]};
-            const double inv = 1.0 / (double)(t + 1);
+            if (take) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const double dlt = v[j] - mean[j];
-                mean[j] += dlt * inv;
-                m2[j] = fma(dlt, v[j] - mean[j], m2[j]);
+                for (int j = 0; j < 4; ++j) x[j] = props[4 * l + j];
+                P0 = P1;
+                ++nacc;
             }
+            if (o.reduce_mode == 0) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) chain_out[j * o.nsim + t] = x[j];
+                }
+            } else {
+                const double v[5] = {x[0], x[1], x[2], x[3], x[1] + x[2]};
+                const double inv = 1.0 / (double)(t + 1);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const double dlt = v[j] - mean[j];
+                    mean[j] += dlt * inv;
+                    m2[j] = fma(dlt, v[j] - mean[j], m2[j]);
+                }
+            }
+            if (take) { used = l + 1; break; }
         }
+        t0 += used;
     }
     if (lane == 0) {
         if (o.reduce_mode != 0) {

@@ -185,9 +185,11 @@ int cb_bouligand_points(const double *kh_dev, const double *params_dev, int64_t 
     return CB_OK;
 }
 
-static int per_warp_launch_shape(int nk, int64_t nwin, bool fit, int *grid, size_t *smem) {
+enum { SLAB_MISFIT = 0, SLAB_FIT = 1, SLAB_MH = 2 };
+static int per_warp_launch_shape(int nk, int64_t nwin, int kind, int *grid, size_t *smem) {
     CB_REQUIRE(nk > 0 && nk <= 512, "nk must be in [1, 512]");
-    *smem = (size_t)CB_FIT_WARPS * (size_t)(fit ? fit_slab_doubles(nk) : warp_slab_doubles(nk, false)) * sizeof(double);
+    const int slab = kind == SLAB_FIT ? fit_slab_doubles(nk) : (kind == SLAB_MH ? mh_slab_doubles(nk) : warp_slab_doubles(nk, false));
+    *smem = (size_t)CB_FIT_WARPS * (size_t)slab * sizeof(double);
     int64_t g = (nwin + CB_FIT_WARPS - 1) / CB_FIT_WARPS;
     CB_REQUIRE(g <= 2147483647LL, "too many windows for one launch");
     *grid = (int)g;
@@ -204,7 +206,7 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
     if (rc) return rc;
     int grid;
     size_t smem;
-    if ((rc = per_warp_launch_shape(nk, m, false, &grid, &smem)) != CB_OK) return rc;
+    if ((rc = per_warp_launch_shape(nk, m, SLAB_MISFIT, &grid, &smem)) != CB_OK) return rc;
     MisfitParams P;
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.phi_stride = phi_stride; P.params = params_dev; P.m = m; P.out = out_dev;
     for (int j = 0; j < 4; ++j) {
@@ -235,7 +237,7 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     if (rc) return rc;
     int grid;
     size_t smem;
-    if ((rc = per_warp_launch_shape(nk, nwin, true, &grid, &smem)) != CB_OK) return rc;
+    if ((rc = per_warp_launch_shape(nk, nwin, SLAB_FIT, &grid, &smem)) != CB_OK) return rc;
     FitParams P;
     memset(&P, 0, sizeof(P));
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
@@ -301,7 +303,7 @@ int cb_mh_batch(const double *kh_dev, int nk, const double *phi_dev, int64_t nwi
     if (rc) return rc;
     int grid;
     size_t smem;
-    if ((rc = per_warp_launch_shape(nk, nwin, false, &grid, &smem)) != CB_OK) return rc;
+    if ((rc = per_warp_launch_shape(nk, nwin, SLAB_MH, &grid, &smem)) != CB_OK) return rc;
     MhParams P;
     memset(&P, 0, sizeof(P));
     P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;

@@ -36,6 +36,7 @@
 #define CB_TEMME_TAB 28
 #define CB_SKIP_LOG 43.0                      /* > 60 ln 2 + ln(4 sqrt(pi/4)) */
 #define CB_COSH_OVERFLOW 710.4758600739439    /* np.cosh overflows above this */
+#define CB_MH_BLOCK 8                         /* proposals prepared together by the MCMC kernel */
 #define CB_MAX_ORDERS 3                       /* parameter vectors evaluated per call group: x, x+h e_beta, x-h e_beta */
 
 #if defined(__CUDACC__) && !defined(CB_EMU)
@@ -69,7 +70,7 @@ struct WarpSlab {          // views into one warp's shared-memory slab
     double *res;                        // [nk] fit only: residuals during the reduction
     double2 *CA;                        // [CB_MILLER_NMAX + 1] (C_n, a_{n+1}) of the order being evaluated
     double2 *rpq;                       // [CB_TEMME_TAB] (1/(j-mu), 1/(j+mu))
-    EvalCoef *coef;                     // [CB_MAX_ORDERS]
+    EvalCoef *coef;                     // [ncoef]: CB_MAX_ORDERS (fit) or CB_MH_BLOCK (MCMC) parameter vectors
     double *scratch;                    // solver state (fit) behind the tables
     int nk;
     bool sorted;
@@ -79,9 +80,9 @@ struct WarpSlab {          // views into one warp's shared-memory slab
 
 #define CB_SLAB_COEF_DOUBLES ((int)((sizeof(EvalCoef) + 7) / 8))
 
-CB_HD int warp_slab_doubles(int nk, bool fit, int scratch_doubles = 0) {
+CB_HD int warp_slab_doubles(int nk, bool fit, int scratch_doubles = 0, int ncoef = CB_MAX_ORDERS) {
     int n = (fit ? 7 : 3) * nk + 2 * (CB_MILLER_NMAX + 1) + 2 * CB_TEMME_TAB +
-            CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES + scratch_doubles;
+            ncoef * CB_SLAB_COEF_DOUBLES + scratch_doubles;
     return (n + 1) & ~1;      // keep every slab 16-byte aligned
 }
 
@@ -110,7 +111,8 @@ CB_HD double ktable_entry(const double *kh, int nk, int i) {
     return i == 0 ? (asc ? 1.0 : 0.0) : (i == 1 ? kmin : kmax);
 }
 
-CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh, const double *ktab) {
+CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh, const double *ktab,
+                               int ncoef = CB_MAX_ORDERS) {
     WarpSlab W;
     W.nk = nk;
     W.k = kh; W.logk = ktab; W.rk = ktab + nk; W.sq = ktab + 2 * nk; W.rn = ktab + 3 * nk;
@@ -121,7 +123,7 @@ CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh,
     double *t = base;
     W.CA = reinterpret_cast<double2 *>(t); t += 2 * (CB_MILLER_NMAX + 1);
     W.rpq = reinterpret_cast<double2 *>(t); t += 2 * CB_TEMME_TAB;
-    W.coef = reinterpret_cast<EvalCoef *>(t); t += CB_MAX_ORDERS * CB_SLAB_COEF_DOUBLES;
+    W.coef = reinterpret_cast<EvalCoef *>(t); t += ncoef * CB_SLAB_COEF_DOUBLES;
     W.obs = t; W.p0 = t + nk; W.kb = t + 2 * nk;
     t += 3 * nk;
     if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; W.res = t + 3 * nk; t += 4 * nk; }
@@ -140,6 +142,24 @@ CB_BODY void warp_slab_load(const Ctx &cx, WarpSlab &W, const double *phi_row, i
     cx.sync_warp();
 }
 
+CB_HD EvalCoef eval_coef_make(double beta, double zt, double dz, double C) {
+    EvalCoef e;
+    e.m = model_coef(beta, zt, dz, C);
+    const ModelCoef &m = e.m;
+    e.a1 = 0.25 - m.ord.mu * m.ord.mu;
+    e.rdz = 1.0 / m.dz;
+    e.rsdz = 1.0 / sqrt(m.dz);
+    e.lgnu = cb_log(m.gnu);
+    e.lgc = cb_log(m.lead * m.gnu * 0.25);
+    e.hp = 0.5 / m.ord.gampl;
+    e.hq = 0.5 / m.ord.gammi;
+    e.rmu = 1.0 / m.ord.mu;
+    e.fast = (m.dz > 0.0 && m.dz < 1e300 && m.nu >= 0.5 && m.nu <= 8.5 && isfinite(m.zt) && isfinite(m.C) &&
+              m.gnu > 0.0 && m.lead > 0.0 && isfinite(m.gnu) && isfinite(m.lead)) ? 1 : 0;
+    e.pad_ = 0;
+    return e;
+}
+
 // Coefficients of `count` parameter vectors x + off[idx] e_beta, idx = first .. first+count-1, with
 // off = (0, +hb, -hb): lane l computes vector first+l (the lanes run the same code on different data).
 template <class Ctx>
@@ -149,22 +169,17 @@ CB_NOINLINE_BODY void model_coefs_warp(const Ctx &cx, const WarpSlab &W, const d
     for (int l = lane; l < count; l += L) {
         const int idx = first + l;
         const double beta = x[0] + (idx == 1 ? hb : (idx == 2 ? -hb : 0.0));
-        EvalCoef e;
-        e.m = model_coef(beta, x[1], x[2], x[3]);
-        const ModelCoef &m = e.m;
-        e.a1 = 0.25 - m.ord.mu * m.ord.mu;
-        e.rdz = 1.0 / m.dz;
-        e.rsdz = 1.0 / sqrt(m.dz);
-        e.lgnu = cb_log(m.gnu);
-        e.lgc = cb_log(m.lead * m.gnu * 0.25);
-        e.hp = 0.5 / m.ord.gampl;
-        e.hq = 0.5 / m.ord.gammi;
-        e.rmu = 1.0 / m.ord.mu;
-        e.fast = (m.dz > 0.0 && m.dz < 1e300 && m.nu >= 0.5 && m.nu <= 8.5 && isfinite(m.zt) && isfinite(m.C) &&
-                  m.gnu > 0.0 && m.lead > 0.0 && isfinite(m.gnu) && isfinite(m.lead)) ? 1 : 0;
-        e.pad_ = 0;
-        W.coef[idx] = e;
+        W.coef[idx] = eval_coef_make(beta, x[1], x[2], x[3]);
     }
+    cx.sync_warp();
+}
+
+// Coefficients of `count` unrelated parameter vectors props[l][0..3] -> slot l, one lane each (the
+// Metropolis-Hastings kernel prepares a block of proposals at once).
+template <class Ctx>
+CB_NOINLINE_BODY void model_coefs_lanes(const Ctx &cx, const WarpSlab &W, const double *props, int count, int lane) {
+    const int L = cx.team_lanes();
+    for (int l = lane; l < count; l += L) W.coef[l] = eval_coef_make(props[4 * l], props[4 * l + 1], props[4 * l + 2], props[4 * l + 3]);
     cx.sync_warp();
 }
 

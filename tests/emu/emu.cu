@@ -291,14 +291,14 @@ int emu_mh(const double *kh, int nk, const double *phi, int64_t nwin, const cb_m
     P.kh = kh; P.ktab = ktab.data(); P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0; P.out = out; P.accepted = accepted;
     if (mode == 0) {
         P.warps_per_block = 1;
-        std::vector<double> sm(warp_slab_doubles(nk, false));
+        std::vector<double> sm(mh_slab_doubles(nk));
         for (int64_t w = 0; w < nwin; ++w) {
             SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
             mh_body(cx, P);
         }
     } else {
         P.warps_per_block = 2;
-        emu_launch((int)((nwin + 1) / 2), 64, 2 * warp_slab_doubles(nk, false) * sizeof(double), [&](const HostCtx &cx) { mh_body(cx, P); });
+        emu_launch((int)((nwin + 1) / 2), 64, 2 * mh_slab_doubles(nk) * sizeof(double), [&](const HostCtx &cx) { mh_body(cx, P); });
     }
     return 0;
 }
