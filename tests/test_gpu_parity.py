@@ -480,3 +480,68 @@ def test_reference_suite_behaviour(pc, grid, mag):
     finally:
         grid.reset_priors()
     assert abs(beta1 - 1.0) < abs(beta - 1.0)
+
+
+# --------------------------------------------------------------------------- C-ABI error behaviour
+def test_c_abi_rejects_bad_arguments(pc, grid):
+    """Every entry point returns a negative cb_status and sets cb_last_error instead of faulting: NULL buffers,
+    negative counts, a workspace that is too small, inconsistent bounds, a window larger than the grid."""
+    import ctypes as C
+    import torch
+    from pycurious_b200 import _lib, _plans
+    lib = _lib.load()
+    plan = _plans.spectrum_plan(101, grid.dx, _plans.taper_vector(np.hanning, 101))
+    g = grid.device_grid()
+    iy0 = torch.zeros(2, dtype=torch.int32, device="cuda")
+    phi = torch.empty((2, plan.nbins), dtype=torch.float64, device="cuda")
+    ws = plan.workspace
+    args = lambda **kw: None
+    # workspace too small
+    rc = lib.cb_spectrum_batch(plan.handle, g.data_ptr(), g.shape[0], g.shape[1], g.stride(0), iy0.data_ptr(), iy0.data_ptr(),
+                               2, 0, 2.0, phi.data_ptr(), phi.data_ptr(), ws.data_ptr(), 1024, None)
+    assert rc == -1 and b"workspace" in lib.cb_last_error()
+    # NULL output
+    rc = lib.cb_spectrum_batch(plan.handle, g.data_ptr(), g.shape[0], g.shape[1], g.stride(0), iy0.data_ptr(), iy0.data_ptr(),
+                               2, 0, 2.0, None, phi.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == -1
+    # grid smaller than the window
+    rc = lib.cb_spectrum_batch(plan.handle, g.data_ptr(), 50, 50, 50, iy0.data_ptr(), iy0.data_ptr(),
+                               2, 0, 2.0, phi.data_ptr(), phi.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == -1
+    # fit: lower bound above upper bound, negative count, NULL spectra
+    o = _lib.FitOptions()
+    for j in range(4):
+        o.x0[j], o.lb[j], o.ub[j], o.prior_mu[j], o.prior_sigma[j] = 1.0, 2.0, 1.0, float("nan"), float("nan")
+    k = torch.linspace(0.1, 3.0, plan.nbins, dtype=torch.float64, device="cuda")
+    x = torch.empty((2, 4), dtype=torch.float64, device="cuda")
+    rc = lib.cb_fit_batch(k.data_ptr(), plan.nbins, phi.data_ptr(), 2, C.byref(o), None, x.data_ptr(), None, None, None, None, None)
+    assert rc == -1 and b"bound" in lib.cb_last_error()
+    for j in range(4):
+        o.lb[j], o.ub[j] = 0.0, float("inf")
+    assert lib.cb_fit_batch(k.data_ptr(), plan.nbins, phi.data_ptr(), -1, C.byref(o), None, x.data_ptr(), None, None, None, None, None) == -1
+    assert lib.cb_fit_batch(k.data_ptr(), plan.nbins, None, 2, C.byref(o), None, x.data_ptr(), None, None, None, None, None) == -1
+    assert lib.cb_fit_batch(k.data_ptr(), 0, phi.data_ptr(), 2, C.byref(o), None, x.data_ptr(), None, None, None, None, None) == -1
+    # zero windows is a no-op
+    assert lib.cb_fit_batch(k.data_ptr(), plan.nbins, phi.data_ptr(), 0, C.byref(o), None, x.data_ptr(), None, None, None, None, None) == 0
+    # MH: bad reduce mode / negative chain length
+    m = _lib.MhOptions()
+    m.nsim, m.burnin, m.reduce_mode = 10, 1, 7
+    out = torch.empty((2, 10), dtype=torch.float64, device="cuda")
+    assert lib.cb_mh_batch(k.data_ptr(), plan.nbins, phi.data_ptr(), 2, C.byref(m), None, out.data_ptr(), None, None) == -1
+    m.reduce_mode, m.nsim = 1, -5
+    assert lib.cb_mh_batch(k.data_ptr(), plan.nbins, phi.data_ptr(), 2, C.byref(m), None, out.data_ptr(), None, None) == -1
+    # plan creation: taper given for one axis only, nonsense bins
+    h = C.c_void_p()
+    t = np.hanning(21)
+    ptr = np.array([0, 1], dtype=np.int32)
+    idx = np.array([5000], dtype=np.int32)
+    assert lib.cb_spectrum_plan_create(21, 1, t.ctypes.data, None, ptr.ctypes.data, idx.ctypes.data, C.byref(h)) == -1
+    assert lib.cb_spectrum_plan_create(21, 1, None, None, ptr.ctypes.data, idx.ctypes.data, C.byref(h)) == -4
+    torch.cuda.synchronize()
+    # the Python face turns statuses into exceptions and keeps the reference's ValueErrors
+    with pytest.raises(ValueError, match="outside data range"):
+        grid.optimise_routine(100e3, [1e9], [1e9])
+    with pytest.raises(ValueError, match="exceeds the data range"):
+        grid.optimise_routine(300e3, [grid.xmin + 1e3], [grid.ymin + 1e3])
+    with pytest.raises(ValueError, match="same size"):
+        grid.optimise_routine(100e3, [150e3, 160e3], [150e3])
