@@ -36,7 +36,7 @@ struct SpectrumParams {
     const int32_t *slot;      // n: slot of X[k] after DIF (direct mode)
     const double *taper_r, *taper_c;   // n each, or NULL
     const int32_t *bin_ptr, *bin_idx;  // folded CSR, ids v*n+u
-    const int32_t *col_span;           // [nvh] (lo | hi << 16): only u in [lo, hi] of column v belong to a bin
+    const int32_t *col_span;           // [nvh] (lo_end | hi_start << 16): u <= lo_end or u >= hi_start belong to a bin (0xffff: none)
     int32_t nbins;
     int32_t detrend;
     double power;
@@ -273,9 +273,10 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                 };
                 // |chirp| = 1, so the modulus needs no post-multiply; outputs go straight to the slab.
                 // The log is only taken where a radial bin will read it (the corners of the plane lie outside).
-                const int span = Ctx::ldg(P.col_span + v), ulo = span & 0xffff, uhi = span >> 16;
+                const int span = Ctx::ldg(P.col_span + v);
+                const int lo_end = (span & 0xffff) == 0xffff ? -1 : (span & 0xffff), hi_start = (int)((unsigned)span >> 16);
                 auto sk = [&](int u, double2 z) {
-                    if (u >= ulo && u <= uhi) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
                 };
                 Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
             }
@@ -455,9 +456,10 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
             if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
                 fused = true;
                 auto ld = [&](int y) -> double2 { return y < n ? element(y) : cplx(0.0, 0.0); };
-                const int span = Ctx::ldg(P.col_span + v), ulo = span & 0xffff, uhi = span >> 16;
+                const int span = Ctx::ldg(P.col_span + v);
+                const int lo_end = (span & 0xffff) == 0xffff ? -1 : (span & 0xffff), hi_start = (int)((unsigned)span >> 16);
                 auto sk = [&](int u, double2 z) {
-                    if (u >= ulo && u <= uhi) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
                 };
                 Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
             }

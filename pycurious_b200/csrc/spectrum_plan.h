@@ -114,15 +114,17 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
     for (int e = bin_ptr[0]; e < bin_ptr[nbins]; ++e)
         if (bin_idx[e] < 0 || bin_idx[e] >= nw * nw) { hp.error = "bin_idx out of range"; return false; }
     fold_bins(nw, nbins, bin_ptr, bin_idx, hp.bin_ptr, hp.bin_idx);
-    {   // per half-plane column the range of u that any bin reads (lo > hi: none)
-        std::vector<int> lo(hp.nvh, 0xffff), hi(hp.nvh, -1);
+    {   // per half-plane column the u that some bin reads: a circular run around u = 0 (low |frequency|),
+        // i.e. u <= lo_end or u >= hi_start; the middle of the column lies beyond the last bin edge
+        const int halfn = nw / 2;
+        std::vector<int> lo_end(hp.nvh, -1), hi_start(hp.nvh, 0xffff);
         for (int32_t id : hp.bin_idx) {
             const int v = id / nw, u = id % nw;
-            lo[v] = std::min(lo[v], u);
-            hi[v] = std::max(hi[v], u);
+            if (u <= halfn) lo_end[v] = std::max(lo_end[v], u);
+            else hi_start[v] = std::min(hi_start[v], u);
         }
         hp.col_span.resize(hp.nvh);
-        for (int v = 0; v < hp.nvh; ++v) hp.col_span[v] = hi[v] < 0 ? 0x0000ffff : (lo[v] | (hi[v] << 16));
+        for (int v = 0; v < hp.nvh; ++v) hp.col_span[v] = (lo_end[v] < 0 ? 0xffff : lo_end[v]) | (hi_start[v] << 16);
     }
 
     hp.line_slots = (fft_line_slots(hp.fft.n) + 1) & ~1;
