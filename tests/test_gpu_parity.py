@@ -135,6 +135,33 @@ def test_shared_row_spectra_path_equals_direct_path(pc, grid, oracle, mag, detre
         np.testing.assert_allclose(ph[i], p0, rtol=1e-10)
 
 
+@pytest.mark.parametrize("nw", [20, 21, 30, 51, 64, 75, 128, 151, 256, 305])
+def test_window_size_sweep_both_paths(pc, oracle, nw):
+    """Odd / even / prime / 2-3-5-smooth window edges (Bluestein on static and generic engines, direct
+    mixed radix), each through cb_spectrum_batch and cb_spectrum_batch_shared_rows, with taper + detrend,
+    against the oracle."""
+    import torch
+    from pycurious_b200 import _plans
+    rng = np.random.default_rng(nw)
+    ny, nx = 2 * nw + 7, 2 * nw + 12
+    data = rng.standard_normal((ny, nx)).cumsum(axis=0).cumsum(axis=1)      # red, trended field
+    ext = pc.synth.grid_extent(ny, nx)
+    G = pc.CurieGrid(data, *ext)
+    origins = [(0, 0), (3, 5), (ny - nw, nx - nw), (3, nx - nw), (8, 5)]
+    iy0 = torch.tensor([o[0] for o in origins], dtype=torch.int32, device="cuda")
+    ix0 = torch.tensor([o[1] for o in origins], dtype=torch.int32, device="cuda")
+    plan = _plans.spectrum_plan(nw, G.dx, _plans.taper_vector(np.hamming, nw))
+    g = G.device_grid()
+    for share in (False, True):
+        phi, sig = plan.run(g, iy0, ix0, True, 2.0, share_rows=share)
+        phi, sig = phi.cpu().numpy(), sig.cpu().numpy()
+        for w, (j0, i0) in enumerate(origins):
+            win = oracle.detrend_plane(data[j0:j0 + nw, i0:i0 + nw])
+            k0, p0, s0 = oracle.radial_spectrum(win, G.dx, taper=np.hamming, power=2.0)
+            np.testing.assert_allclose(phi[w], p0, rtol=2e-10, atol=1e-10, err_msg=str((nw, share, w)))
+            np.testing.assert_allclose(sig[w], s0, rtol=1e-8)
+
+
 def test_emag2_shaped_grid_far_corner(pc, oracle):
     """BASELINE config 5 geometry: a 21600 x 10800 node grid (1.87 GB).  Windows in the far corner address
     elements beyond 2^31 bytes; all three window sizes (101 / 201 / 301 nodes -> Bluestein 256 / 512 / 625),
@@ -280,6 +307,49 @@ def test_fit_200km_priors_detrend(grid, oracle):
         grid.reset_priors()
     assert x.shape == (4,)
     _check_fit(oracle, g, "w300_betaprior", x[None, :])
+
+
+def test_fit_random_truths_bounds_and_priors(grid, oracle):
+    """Spectra synthesised from random (beta, zt, dz, C) with noise, fitted under default bounds, a custom
+    box (grid.bounds is user-writable, optimise.py:111-114) and priors: never worse than the reference's
+    stopping point, parameters within 1e-4 where the reference is itself converged."""
+    import torch
+    from pycurious_b200 import _lib
+    rng = np.random.default_rng(2026)
+    k = load_golden("fit.npz")["w200_k"]
+    n = 24
+    truth = np.c_[rng.uniform(1.5, 4.5, n), rng.uniform(0.0, 3.0, n), rng.uniform(3.0, 60.0, n), rng.uniform(-25, 25, n)]
+    phi = np.array([oracle.bouligand2009(k, *t) for t in truth]) + 0.5 * rng.standard_normal((n, k.size))
+    phi_t = torch.from_numpy(phi).cuda()
+    cases = [("default", [(0.0, None), (0.0, None), (0.0, None), (None, None)], {}),
+             ("box", [(2.0, 4.0), (0.1, 2.0), (5.0, 40.0), (None, None)], {}),
+             ("priors", [(0.0, None), (0.0, None), (0.0, None), (None, None)], dict(beta=(3.0, 0.3), dz=(20.0, 5.0)))]
+    saved = grid.bounds
+    try:
+        for tag, bounds, priors in cases:
+            grid.bounds = bounds
+            grid.reset_priors()
+            if priors:
+                grid.add_prior(**priors)
+            mu, sg = grid._prior_arrays()
+            x = grid._fit_device(k, phi_t, (3.0, 1.0, 10.0, 5.0)).cpu().numpy()
+            ngate = 0
+            for i in range(n):
+                ref = oracle.map_fit(k, phi[i], bounds=bounds, prior_mu=mu, prior_sigma=sg)
+                f_ref = oracle.misfit(ref, k, phi[i], mu, sg)
+                f_us = oracle.misfit(x[i], k, phi[i], mu, sg)
+                assert f_us <= f_ref * (1 + 1e-9) + 1e-12, (tag, i, f_us, f_ref, x[i], ref)
+                lo = np.array([-np.inf if b[0] is None else b[0] for b in bounds])
+                hi = np.array([np.inf if b[1] is None else b[1] for b in bounds])
+                assert np.all(x[i] >= lo - 1e-12) and np.all(x[i] <= hi + 1e-12), (tag, i, x[i])
+                if abs(f_ref - f_us) <= 1e-9 * max(1.0, f_ref):          # the reference reached the same minimum
+                    rel = np.max(np.abs(x[i] - ref) / np.maximum(np.abs(ref), 1e-3))
+                    if rel < 1e-4:
+                        ngate += 1
+            assert ngate >= n // 2, (tag, ngate)
+    finally:
+        grid.bounds = saved
+        grid.reset_priors()
 
 
 def test_fit_custom_process_subgrid_and_single(grid, oracle, mag):
