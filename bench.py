@@ -27,6 +27,9 @@ import time
 os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")      # fair CPU baseline: 1 BLAS thread per worker process
 os.environ.setdefault("OMP_NUM_THREADS", "1")
 os.environ.setdefault("MKL_NUM_THREADS", "1")
+# stdout carries exactly one JSON line: keep NCCL's banner (NCCL_DEBUG=VERSION/INFO on some boxes) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("CB_BENCH_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np
 
