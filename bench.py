@@ -104,7 +104,7 @@ def run_reference(args):
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     sample = "%d of %d windows per step (evenly spaced), oracle port, fork pool, OPENBLAS_NUM_THREADS=1" % (nsample, xc.size)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([d for _, d in vals])),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -373,7 +373,7 @@ def run_gpu(args):
                 "plan": {"fft_len": info.fft_len, "bluestein": info.bluestein, "radix": list(info.radix[:info.npass]),
                          "teams": info.teams, "ctas": info.grid_max, "smem_bytes": info.smem_bytes},
                 "mcmc": mcmc, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -382,7 +382,27 @@ def nb_points(plan):
     return plan.nbins
 
 
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries (NCCL's version banner, for one) write to file
+    descriptor 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes
+    to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
+_OUT = None
+
+
+def emit(line):
+    _OUT.write(line + "\n")
+    _OUT.flush()
+
+
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
