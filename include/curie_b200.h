@@ -229,6 +229,23 @@ int cb_mh_batch(const double *kh_dev, int nk,
                 void *stream);
 
 /* ------------------------------------------------------------------------
+ * FFT-domain filters of a whole array:  out = real(ifft2(filter * fft2(data)))
+ * replaces the numpy.fft.fft2 / ifft2 pairs of CurieGrid.reduce_to_pole (pycurious/grid.py:489-490) and
+ * CurieGrid.upward_continuation (grid.py:545-546).  `filter_dev` is a complex128 [ny, nx] array (interleaved
+ * re, im) built by the host with the reference's expressions; arbitrary ny, nx (Bluestein for non-smooth
+ * lengths) up to the shared-memory line limit (~14,000 points smooth, ~6,000 otherwise).
+ * ---------------------------------------------------------------------- */
+typedef struct cb_fft_plan cb_fft_plan;
+int cb_fft_plan_create(int n, cb_fft_plan **out);
+int cb_fft_plan_destroy(cb_fft_plan *plan);
+int64_t cb_fft2_filter_workspace_bytes(int64_t ny, int64_t nx);
+int cb_fft2_filter(const cb_fft_plan *plan_x /* length nx */, const cb_fft_plan *plan_y /* length ny */,
+                   const double *data_dev, int64_t ny, int64_t nx, int64_t ld,
+                   const void *filter_dev /* complex128 [ny, nx] */,
+                   double *out_dev, int64_t out_ld,
+                   void *workspace_dev, int64_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
  * Tanaka et al. (1999):  tanaka1999 + ComputeTanaka (pycurious/grid.py:603-699) for a batch of
  * radial spectra taken with power = 0.5.  out[w, 0..7] = Ztr, btr, dZtr, Zor, bor, dZor, Zb, eZb;
  * (kmin_lo, kmin_hi) / (kmax_lo, kmax_hi) are the reference's kmin_range / kmax_range.

@@ -577,6 +577,54 @@ def compute_tanaka(Ztr, dZtr, Zor, dZor):
 
 
 # --------------------------------------------------------------------------
+# FFT-domain filters  (pycurious/grid.py:405-546, :738-808)
+# --------------------------------------------------------------------------
+def dircos(inc, dec):
+    """grid.py:786-808: unit vector (x north, y east, z down) from inclination / declination in degrees."""
+    d2r = np.pi / 180.0
+    return [np.cos(d2r * inc) * np.cos(d2r * dec), np.cos(d2r * inc) * np.sin(d2r * dec), np.sin(d2r * inc)]
+
+
+def fft_wavenumbers(dx, dy, shape):
+    """_fftfreqs (grid.py:738-744): kx varies along axis 0 with spacing dx, ky along axis 1 with dy."""
+    fx = 2.0 * np.pi * np.fft.fftfreq(shape[0], dx)
+    fy = 2.0 * np.pi * np.fft.fftfreq(shape[1], dy)
+    return np.meshgrid(fy, fx)[::-1]
+
+
+def upward_continuation_filter(shape, dx, dy, height):
+    """exp(-height |k|) of grid.py:538-545."""
+    kx, ky = fft_wavenumbers(dx, dy, shape)
+    return np.exp(-height * np.hypot(kx, ky))
+
+
+def reduce_to_pole_filter(shape, dx, dy, inc, dec, sinc=None, sdec=None):
+    """The RTP operator of grid.py:462-488, literally (including sqrt(|k|) in the imaginary part and the
+    zeroed DC term)."""
+    fx, fy, fz = dircos(inc, dec)
+    if sinc is None or sdec is None:
+        mx, my, mz = fx, fy, fz
+    else:
+        mx, my, mz = dircos(sinc, sdec)
+    kx, ky = fft_wavenumbers(dx, dy, shape)
+    kz = np.hypot(kx, ky)
+    a1 = mz * fz - mx * fx
+    a2 = mz * fz - my * fy
+    a3 = -my * fx - mx * fy
+    b1 = mx * fz + mz * fx
+    b2 = my * fz + mz * fy
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rtp = kz / (a1 * kx ** 2 + a2 * ky ** 2 + a3 * kx * ky + 1j * np.sqrt(kz) * (b1 * kx + b2 * ky))
+    rtp[0, 0] = 0
+    return rtp
+
+
+def fft_filter(data, filt):
+    """real(ifft2(filt * fft2(data))) (grid.py:489-490, :545-546)."""
+    return np.real(np.fft.ifft2(filt * np.fft.fft2(data)))
+
+
+# --------------------------------------------------------------------------
 # synthetic fractal grid  (SURVEY.md section 8d; not in the reference)
 # --------------------------------------------------------------------------
 def synthetic_grid(ny, nx, seed=20261019, beta=3.0, zt=1.0, dz=20.0, std=100.0):

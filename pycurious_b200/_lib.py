@@ -67,6 +67,10 @@ SIGNATURES = {
     "cb_fit_batch": (_I, [_VP, _I, _VP, _I64, C.POINTER(FitOptions), _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "cb_fit_batch_rows": (_I, [_VP, _I, _VP, _I64, C.POINTER(FitOptions), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "cb_perturb_spectra": (_I, [_VP, _VP, _I64, _I, _I64, C.c_uint64, C.c_uint64, _VP, _VP]),
+    "cb_fft_plan_create": (_I, [_I, C.POINTER(_VP)]),
+    "cb_fft_plan_destroy": (_I, [_VP]),
+    "cb_fft2_filter_workspace_bytes": (_I64, [_I64, _I64]),
+    "cb_fft2_filter": (_I, [_VP, _VP, _VP, _I64, _I64, _I64, _VP, _VP, _I64, _VP, _I64, _VP]),
     "cb_tanaka_batch": (_I, [_VP, _I, _VP, _VP, _I64, _D, _D, _D, _D, _VP, _VP]),
     "cb_mh_batch": (_I, [_VP, _I, _VP, _I64, C.POINTER(MhOptions), _VP, _VP, _VP, _VP]),
     "cb_radon_plan_create": (_I, [_I, _I, _VP, _VP, C.POINTER(_VP)]),

@@ -265,6 +265,34 @@ def spectrum_plan(nw, dx, taper_vec):
     return plan
 
 
+class FftPlan:
+    """1-D transform plan of cb_fft2_filter (one per line length and device)."""
+
+    def __init__(self, n):
+        _lib.require_cuda()
+        lib = _lib.load()
+        handle = C.c_void_p()
+        _lib.check(lib.cb_fft_plan_create(int(n), C.byref(handle)))
+        self.handle = handle
+        self.n = int(n)
+        self._finalizer = weakref.finalize(self, lib.cb_fft_plan_destroy, handle)
+
+
+_fft_plan_cache = {}
+
+
+def fft_plan(n):
+    torch = _lib.require_cuda()
+    key = (int(n), torch.cuda.current_device())
+    plan = _fft_plan_cache.get(key)
+    if plan is None:
+        if len(_fft_plan_cache) > 32:
+            _fft_plan_cache.clear()
+        plan = FftPlan(n)
+        _fft_plan_cache[key] = plan
+    return plan
+
+
 # ----------------------------------------------------------------------------
 # Radon ray end points  (src/radon.pyx:30-96)
 # ----------------------------------------------------------------------------

@@ -192,12 +192,45 @@ class CurieGrid(object):
         torch.cuda.current_stream().synchronize()     # tv is host memory read by an async copy
         return kbins, S, dtheta
 
-    def reduce_to_pole(self, *args, **kwargs):
-        raise NotImplementedError("reduce_to_pole is outside the accelerated per-window path (SURVEY.md 8f); "
-                                  "apply it with the reference and pass the result as the grid")
+    # ------------------------------------------------------------------ FFT-domain filters (grid.py:405-546)
+    def _fft_filter_device(self, data, filt):
+        """real(ifft2(filt * fft2(data))) on the device (cb_fft2_filter); `filt` is the host-built operator."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        ny, nx = data.shape
+        px, py = _plans.fft_plan(nx), _plans.fft_plan(ny)
+        d_t = torch.from_numpy(data).cuda()
+        f_t = torch.from_numpy(np.ascontiguousarray(filt, dtype=np.complex128).view(np.float64)).cuda()
+        out = torch.empty((ny, nx), dtype=torch.float64, device="cuda")
+        ws = torch.empty(int(lib.cb_fft2_filter_workspace_bytes(ny, nx)), dtype=torch.uint8, device="cuda")
+        _lib.check(lib.cb_fft2_filter(px.handle, py.handle, d_t.data_ptr(), ny, nx, nx, f_t.data_ptr(), out.data_ptr(), nx,
+                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch)))
+        return out.cpu().numpy()
 
-    def upward_continuation(self, *args, **kwargs):
-        raise NotImplementedError("upward_continuation is outside the accelerated per-window path (SURVEY.md 8f)")
+    def reduce_to_pole(self, data, inc, dec, sinc=None, sdec=None):
+        """Reduce total-field anomaly data to the pole (grid.py:405-490): the Blakely (1996) operator is built
+        on the host with the reference's expressions -- including its sqrt(|k|) in the imaginary part and the
+        zeroed DC term -- and applied in the Fourier domain on the device."""
+        data = np.asarray(data)
+        nr, nc = data.shape
+        if nr != nc:
+            warnings.warn("subgrid is not square {}".format((nr, nc)), RuntimeWarning)
+        field = np.asarray(ang2vec(1.0, inc, dec), dtype=np.float64)
+        magn = field if (sinc is None or sdec is None) else np.asarray(ang2vec(1.0, sinc, sdec), dtype=np.float64)
+        rtp = _rtp_operator(_fftfreqs(self.dx, self.dy, data.shape), field, magn)
+        return self._fft_filter_device(data, rtp)
+
+    def upward_continuation(self, data, height):
+        """Upward continuation F{h_up} = F{h} exp(-height |k|) (grid.py:492-546), FFTs on the device."""
+        data = np.asarray(data)
+        nr, nc = data.shape
+        if nr != nc:
+            warnings.warn("subgrid is not square {}".format((nr, nc)), RuntimeWarning)
+        if height <= 0:
+            warnings.warn("Using 'height' <= 0 means downward continuation, " + "which is known to be unstable.")
+        kx, ky = _fftfreqs(self.dx, self.dy, (nr, nc))
+        return self._fft_filter_device(data, np.exp(-height * np.hypot(kx, ky)))
 
     # ------------------------------------------------------------------ batched extensions
     def radial_spectrum_batch(self, window, xc_list, yc_list, *, taper=np.hanning, power=2.0, detrend=False,
@@ -295,6 +328,39 @@ def tanaka1999(k, lnPhi, sigma_lnPhi, kmin_range=(0.05, 0.2), kmax_range=(0.05, 
     lower = _two_band_line(Xc, np.log(np.exp(lnPhi[cen]) / (Xc * 2 * np.pi)),
                            np.log(np.exp(var[cen]) / (Xc * 2 * np.pi)))
     return upper, lower
+
+
+def _fftfreqs(dx, dy, shape):
+    """Wave numbers in the x and y directions as two 2D arrays (grid.py:738-744)."""
+    fx = 2.0 * np.pi * np.fft.fftfreq(shape[0], dx)
+    fy = 2.0 * np.pi * np.fft.fftfreq(shape[1], dy)
+    return np.meshgrid(fy, fx)[::-1]
+
+
+def _rtp_operator(k, f, m):
+    """Blakely's (1996) reduction-to-the-pole operator |k| / (quadratic form + i sqrt(|k|) linear form) on
+    the wavenumber planes k = (kx, ky) for unit vectors f (geomagnetic field) and m (total magnetisation).
+    The square root on |k| in the imaginary part and the zeroed DC term are the reference's (grid.py:477-488)."""
+    kx, ky = k
+    kabs = np.hypot(kx, ky)
+    quad = (m[2] * f[2] - m[0] * f[0]) * kx ** 2 + (m[2] * f[2] - m[1] * f[1]) * ky ** 2 \
+        + (-m[1] * f[0] - m[0] * f[1]) * kx * ky
+    lin = (m[0] * f[2] + m[2] * f[0]) * kx + (m[1] * f[2] + m[2] * f[1]) * ky
+    with np.errstate(divide="ignore", invalid="ignore"):
+        op = kabs / (quad + 1j * np.sqrt(kabs) * lin)
+    op[0, 0] = 0
+    return op
+
+
+def dircos(inc, dec):
+    """Unit vector (x north, y east, z down) from inclination and declination in degrees (grid.py:786-808)."""
+    d2r = np.pi / 180.0
+    return [np.cos(d2r * inc) * np.cos(d2r * dec), np.cos(d2r * inc) * np.sin(d2r * dec), np.sin(d2r * inc)]
+
+
+def ang2vec(intensity, inc, dec):
+    """Intensity, inclination, declination -> 3-component vector (grid.py:747-783)."""
+    return np.transpose([intensity * i for i in dircos(inc, dec)])
 
 
 def ComputeTanaka(Ztr, dZtr, Zor, dZor):

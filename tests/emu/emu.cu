@@ -12,6 +12,7 @@
 #include "fit_body.cuh"
 #include "mh_body.cuh"
 #include "tanaka_body.cuh"
+#include "fft2d_body.cuh"
 #include "radon_body.cuh"
 
 void cb_set_error(const char *fmt, ...) { (void)fmt; }
@@ -264,6 +265,48 @@ void emu_tanaka(const double *k, int nk, const double *lnphi, const double *sigm
     P.k = k; P.nk = nk; P.lnphi = lnphi; P.sigma = sigma; P.nwin = nwin;
     P.top_lo = a0; P.top_hi = a1; P.cen_lo = b0; P.cen_hi = b1; P.out = out; P.warps_per_block = 2;
     emu_launch((int)((nwin + 1) / 2), 64, 64, [&](const HostCtx &cx) { tanaka_body(cx, P); });
+}
+
+// out = real(ifft2(filter * fft2(data))) through line_fft_body, the four passes of cb_fft2_filter
+int emu_fft2_filter(const double *data, int64_t ny, int64_t nx, const double *filter_re_im, double *out) {
+    struct Plan { FftPlan fft; std::vector<double2> tw, chirp, filt; std::vector<int32_t> slot; int bl, line_slots; };
+    auto make = [](int n, Plan &p) {
+        if (cbplan::build_fft_plan(n, p.fft, p.tw)) { p.bl = 0; p.slot = cbplan::digit_reversed_slots(p.fft); }
+        else {
+            int M = cbplan::bluestein_length(n);
+            if (!M || !cbplan::build_fft_plan(M, p.fft, p.tw)) return false;
+            p.bl = 1;
+            cbplan::build_bluestein_tables(n, p.fft, p.chirp, p.filt);
+        }
+        p.line_slots = (fft_line_slots(p.fft.n) + 1) & ~1;
+        if (p.bl) p.filt.resize(p.line_slots, cplx(0.0, 0.0));
+        return true;
+    };
+    Plan px, py;
+    if (!make((int)nx, px) || !make((int)ny, py)) return -1;
+    std::vector<double2> A(ny * nx), B(ny * nx);
+    auto run = [&](const Plan &pl, LineFftParams P) {
+        P.bluestein = pl.bl; P.fft = pl.fft; P.tw = pl.tw.data(); P.chirp = pl.chirp.data(); P.filt = pl.filt.data();
+        P.slot = pl.slot.data(); P.line_slots = pl.line_slots;
+        emu_launch(2, 64, (size_t)2 * pl.line_slots * 16, [&](const HostCtx &cx) { line_fft_body(cx, P); });
+    };
+    LineFftParams P;
+    memset(&P, 0, sizeof(P));
+    P.in_real = data; P.in_es = 1; P.in_ls = nx; P.out_cplx = A.data(); P.out_es = 1; P.out_ls = nx; P.nlines = ny; P.n = (int)nx; P.scale = 1.0;
+    run(px, P);
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = A.data(); P.in_es = nx; P.in_ls = 1; P.out_cplx = B.data(); P.out_es = nx; P.out_ls = 1; P.nlines = nx; P.n = (int)ny; P.scale = 1.0;
+    P.mul = reinterpret_cast<const double2 *>(filter_re_im);
+    run(py, P);
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = B.data(); P.in_es = nx; P.in_ls = 1; P.out_cplx = A.data(); P.out_es = nx; P.out_ls = 1; P.nlines = nx; P.n = (int)ny;
+    P.inverse = 1; P.scale = 1.0 / (double)ny;
+    run(py, P);
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = A.data(); P.in_es = 1; P.in_ls = nx; P.out_real = out; P.out_es = 1; P.out_ls = nx; P.nlines = ny; P.n = (int)nx;
+    P.inverse = 1; P.scale = 1.0 / (double)nx;
+    run(px, P);
+    return 0;
 }
 
 // fit with per-row prior means (the inner loop of CurieOptimise.sensitivity)

@@ -406,6 +406,20 @@ def test_radon_bodies_bit_exact(emu, oracle, mag):
         np.testing.assert_allclose(S[0], g["n%d_az_S" % nw], rtol=1e-11)
 
 
+@pytest.mark.parametrize("ny,nx", [(64, 64), (101, 101), (30, 45), (75, 64)])
+def test_fft2_filter_body_matches_reference_filters(emu, oracle, mag, ny, nx):
+    """line_fft_body x 4 = real(ifft2(filter * fft2(data))): upward continuation and reduction to the pole
+    (grid.py:405-546) on square / rectangular, smooth / Bluestein shapes."""
+    d = np.ascontiguousarray(mag[0][5:5 + ny, 9:9 + nx])
+    out = np.empty_like(d)
+    for filt in (oracle.upward_continuation_filter(d.shape, 1000.0, 1000.0, 800.0),
+                 oracle.reduce_to_pole_filter(d.shape, 1000.0, 1000.0, -60.0, 12.0, 40.0, 3.0)):
+        f = np.ascontiguousarray(filt.astype(np.complex128))
+        assert emu.emu_fft2_filter(P(d), C.c_int64(ny), C.c_int64(nx), P(f.view(np.float64)), P(out)) == 0
+        ref = oracle.fft_filter(d, filt)
+        np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+
+
 def test_tanaka_body_matches_reference_formulas(emu, oracle):
     """tanaka1999 + ComputeTanaka (grid.py:603-699) batched, one window per warp, against the oracle and the
     reference's golden value."""

@@ -364,6 +364,32 @@ def test_fit_custom_process_subgrid_and_single(grid, oracle, mag):
     np.testing.assert_allclose(x_dev, xp, rtol=2e-5)
 
 
+def test_fft_domain_filters_match_reference(grid, oracle, mag):
+    """CurieGrid.upward_continuation / reduce_to_pole (grid.py:405-546): FFTs on the device, golden outputs of
+    the reference itself; also as a `process_subgrid` callback of optimise (optimise.py:282-294)."""
+    g = load_golden("filters.npz")
+    d, _ = mag
+    for name in g["names"]:
+        j0, i0, n, st = (int(v) for v in g[str(name) + "_meta"])
+        win = d[j0:j0 + n, i0:i0 + n]
+        for tag, fn in (("up500", lambda w: grid.upward_continuation(w, 500.0)),
+                        ("up5000", lambda w: grid.upward_continuation(w, 5000.0)),
+                        ("rtp_induced", lambda w: grid.reduce_to_pole(w, -60.0, 12.0)),
+                        ("rtp_remanent", lambda w: grid.reduce_to_pole(w, 35.0, -5.0, sinc=50.0, sdec=20.0))):
+            ref = g["%s_%s" % (name, tag)]
+            out = fn(win)
+            assert out.shape == win.shape
+            np.testing.assert_allclose(out[::st, ::st], ref, rtol=0, atol=1e-11 * np.abs(ref).max(), err_msg=str((name, tag)))
+    # rectangular input warns like the reference and still works
+    with pytest.warns(RuntimeWarning):
+        out = grid.upward_continuation(d[:64, :96], 1000.0)
+    ref = oracle.fft_filter(d[:64, :96], oracle.upward_continuation_filter((64, 96), grid.dx, grid.dy, 1000.0))
+    np.testing.assert_allclose(out, ref, rtol=0, atol=1e-11 * np.abs(ref).max())
+    # as a process_subgrid callback
+    x = grid.optimise(150e3, 152.5e3, 140.5e3, process_subgrid=lambda w: grid.upward_continuation(w, 2000.0))
+    assert x.shape == (4,) and np.all(np.isfinite(x))
+
+
 def test_tanaka_batch_matches_reference(pc, grid, oracle, mag):
     """CurieGrid.tanaka_batch = radial_spectrum(power=0.5) -> tanaka1999 -> ComputeTanaka per centroid."""
     d, ext = mag

@@ -167,3 +167,18 @@ def test_tanaka_matches_reference(oracle, mag):
     (Ztr, btr, dZtr), (Zor, bor, dZor) = oracle.tanaka1999(k, phi, sig, (0.005, 0.03), (0.03, 0.7))
     Zb, eZb = oracle.compute_tanaka(Ztr, dZtr, Zor, dZor)
     np.testing.assert_allclose([Ztr, btr, dZtr, Zor, bor, dZor, Zb, eZb], g["tanaka"], rtol=1e-8)   # ill-conditioned normal equations; grouping differs
+
+
+def test_fft_filters_match_reference(oracle):
+    """upward_continuation / reduce_to_pole restatements against the reference's own outputs."""
+    g = load_golden("filters.npz")
+    d = load_golden("mag_grid.npz")["d"]
+    for name in g["names"]:
+        j0, i0, n, st = (int(v) for v in g[str(name) + "_meta"])
+        win = d[j0:j0 + n, i0:i0 + n]
+        for tag, filt in (("up500", oracle.upward_continuation_filter(win.shape, 1000.0, 1000.0, 500.0)),
+                          ("up5000", oracle.upward_continuation_filter(win.shape, 1000.0, 1000.0, 5000.0)),
+                          ("rtp_induced", oracle.reduce_to_pole_filter(win.shape, 1000.0, 1000.0, -60.0, 12.0)),
+                          ("rtp_remanent", oracle.reduce_to_pole_filter(win.shape, 1000.0, 1000.0, 35.0, -5.0, 50.0, 20.0))):
+            ref = g["%s_%s" % (name, tag)]
+            np.testing.assert_allclose(oracle.fft_filter(win, filt)[::st, ::st], ref, rtol=0, atol=1e-12 * np.abs(ref).max())
