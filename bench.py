@@ -368,7 +368,8 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, nwin, world),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": (4 if shared else 3) * args.steps,   # rowspec + colspec (or spectrum) + ktable + fit "roofline": roofline, "stages": stages,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": (4 if shared else 3) * args.steps,
+                "roofline": roofline, "stages": stages,
                 "spectrum_path": "shared_rows" if shared else "direct",
                 "plan": {"fft_len": info.fft_len, "bluestein": info.bluestein, "radix": list(info.radix[:info.npass]),
                          "teams": info.teams, "ctas": info.grid_max, "smem_bytes": info.smem_bytes},
