@@ -14,14 +14,14 @@ if [ "$2" = "full" ]; then
   python bench.py --grid 1024 --steps 2 --warmup 1 --no-cpu-baseline > $OUT/plain_$TAG.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv \
       python bench.py --grid 1024 --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1
-  ncu --set full --clock-control none --import-source on -c 3 -f -o $OUT/prof_$TAG \
+  ncu --set full --clock-control none --import-source on -k regex:'rowspec_kernel|colspec_kernel|spectrum_kernel|fit_kernel|mh_kernel' -c 4 -f -o $OUT/prof_$TAG \
       python bench.py --grid 1024 --steps 1 --warmup 0 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
 fi
 ls -la $OUT | tail -20
 if [ "$2" = "big" ]; then
   # full-size (152,100 windows) captures of the two kernels: DRAM traffic and pipe utilisation per launch
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline --mcmc-steps 0 > $OUT/plain_big_$TAG.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:'spec_kernel|spectrum_kernel|fit_kernel' -s 3 -c 3 -f -o $OUT/prof_big_$TAG \
+  ncu --set full --clock-control none --import-source on -k regex:'rowspec_kernel|colspec_kernel|spectrum_kernel|fit_kernel' -s 3 -c 3 -f -o $OUT/prof_big_$TAG \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline --mcmc-steps 0 > $OUT/ncu_big_$TAG.log 2>&1
   ls -la $OUT | tail -5
 fi
