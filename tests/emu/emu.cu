@@ -178,6 +178,13 @@ int emu_spectrum_shared(int nw, int nbins, const double *taper_r, const double *
     P.grid = grid; P.ld = ld; P.iy0 = iy0; P.ix0 = ix0; P.nwin = nwin;
     P.detrend = detrend; P.power = power; P.phi = phi; P.sigma = sigma;
     P.group_of_win = gof.data(); P.group_ix0 = gix.data(); P.ngroups = (int)gix.size();
+    // processing order as the host builds it: by (group, iy0) -- here reversed as well, to exercise the indirection
+    std::vector<int32_t> order(nwin);
+    for (int64_t w = 0; w < nwin; ++w) order[w] = (int32_t)w;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return gof[a] != gof[b] ? gof[a] > gof[b] : iy0[a] > iy0[b];
+    });
+    P.win_order = order.data();
     P.row_lo = row_lo; P.nrows_valid = row_hi - row_lo; P.nrows = (P.nrows_valid + 1) & ~1;
     std::vector<double2> rt((size_t)P.ngroups * hp.nvh * P.nrows);
     std::vector<double> lh((size_t)nblocks * 2 * hp.lh_stride);

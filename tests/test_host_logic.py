@@ -235,3 +235,29 @@ def test_bench_contract_keys():
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "stages",
                 "cpu_baseline", "mcmc"):
         assert '"%s"' % key in code, key
+
+
+def test_lattice_fast_path_equals_generic_rule(pc):
+    """window_origins: the O(n) path for create_centroid_list lattices against the per-centroid argmin rule,
+    and the fallback for lists that only look like lattices."""
+    from pycurious_b200 import _plans
+    n = 700
+    d = np.zeros((n, n))
+    G = pc.CurieGrid(d, 0.0, (n - 1) * 1000.0, 0.0, (n - 1) * 1000.0)
+    xc, yc = G.create_centroid_list(100e3, 7300.0, 9100.0)          # spacing not a multiple of dx: ties / rounding
+    assert xc.size >= 4096
+    assert _plans._lattice_shape(xc, yc) is not None
+    iy0, ix0, nw = _plans.window_origins(G, 100e3, xc, yc)
+    half = nw // 2
+    assert np.array_equal(ix0, _plans.nearest_node(G.xcoords, xc) - half)
+    assert np.array_equal(iy0, _plans.nearest_node(G.ycoords, yc) - half)
+    xs = xc.copy()
+    xs[-1] += 1000.0                                                  # breaks the lattice in the last element only
+    assert _plans._lattice_shape(xs, yc) is None
+    iy1, ix1, _ = _plans.window_origins(G, 100e3, xs, yc)
+    assert np.array_equal(ix1[:-1], ix0[:-1]) and ix1[-1] == ix0[-1] + 1
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(xc.size)
+    assert _plans._lattice_shape(xc[perm], yc[perm]) is None
+    iy2, ix2, _ = _plans.window_origins(G, 100e3, xc[perm], yc[perm])
+    assert np.array_equal(ix2, ix0[perm]) and np.array_equal(iy2, iy0[perm])
