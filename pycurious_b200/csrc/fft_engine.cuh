@@ -371,8 +371,47 @@ struct StaticFft {
     static constexpr int HALF = (R0 + 1) / 2;            // inputs / outputs per butterfly that can be live
     static constexpr int FUSED_SPAN = HALF * (N / R0);   // the engine serves windows with n <= FUSED_SPAN
 
+    static constexpr int NIT = (N / R0 + CB_WARP - 1) / CB_WARP;    // first-pass butterflies per lane
+    // a second line's inputs fit in registers beside the transform only while they are <= 8 complex values
+    static constexpr bool PREFETCH = FUSED_SPAN > 0 && NIT * HALF <= 8;
+    // line index of input (it, t) of lane `lane` in the first pass
+    CB_HD static int input_index(int it, int t, int lane) { return it * CB_WARP + lane + t * (N / R0); }
+
+    // The live inputs of this lane's first-pass butterflies, fetched with `raw(x)` (x < FUSED_SPAN).  Split
+    // from the pass itself so that a caller can request the NEXT line's inputs before transforming the
+    // current one (software prefetch in registers: the loads are in flight during a whole line's passes).
+    template <class Raw> CB_HD static void gather(double2 (&in)[NIT][HALF], int lane, Raw raw) {
+        constexpr int NB = N / R0;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it)
+#pragma unroll
+            for (int t = 0; t < HALF; ++t)
+                in[it][t] = (NB % CB_WARP == 0 || it * CB_WARP + lane < NB) ? raw(input_index(it, t, lane)) : cplx(0.0, 0.0);
+    }
+
+    CB_HD static void first_pass_pre(double2 *buf, const double2 *tw, int lane, const double2 (&in)[NIT][HALF]) {
+        constexpr int R = R0, SUB = N / R0, NB = N / R;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int j = it * CB_WARP + lane;
+            if (NB % CB_WARP != 0 && j >= NB) break;
+            double2 v[R];
+#pragma unroll
+            for (int t = 0; t < R; ++t) v[t] = t < HALF ? in[it][t] : cplx(0.0, 0.0);
+            if (R == 8) dft8_half_in(v);
+            else Dft<R>::run(v);
+            double2 w[R];
+            tw_powers<R>(tw[j], w);
+#pragma unroll
+            for (int s = 1; s < R; ++s) v[s] = cmul(v[s], w[s]);
+            const int pad0 = CB_PAD(j);
+#pragma unroll
+            for (int s = 0; s < R; ++s) buf[slot<SUB>(j, pad0, s)] = v[s];
+        }
+    }
+
     template <class Loader> CB_HD static void first_pass(double2 *buf, const double2 *tw, int lane, Loader ld) {
-        constexpr int R = R0, SUB = N / R0, NB = N / R, NIT = (NB + CB_WARP - 1) / CB_WARP;
+        constexpr int R = R0, SUB = N / R0, NB = N / R;
         // every input of every butterfly of this lane is requested before the first one is used: the
         // loads come from L2 / HBM (grid rows, shared row spectra) and their latency is paid once per line
         double2 in[NIT][HALF];
@@ -439,6 +478,22 @@ struct StaticFft {
         last_pass(buf, tw, lane, sk);
     }
 
+    // convolve_io with the first-pass inputs already in registers (see gather)
+    template <class Ctx, class Sink>
+    CB_BODY static void convolve_pre(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, int lane,
+                                     const double2 (&in)[NIT][HALF], Sink sk) {
+        cx.sync_warp();
+        first_pass_pre(buf, tw, lane, in);
+        cx.sync_warp();
+        if (NPASS > 2) { pass<1, false>(buf, tw, lane); cx.sync_warp(); }
+        if (NPASS > 3) { pass<2, false>(buf, tw, lane); cx.sync_warp(); }
+        mid(buf, filt, lane);
+        cx.sync_warp();
+        if (NPASS > 3) { pass<2, true>(buf, tw, lane); cx.sync_warp(); }
+        if (NPASS > 2) { pass<1, true>(buf, tw, lane); cx.sync_warp(); }
+        last_pass(buf, tw, lane, sk);
+    }
+
     template <class Ctx>
     CB_BODY static void convolve(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, const FftPlan &,
                                  int lane) {
@@ -462,6 +517,7 @@ struct StaticFft {
 
 struct GenericFft {
     static constexpr int FUSED_SPAN = 0;                  // no fused-I/O path
+    static constexpr bool PREFETCH = false;
     static bool matches(const FftPlan &) { return true; }
     template <class Ctx>
     CB_BODY static void convolve(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, const FftPlan &pl,

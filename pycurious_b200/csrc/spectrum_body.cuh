@@ -188,7 +188,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
             const double t1 = (P.taper_r && has1) ? Ctx::ldg(P.taper_r + y1) : 1.0;
             const double pl0 = c0 + cy1 * ((double)y0 - ctr), pl1 = c0 + cy1 * ((double)y1 - ctr);
             bool fused = false;
-            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+            if constexpr (Engine::PREFETCH) if (P.bluestein) {
                 fused = true;
                 // the first FFT pass pulls its inputs straight from the grid (coalesced: lane j reads
                 // x = j + t*SUB), the last one leaves the n live outputs in the line
@@ -265,7 +265,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
             const double2 *col = Gt + (int64_t)v * npad;
             double *out = Lh + (int64_t)v * n;
             bool fused = false;
-            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+            if constexpr (Engine::PREFETCH) if (P.bluestein) {
                 fused = true;
                 auto ld = [&](int y) -> double2 {
                     if (y >= n) return cplx(0.0, 0.0);
@@ -360,7 +360,7 @@ CB_BODY void rowspec_body(const Ctx &cx, const SpectrumParams &P) {
         const double *r0 = P.grid + (int64_t)(P.row_lo + (has0 ? 2 * p : 0)) * P.ld + Ctx::ldg(P.group_ix0 + g);
         const double *r1 = has1 ? r0 + P.ld : r0;
         bool fused = false;
-        if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+        if constexpr (Engine::PREFETCH) if (P.bluestein) {
             fused = true;
             auto ld = [&](int x) -> double2 {
                 if (x >= n) return cplx(0.0, 0.0);
@@ -434,6 +434,53 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
         if (P.detrend)
             window_plane(cx, P, P.grid + (int64_t)iy0 * P.ld + P.ix0[w], s_red, warp, lane, nwarps, c0, cx1, cy1);
         const double2 *rt_w = P.rt + ((int64_t)g * nvh) * P.nrows + (iy0 - P.row_lo);
+        if constexpr (Engine::PREFETCH) if (P.bluestein) {
+            // Static engines: the raw row-spectrum slice of the NEXT column is requested before the current
+            // column is transformed, so its L2 / HBM latency hides behind a whole column's passes (ncu r01s:
+            // 18 % of this kernel's stall samples sat on the first use of these loads).
+            double2 nxt[Engine::NIT][Engine::HALF];
+            auto raw_of = [&](const double2 *c) {
+                return [=](int y) -> double2 { return y < n ? Ctx::ldcg(c + y) : cplx(0.0, 0.0); };
+            };
+            if (warp < nvh) Engine::gather(nxt, lane, raw_of(rt_w + (int64_t)warp * P.nrows));
+            for (int v = warp; v < nvh; v += nwarps) {
+                double2 cur[Engine::NIT][Engine::HALF];
+#pragma unroll
+                for (int it = 0; it < Engine::NIT; ++it)
+#pragma unroll
+                    for (int t = 0; t < Engine::HALF; ++t) cur[it][t] = nxt[it][t];
+                if (v + nwarps < nvh) Engine::gather(nxt, lane, raw_of(rt_w + (int64_t)(v + nwarps) * P.nrows));
+                double2 t0 = cplx(0.0, 0.0), t1 = cplx(0.0, 0.0);
+                if (P.detrend) {
+                    t0 = Ctx::ldg(P.plane_t0 + v);
+                    t1 = cscale(Ctx::ldg(P.plane_t1 + v), cx1);
+                }
+#pragma unroll
+                for (int it = 0; it < Engine::NIT; ++it)
+#pragma unroll
+                    for (int t = 0; t < Engine::HALF; ++t) {
+                        const int y = Engine::input_index(it, t, lane);
+                        double2 z = cur[it][t];
+                        if (y < n) {
+                            if (P.detrend) {
+                                const double a = c0 + cy1 * ((double)y - ctr);
+                                z = cplx(z.x - fma(a, t0.x, t1.x), z.y - fma(a, t0.y, t1.y));
+                            }
+                            z = cmul(z, s_rw[y]);
+                        }
+                        cur[it][t] = z;
+                    }
+                double *out = Lh + (int64_t)v * n;
+                const int span = Ctx::ldg(P.col_span + v);
+                const int lo_end = (span & 0xffff) == 0xffff ? -1 : (span & 0xffff), hi_start = (int)((unsigned)span >> 16);
+                auto sk = [&](int u, double2 z) {
+                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                };
+                Engine::convolve_pre(cx, buf, s_tw, s_filt, lane, cur, sk);
+                cx.sync_warp();
+            }
+        }
+        if (!(Engine::PREFETCH && P.bluestein))
         for (int v = warp; v < nvh; v += nwarps) {
             const double2 *col = rt_w + (int64_t)v * P.nrows;
             double *out = Lh + (int64_t)v * n;
@@ -453,7 +500,7 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
                 return P.bluestein ? cmul(z, rw) : cscale(z, rw.x);
             };
             bool fused = false;
-            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
+            if constexpr (Engine::PREFETCH) if (P.bluestein) {
                 fused = true;
                 auto ld = [&](int y) -> double2 { return y < n ? element(y) : cplx(0.0, 0.0); };
                 const int span = Ctx::ldg(P.col_span + v);
