@@ -103,42 +103,71 @@ CB_BODY void window_plane(const Ctx &cx, const SpectrumParams &P, const double *
 }
 
 // Phase C: radial bins (grid.py:281-286), mean / population std of the members of each bin, one
-// warp per bin over the folded CSR.
+// warp per bin over the folded CSR.  The members are gathered through two dependent L2 loads (CSR
+// index, then the log-power), so the walk is software pipelined over 128-member chunks: the indices of
+// the NEXT chunk -- of this bin or of the warp's next bin -- are requested while the values of the
+// current one are in flight.  Sum and sum of squares are taken about a pivot member (the first one):
+// the population variance is shift invariant and the pivot removes the mean^2 cancellation.
 template <class Ctx>
 CB_BODY void bin_phase(const Ctx &cx, const SpectrumParams &P, const double *Lh, int64_t w, int warp, int lane,
                        int nwarps) {
-    for (int b = warp; b < P.nbins; b += nwarps) {
-        const int lo = Ctx::ldg(P.bin_ptr + b), hi = Ctx::ldg(P.bin_ptr + b + 1);
-        // one pass over the members: sum and sum of squares about a pivot member (the population
-        // variance is shift invariant; the pivot removes the mean^2 cancellation), 4 gathers in flight
-        double pivot = lo < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + lo)) : 0.0;
-        if (!isfinite(pivot)) pivot = 0.0;          // log(0) = -inf members: plain sums, numpy's -inf / nan result
-        double s = 0.0, q = 0.0;
-        for (int eb = lo; eb < hi; eb += 4 * CB_WARP) {
-            double v[4];
+    constexpr int CHUNK = 4 * CB_WARP;
+    int b = warp;
+    if (b >= P.nbins) return;
+    int lo = Ctx::ldg(P.bin_ptr + b), hi = Ctx::ldg(P.bin_ptr + b + 1), eb = lo;
+    int idx[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int e = eb + j * CB_WARP + lane;
-                v[j] = e < hi ? Ctx::ldcg(Lh + Ctx::ldg(P.bin_idx + e)) : pivot;
-            }
+    for (int j = 0; j < 4; ++j) {
+        const int e = eb + j * CB_WARP + lane;
+        idx[j] = e < hi ? Ctx::ldg(P.bin_idx + e) : -1;
+    }
+    double s = 0.0, q = 0.0, pivot = 0.0;
+    while (b < P.nbins) {
+        double v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double d = v[j] - pivot;      // padding lanes contribute exactly 0
-                s += d;
-                q = fma(d, d, q);
+        for (int j = 0; j < 4; ++j) v[j] = idx[j] >= 0 ? Ctx::ldcg(Lh + idx[j]) : 0.0;
+        const bool head = eb == lo;
+        const bool last = eb + CHUNK >= hi;
+        int nb = b, nlo = lo, nhi = hi, neb = eb + CHUNK;
+        if (last) {
+            nb = b + nwarps;
+            nlo = nhi = 0;
+            if (nb < P.nbins) { nlo = Ctx::ldg(P.bin_ptr + nb); nhi = Ctx::ldg(P.bin_ptr + nb + 1); }
+            neb = nlo;
+        }
+        int nidx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = neb + j * CB_WARP + lane;
+            nidx[j] = e < nhi ? Ctx::ldg(P.bin_idx + e) : -1;
+        }
+        if (head) {
+            pivot = cx.shfl(v[0], 0);                // member `lo` (an empty bin has no pivot: 0)
+            if (!isfinite(pivot) || lo >= hi) pivot = 0.0;   // log(0) = -inf members: plain sums, numpy's -inf / nan result
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double d = idx[j] >= 0 ? v[j] - pivot : 0.0;
+            s += d;
+            q = fma(d, d, q);
+        }
+        if (last) {
+            s = cx.warp_sum(s);
+            q = cx.warp_sum(q);
+            const double cnt = (double)(hi - lo);
+            const double md = s / cnt;                  // mean - pivot
+            const double mean = pivot + md;
+            q -= s * md;                                // sum (x - mean)^2
+            if (q < 0.0) q = 0.0;                       // (a nan stays a nan)
+            if (lane == 0) {
+                P.phi[w * P.nbins + b] = P.power * mean;
+                P.sigma[w * P.nbins + b] = fabs(P.power) * sqrt(q / cnt);
             }
+            s = q = 0.0;
         }
-        s = cx.warp_sum(s);
-        q = cx.warp_sum(q);
-        const double cnt = (double)(hi - lo);
-        const double md = s / cnt;                  // mean - pivot
-        const double mean = pivot + md;
-        q -= s * md;                                // sum (x - mean)^2
-        if (q < 0.0) q = 0.0;                       // (a nan stays a nan)
-        if (lane == 0) {
-            P.phi[w * P.nbins + b] = P.power * mean;
-            P.sigma[w * P.nbins + b] = fabs(P.power) * sqrt(q / cnt);
-        }
+        b = nb; lo = nlo; hi = nhi; eb = neb;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = nidx[j];
     }
 }
 
