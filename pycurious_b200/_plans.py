@@ -81,6 +81,53 @@ def window_origins(g, window, xc, yc):
     return (iy - half).astype(np.int32), (ix - half).astype(np.int32), 2 * half + 1
 
 
+class Lattice:
+    """The centroid lattice xs x ys (x fastest) standing in for create_centroid_list's two raveled lists:
+    the batch entry points accept it in place of (xc_list, yc_list) and never expand it on the host."""
+
+    def __init__(self, xs, ys):
+        self.xs = np.atleast_1d(np.asarray(xs, dtype=np.float64))
+        self.ys = np.atleast_1d(np.asarray(ys, dtype=np.float64))
+
+    @property
+    def shape(self):
+        return self.ys.size, self.xs.size
+
+    def __len__(self):
+        return self.xs.size * self.ys.size
+
+
+def _first_offender(bad_x, bad_y):
+    """(row, col) of the first flagged centroid in the x-fastest order of create_centroid_list."""
+    if bad_y[0]:
+        return 0, 0
+    if bad_x.any():
+        return 0, int(np.flatnonzero(bad_x)[0])
+    return int(np.flatnonzero(bad_y)[0]), 0
+
+
+def lattice_origins(g, window, xs, ys):
+    """window_origins for the lattice xs x ys (x fastest) without forming the centroid lists: per-axis
+    top-left nodes (iyu[rows], ixu[cols]) and the window edge.  The window of centroid (r, c) starts at
+    (iyu[r], ixu[c]); validation is O(rows + cols), first offender and messages as in grid.py:131-153."""
+    xs = np.atleast_1d(np.asarray(xs, dtype=np.float64))
+    ys = np.atleast_1d(np.asarray(ys, dtype=np.float64))
+    if xs.size == 0 or ys.size == 0:
+        raise ValueError("empty centroid lattice")
+    bx, by = (xs < g.xmin) | (xs > g.xmax), (ys < g.ymin) | (ys > g.ymax)
+    if bx.any() or by.any():
+        r, c = _first_offender(bx, by)
+        raise ValueError("Point {} outside data range".format((xs[c], ys[r])))
+    _, half = window_nodes(window, g.dx)
+    ix, iy = nearest_node(g.xcoords, xs), nearest_node(g.ycoords, ys)
+    wx = (ix - half < 0) | (ix + half + 1 > g.nx)
+    wy = (iy - half < 0) | (iy + half + 1 > g.ny)
+    if wx.any() or wy.any():
+        r, c = _first_offender(wx, wy)
+        raise ValueError("Window size {} at centroid {} exceeds the data range".format(window, (xs[c], ys[r])))
+    return (iy - half).astype(np.int32), (ix - half).astype(np.int32), 2 * half + 1
+
+
 # ----------------------------------------------------------------------------
 # radial bins  (CurieGrid._taper_spectrum / _FFT_spectrum, grid.py:242-245, :277-286)
 # ----------------------------------------------------------------------------

@@ -110,6 +110,28 @@ class CurieGrid(object):
         iy0_t._cb_host, ix0_t._cb_host = iy0, ix0      # the spectrum plan groups windows by ix0 on the host
         return (iy0_t, ix0_t, n)
 
+    def _origins_lattice_device(self, window, xs, ys):
+        """_origins_device for the lattice xs x ys: only the per-axis nodes cross to the device, the
+        (rows*cols) origin arrays are expanded there."""
+        torch = _lib.require_cuda()
+        iyu, ixu, n = _plans.lattice_origins(self, window, xs, ys)
+        rows, cols = iyu.size, ixu.size
+        iy0_t = torch.from_numpy(iyu).cuda().repeat_interleave(cols)
+        ix0_t = torch.from_numpy(ixu).cuda().repeat(rows)
+        iy0_t._cb_host, ix0_t._cb_host = np.repeat(iyu, cols), np.tile(ixu, rows)
+        return (iy0_t, ix0_t, n)
+
+    def centroid_lattice(self, window, spacingX=None, spacingY=None):
+        """The two axes (xs, ys) of create_centroid_list's meshgrid (grid.py:159-195, before the ravel)."""
+        _, half = _plans.window_nodes(window, self.dx)
+        xs = self.xcoords[half:-half]
+        ys = self.ycoords[half:-half]
+        if spacingX is not None:
+            xs = np.arange(xs.min(), xs.max(), spacingX)
+        if spacingY is not None:
+            ys = np.arange(ys.min(), ys.max(), spacingY)
+        return xs, ys
+
     # ------------------------------------------------------------------ reference API
     def subgrid(self, window, xc, yc):
         """Window of the data around (xc, yc); a view, like the reference (grid.py:112-157)."""
@@ -119,14 +141,7 @@ class CurieGrid(object):
 
     def create_centroid_list(self, window, spacingX=None, spacingY=None):
         """Centroids whose windows fit in the grid (grid.py:159-197); x varies fastest."""
-        _, half = _plans.window_nodes(window, self.dx)
-        xs = self.xcoords[half:-half]
-        ys = self.ycoords[half:-half]
-        if spacingX is not None:
-            xs = np.arange(xs.min(), xs.max(), spacingX)
-        if spacingY is not None:
-            ys = np.arange(ys.min(), ys.max(), spacingY)
-        xq, yq = np.meshgrid(xs, ys)
+        xq, yq = np.meshgrid(*CurieGrid.centroid_lattice(self, window, spacingX, spacingY))
         return xq.ravel(), yq.ravel()
 
     def remove_trend_linear(self, data):

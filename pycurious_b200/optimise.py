@@ -120,11 +120,18 @@ class CurieOptimise(CurieGrid):
         torch = _lib.require_cuda()
         kwargs = dict(kwargs)
         power = kwargs.pop("power", 2.0)
+        lattice = xc_list if isinstance(xc_list, _plans.Lattice) else None
         if process_subgrid is None or self._is_detrend(process_subgrid):
-            iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+            if lattice is not None:
+                iy0, ix0, n = self._origins_lattice_device(window, lattice.xs, lattice.ys)
+            else:
+                iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
             plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
             phi, sig = plan.run(self.device_grid(), iy0, ix0, process_subgrid is not None, power)
             return plan.k, phi, sig
+        if lattice is not None:
+            xq, yq = np.meshgrid(lattice.xs, lattice.ys)
+            xc_list, yc_list = xq.ravel(), yq.ravel()
         wins = [np.asarray(process_subgrid(self.subgrid(window, xc, yc)), dtype=np.float64)
                 for xc, yc in zip(xc_list, yc_list)]
         n = wins[0].shape[0]
@@ -186,6 +193,57 @@ class CurieOptimise(CurieGrid):
                 return x.cpu().numpy(), {kk: v.cpu().numpy() for kk, v in diag.items()}
             return x, diag
         return res.cpu().numpy() if as_numpy else res
+
+    # ------------------------------------------------------------------ map assembly
+    def curie_depth_maps(self, window, spacingX=None, spacingY=None, *, beta=3.0, zt=1.0, dz=10.0, C=5.0,
+                         taper=np.hanning, process_subgrid=None, uncertainty=None, nsim=100, burnin=1000,
+                         x_scale=None, seed=None, as_numpy=True, **kwargs):
+        """The map workflow of the reference's notebooks in one call: create_centroid_list(window, spacingX,
+        spacingY) -> optimise_routine -> reshape to the centroid lattice -> Curie depth zt + dz, optionally
+        with uncertainty maps.  The centroid lists are never formed: the lattice axes go to the device and the
+        window origins are expanded there; the (rows, cols) maps are views of the solver's (n, 4) output.
+
+        uncertainty=None           MAP maps only
+        uncertainty='sensitivity'  + population std over `nsim` perturbed re-fits per window (optimise.py:635-725)
+        uncertainty='mcmc'         + posterior mean / std from one Metropolis-Hastings chain per window
+                                     (nsim samples after `burnin`), started at the window's MAP estimate
+
+        Returns a dict: xc (cols,), yc (rows,), beta, zt, dz, C, curie_depth (rows, cols) and, with
+        uncertainty, `<name>_std` (plus `<name>_mean` for 'mcmc') for the same five quantities."""
+        torch = _lib.require_cuda()
+        if uncertainty not in (None, "sensitivity", "mcmc"):
+            raise ValueError("uncertainty must be None, 'sensitivity' or 'mcmc'")
+        xs, ys = self.centroid_lattice(window, spacingX, spacingY)
+        lat = _plans.Lattice(xs, ys)
+        rows, cols = lat.shape
+        k, phi, sig = self._batch_spectra(window, lat, lat, taper, process_subgrid, kwargs)
+        x0 = (beta, zt, dz, C)
+        x = self._fit_device(k, phi, x0)
+        names = ("beta", "zt", "dz", "C", "curie_depth")
+        cols5 = torch.cat([x, (x[:, 1] + x[:, 2]).unsqueeze(1)], dim=1)
+        maps = {nm: cols5[:, j].reshape(rows, cols) for j, nm in enumerate(names)}
+        if uncertainty == "sensitivity":
+            std = torch.empty((rows * cols, 5), dtype=torch.float64, device="cuda")
+            if seed is None:
+                seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
+            step = max(1, (1 << 22) // max(int(nsim), 1))        # bound the perturbed-spectra slab
+            for a in range(0, rows * cols, step):
+                b = min(a + step, rows * cols)
+                smp = self._sensitivity_device(k, phi[a:b], sig[a:b], nsim, x0, seed, chain_offset=a)
+                smp = torch.cat([smp, (smp[..., 1] + smp[..., 2]).unsqueeze(-1)], dim=-1)
+                std[a:b] = smp.std(dim=1, unbiased=False)
+            for j, nm in enumerate(names):
+                maps[nm + "_std"] = std[:, j].reshape(rows, cols)
+        elif uncertainty == "mcmc":
+            mom, acc = self._mh_device(k, phi, nsim, burnin, x_scale, x0, x, seed, 1)
+            self.last_accepted = acc
+            for j, nm in enumerate(names):
+                maps[nm + "_mean"] = mom[:, j].reshape(rows, cols)
+                maps[nm + "_std"] = mom[:, 5 + j].reshape(rows, cols)
+        if as_numpy:
+            maps = {nm: v.cpu().numpy() for nm, v in maps.items()}
+        maps["xc"], maps["yc"] = xs, ys
+        return maps
 
     # ------------------------------------------------------------------ fan-out (optimise.py:317-444)
     @staticmethod

@@ -519,6 +519,41 @@ def test_parallelise_routine_containers(grid):
         grid.optimise_routine(100e3, [10e3], [150e3])
 
 
+def test_curie_depth_maps_equal_notebook_workflow(grid):
+    """curie_depth_maps (lattice expanded on the device, maps as views of the solver output) against the
+    reference's notebook sequence create_centroid_list -> optimise_routine -> reshape -> zt + dz, and its
+    two uncertainty modes against the batched sensitivity / Metropolis-Hastings calls with the same streams."""
+    xc, yc = grid.create_centroid_list(100e3, 40e3, 50e3)
+    beta, zt, dz, C = grid.optimise_routine(100e3, xc, yc)
+    m = grid.curie_depth_maps(100e3, 40e3, 50e3)
+    rows, cols = m["yc"].size, m["xc"].size
+    assert rows * cols == xc.size and m["beta"].shape == (rows, cols)
+    for name, ref in (("beta", beta), ("zt", zt), ("dz", dz), ("C", C), ("curie_depth", zt + dz)):
+        assert np.array_equal(m[name], ref.reshape(rows, cols)), name
+    assert np.array_equal(np.meshgrid(m["xc"], m["yc"])[0].ravel(), xc)
+
+    ms = grid.curie_depth_maps(100e3, 40e3, 50e3, uncertainty="sensitivity", nsim=24, seed=11)
+    smp = grid.sensitivity_batch(100e3, xc, yc, 24, seed=11)                 # (n, nsim, 4)
+    np.testing.assert_allclose(ms["dz_std"].ravel(), smp[:, :, 2].std(axis=1), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(ms["curie_depth_std"].ravel(), (smp[:, :, 1] + smp[:, :, 2]).std(axis=1),
+                               rtol=1e-12, atol=1e-14)
+    assert np.array_equal(ms["beta"], m["beta"])
+
+    grid.add_prior(beta=(3.0, 1.0), zt=(1.0, 1.0), dz=(20.0, 10.0), C=(-20.0, 5.0))
+    try:
+        x_map = grid.optimise_batch(100e3, xc, yc)
+        mm = grid.curie_depth_maps(100e3, 40e3, 50e3, uncertainty="mcmc", nsim=400, burnin=50,
+                                   x_scale=[0.25, 0.1, 1.0, 0.5], seed=5)
+        mom = grid.metropolis_hastings_batch(100e3, xc, yc, 400, 50, x_scale=[0.25, 0.1, 1.0, 0.5], x0=x_map, seed=5)
+        assert np.array_equal(mm["curie_depth_mean"].ravel(), mom[:, 4])
+        assert np.array_equal(mm["curie_depth_std"].ravel(), mom[:, 9])
+        assert np.all(mm["beta_std"] > 0)
+    finally:
+        grid.reset_priors()
+    with pytest.raises(ValueError, match="uncertainty"):
+        grid.curie_depth_maps(100e3, 40e3, 50e3, uncertainty="bootstrap")
+
+
 # --------------------------------------------------------------------------- Radon / azimuthal
 def test_radon_csr_bit_exact_and_sinogram(pc, grid):
     g = load_golden("radon.npz")

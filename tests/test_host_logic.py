@@ -261,3 +261,36 @@ def test_lattice_fast_path_equals_generic_rule(pc):
     assert _plans._lattice_shape(xc[perm], yc[perm]) is None
     iy2, ix2, _ = _plans.window_origins(G, 100e3, xc[perm], yc[perm])
     assert np.array_equal(ix2, ix0[perm]) and np.array_equal(iy2, iy0[perm])
+
+
+def test_lattice_origins_match_centroid_lists(pc):
+    """lattice_origins (axes only) against window_origins on the expanded lists, including which centroid
+    the reference would name in its two ValueErrors (first offender in x-fastest order)."""
+    from pycurious_b200 import _plans
+    n = 300
+    G = pc.CurieGrid(np.zeros((n, n)), 0.0, (n - 1) * 1000.0, 0.0, (n - 1) * 1000.0)
+    xs, ys = G.centroid_lattice(60e3, 7300.0, 9100.0)
+    xc, yc = G.create_centroid_list(60e3, 7300.0, 9100.0)
+    assert np.array_equal(np.meshgrid(xs, ys)[0].ravel(), xc)
+    iyu, ixu, nw = _plans.lattice_origins(G, 60e3, xs, ys)
+    iy0, ix0, nw2 = _plans.window_origins(G, 60e3, xc, yc)
+    assert nw == nw2
+    assert np.array_equal(np.repeat(iyu, xs.size), iy0) and np.array_equal(np.tile(ixu, ys.size), ix0)
+    lat = _plans.Lattice(xs, ys)
+    assert lat.shape == (ys.size, xs.size) and len(lat) == xc.size
+
+    def message(fn, *a):
+        with pytest.raises(ValueError) as e:
+            fn(*a)
+        return str(e.value)
+
+    for bx, by in [((3, -5e3), None), (None, (2, 4e8)), ((5, 1e3), None), (None, (0, 2e3)), ((4, -1.0), (1, 1e3)),
+                   ((4, 1e3), (0, 1e3)), ((2, 5e8), (3, -7.0))]:
+        x2, y2 = xs.copy(), ys.copy()
+        if bx:
+            x2[bx[0]] = bx[1]
+        if by:
+            y2[by[0]] = by[1]
+        xq, yq = np.meshgrid(x2, y2)
+        assert message(_plans.lattice_origins, G, 60e3, x2, y2) == \
+            message(_plans.window_origins, G, 60e3, xq.ravel(), yq.ravel())
