@@ -245,6 +245,17 @@ int cb_fft2_filter(const cb_fft_plan *plan_x /* length nx */, const cb_fft_plan 
                    double *out_dev, int64_t out_ld,
                    void *workspace_dev, int64_t workspace_bytes, void *stream);
 
+/* The same filter applied to a batch of n x n windows cut from a survey grid at (iy0[i], ix0[i]) -- the
+ * `process_subgrid` stage of CurieOptimise.optimise (pycurious/optimise.py:285-287) when the callable is
+ * reduce_to_pole / upward_continuation (grid.py:405-546).  `plan` is the length-n plan, `filter_dev` the
+ * complex128 [n, n] operator, `out_dev` a dense [nwin, n, n] stack that cb_spectrum_batch can read as a grid of
+ * nwin*n rows.  The caller validates the origins (0 <= iy0 <= ny-n, 0 <= ix0 <= nx-n). */
+int64_t cb_fft2_filter_windows_workspace_bytes(int n, int64_t nwin);
+int cb_fft2_filter_windows(const cb_fft_plan *plan, const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
+                           const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin, const void *filter_dev,
+                           double *out_dev /* [nwin, n, n] */, void *workspace_dev, int64_t workspace_bytes,
+                           void *stream);
+
 /* ------------------------------------------------------------------------
  * Tanaka et al. (1999):  tanaka1999 + ComputeTanaka (pycurious/grid.py:603-699) for a batch of
  * radial spectra taken with power = 0.5.  out[w, 0..7] = Ztr, btr, dZtr, Zor, bor, dZor, Zb, eZb;

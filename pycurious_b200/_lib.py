@@ -71,6 +71,8 @@ SIGNATURES = {
     "cb_fft_plan_destroy": (_I, [_VP]),
     "cb_fft2_filter_workspace_bytes": (_I64, [_I64, _I64]),
     "cb_fft2_filter": (_I, [_VP, _VP, _VP, _I64, _I64, _I64, _VP, _VP, _I64, _VP, _I64, _VP]),
+    "cb_fft2_filter_windows_workspace_bytes": (_I64, [_I, _I64]),
+    "cb_fft2_filter_windows": (_I, [_VP, _VP, _I64, _I64, _I64, _VP, _VP, _I64, _VP, _VP, _VP, _I64, _VP]),
     "cb_tanaka_batch": (_I, [_VP, _I, _VP, _VP, _I64, _D, _D, _D, _D, _VP, _VP]),
     "cb_mh_batch": (_I, [_VP, _I, _VP, _I64, C.POINTER(MhOptions), _VP, _VP, _VP, _VP]),
     "cb_radon_plan_create": (_I, [_I, _I, _VP, _VP, C.POINTER(_VP)]),

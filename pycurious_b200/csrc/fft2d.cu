@@ -143,4 +143,49 @@ int cb_fft2_filter(const cb_fft_plan *plan_x, const cb_fft_plan *plan_y, const d
     return launch_lines(plan_x, P, st);
 }
 
+int64_t cb_fft2_filter_windows_workspace_bytes(int n, int64_t nwin) {
+    if (n <= 0 || nwin <= 0) return 0;
+    return 2 * nwin * (int64_t)n * n * 16 + 512;
+}
+
+int cb_fft2_filter_windows(const cb_fft_plan *plan, const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
+                           const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin, const void *filter_dev,
+                           double *out_dev, void *workspace_dev, int64_t workspace_bytes, void *stream) {
+    CB_REQUIRE(plan != nullptr, "plan is NULL");
+    if (nwin == 0) return CB_OK;
+    CB_REQUIRE(nwin > 0, "nwin < 0");
+    CB_REQUIRE(grid_dev && iy0_dev && ix0_dev && filter_dev && out_dev && workspace_dev, "NULL buffer");
+    const int64_t n = plan->n;
+    CB_REQUIRE(ny >= n && nx >= n && ld >= nx, "windows larger than the grid");
+    CB_REQUIRE(nwin * n < ((int64_t)1 << 40), "batch too large");
+    CB_REQUIRE(workspace_bytes >= cb_fft2_filter_windows_workspace_bytes((int)n, nwin),
+               "workspace too small (see cb_fft2_filter_windows_workspace_bytes)");
+    cudaStream_t st = (cudaStream_t)stream;
+    double2 *A = reinterpret_cast<double2 *>(((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255);
+    double2 *B = A + nwin * n * n;
+    int rc;
+    LineFftParams P;
+    // 1. rows forward, gathered from the grid: window i -> A[i]
+    memset(&P, 0, sizeof(P));
+    P.in_real = grid_dev; P.in_es = 1; P.in_ls = ld; P.in_ld = ld; P.iy0 = iy0_dev; P.ix0 = ix0_dev;
+    P.out_cplx = A; P.out_es = 1; P.out_ls = n; P.out_bs = n * n; P.lines_per_img = n; P.nlines = nwin * n; P.scale = 1.0;
+    if ((rc = launch_lines(plan, P, st))) return rc;
+    // 2. columns forward, times the filter: A -> B
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = A; P.in_es = n; P.in_ls = 1; P.in_bs = n * n; P.out_cplx = B; P.out_es = n; P.out_ls = 1; P.out_bs = n * n;
+    P.lines_per_img = n; P.nlines = nwin * n; P.scale = 1.0;
+    P.mul = reinterpret_cast<const double2 *>(filter_dev);
+    if ((rc = launch_lines(plan, P, st))) return rc;
+    // 3. columns inverse: B -> A
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = B; P.in_es = n; P.in_ls = 1; P.in_bs = n * n; P.out_cplx = A; P.out_es = n; P.out_ls = 1; P.out_bs = n * n;
+    P.lines_per_img = n; P.nlines = nwin * n; P.inverse = 1; P.scale = 1.0 / (double)n;
+    if ((rc = launch_lines(plan, P, st))) return rc;
+    // 4. rows inverse, real part: A -> out stack
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = A; P.in_es = 1; P.in_ls = n; P.in_bs = n * n; P.out_real = out_dev; P.out_es = 1; P.out_ls = n; P.out_bs = n * n;
+    P.lines_per_img = n; P.nlines = nwin * n; P.inverse = 1; P.scale = 1.0 / (double)n;
+    return launch_lines(plan, P, st);
+}
+
 }  // extern "C"

@@ -14,11 +14,16 @@ callers that want many windows per call: `radial_spectrum_batch`,
 """
 from __future__ import annotations
 
+import functools
+import inspect
 import warnings
 
 import numpy as np
 
 from . import _lib, _plans
+
+
+_WINDOW = object()        # stands for the window argument when a process_subgrid partial is inspected
 
 
 class CurieGrid(object):
@@ -222,6 +227,57 @@ class CurieGrid(object):
         _lib.check(lib.cb_fft2_filter(px.handle, py.handle, d_t.data_ptr(), ny, nx, nx, f_t.data_ptr(), out.data_ptr(), nx,
                                       ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch)))
         return out.cpu().numpy()
+
+    def _window_filter(self, process_subgrid, n):
+        """The [n, n] FFT-domain operator when `process_subgrid` is `functools.partial(self.reduce_to_pole, ...)`
+        or `functools.partial(self.upward_continuation, ...)` (the window itself being the only missing
+        argument), else None.  Lets the batch entry points run those two stages on the device for every window
+        (cb_fft2_filter_windows) instead of calling back into Python window by window."""
+        if not isinstance(process_subgrid, functools.partial):
+            return None
+        f = process_subgrid.func
+        if not (inspect.ismethod(f) and f.__self__ is self):
+            return None
+        try:
+            if f.__func__ is CurieGrid.upward_continuation:
+                b = inspect.signature(CurieGrid.upward_continuation).bind(self, *process_subgrid.args, _WINDOW,
+                                                                          **process_subgrid.keywords)
+                if b.arguments["data"] is not _WINDOW:
+                    return None
+                height = b.arguments["height"]
+                if height <= 0:
+                    warnings.warn("Using 'height' <= 0 means downward continuation, " + "which is known to be unstable.")
+                kx, ky = _fftfreqs(self.dx, self.dy, (n, n))
+                return np.exp(-height * np.hypot(kx, ky)).astype(np.complex128)
+            if f.__func__ is CurieGrid.reduce_to_pole:
+                b = inspect.signature(CurieGrid.reduce_to_pole).bind(self, *process_subgrid.args, _WINDOW,
+                                                                     **process_subgrid.keywords)
+                if b.arguments["data"] is not _WINDOW:
+                    return None
+                b.apply_defaults()
+                a = b.arguments
+                field = np.asarray(ang2vec(1.0, a["inc"], a["dec"]), dtype=np.float64)
+                magn = field if (a["sinc"] is None or a["sdec"] is None) else np.asarray(
+                    ang2vec(1.0, a["sinc"], a["sdec"]), dtype=np.float64)
+                return np.asarray(_rtp_operator(_fftfreqs(self.dx, self.dy, (n, n)), field, magn), dtype=np.complex128)
+        except TypeError:
+            return None                       # arguments do not bind: let the host path raise the caller's error
+        return None
+
+    def _filter_windows_device(self, filt, iy0_t, ix0_t, n):
+        """Stack [nwin, n, n] (cuda) of the windows at (iy0, ix0) after real(ifft2(filt * fft2(window)))."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        g = self.device_grid()
+        nwin = int(iy0_t.numel())
+        plan = _plans.fft_plan(n)
+        f_t = torch.from_numpy(np.ascontiguousarray(filt, dtype=np.complex128).view(np.float64)).cuda()
+        out = torch.empty((nwin, n, n), dtype=torch.float64, device="cuda")
+        ws = torch.empty(int(lib.cb_fft2_filter_windows_workspace_bytes(n, nwin)), dtype=torch.uint8, device="cuda")
+        _lib.check(lib.cb_fft2_filter_windows(plan.handle, g.data_ptr(), g.shape[0], g.shape[1], g.stride(0),
+                                              iy0_t.data_ptr(), ix0_t.data_ptr(), nwin, f_t.data_ptr(), out.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), _lib.stream_ptr(torch)))
+        return out
 
     def reduce_to_pole(self, data, inc, dec, sinc=None, sdec=None):
         """Reduce total-field anomaly data to the pole (grid.py:405-490): the Blakely (1996) operator is built

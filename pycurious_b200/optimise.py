@@ -129,6 +129,10 @@ class CurieOptimise(CurieGrid):
             plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
             phi, sig = plan.run(self.device_grid(), iy0, ix0, process_subgrid is not None, power)
             return plan.k, phi, sig
+        n_probe = _plans.window_nodes(window, self.dx)[1] * 2 + 1
+        filt = self._window_filter(process_subgrid, n_probe)
+        if filt is not None:
+            return self._batch_spectra_filtered(window, xc_list, yc_list, lattice, filt, taper, power, kwargs)
         if lattice is not None:
             xq, yq = np.meshgrid(lattice.xs, lattice.ys)
             xc_list, yc_list = xq.ravel(), yq.ravel()
@@ -143,6 +147,31 @@ class CurieOptimise(CurieGrid):
         ix0 = torch.zeros(len(wins), dtype=torch.int32, device="cuda")
         plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
         phi, sig = plan.run(stack, iy0, ix0, False, power)
+        return plan.k, phi, sig
+
+    FILTER_CHUNK_BYTES = 6 << 30     # device scratch per slice of the filtered-window path
+
+    def _batch_spectra_filtered(self, window, xc_list, yc_list, lattice, filt, taper, power, kwargs):
+        """Spectra of reduce_to_pole / upward_continuation windows: windows are filtered on the device in slices
+        (cb_fft2_filter_windows -> a dense stack) and each stack goes through the spectrum kernel as a grid of
+        its own (one window per n rows)."""
+        torch = _lib.require_cuda()
+        if lattice is not None:
+            iy0, ix0, n = self._origins_lattice_device(window, lattice.xs, lattice.ys)
+        else:
+            iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+        plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
+        nwin = int(iy0.numel())
+        phi = torch.empty((nwin, plan.nbins), dtype=torch.float64, device="cuda")
+        sig = torch.empty_like(phi)
+        step = max(1, int(self.FILTER_CHUNK_BYTES // (n * n * 40)))      # 2 complex scratch planes + the real stack
+        for a in range(0, nwin, step):
+            b = min(a + step, nwin)
+            stack = self._filter_windows_device(filt, iy0[a:b].contiguous(), ix0[a:b].contiguous(), n)
+            sy = torch.arange(b - a, dtype=torch.int32, device="cuda") * n
+            sx = torch.zeros(b - a, dtype=torch.int32, device="cuda")
+            p, s = plan.run(stack.view((b - a) * n, n), sy, sx, False, power, share_rows=False)
+            phi[a:b], sig[a:b] = p, s
         return plan.k, phi, sig
 
     # ------------------------------------------------------------------ MAP fit

@@ -316,6 +316,47 @@ int emu_fft2_filter(const double *data, int64_t ny, int64_t nx, const double *fi
     return 0;
 }
 
+// the four passes of cb_fft2_filter_windows: nwin windows of edge n gathered from a grid, filtered, stacked
+int emu_fft2_filter_windows(const double *grid, int64_t ny, int64_t nx, const int32_t *iy0, const int32_t *ix0,
+                            int64_t nwin, int n, const double *filter_re_im, double *out) {
+    (void)ny;
+    FftPlan fft; std::vector<double2> tw, chirp, filt; std::vector<int32_t> slot; int bl = 0;
+    if (cbplan::build_fft_plan(n, fft, tw)) slot = cbplan::digit_reversed_slots(fft);
+    else {
+        int M = cbplan::bluestein_length(n);
+        if (!M || !cbplan::build_fft_plan(M, fft, tw)) return -1;
+        bl = 1;
+        cbplan::build_bluestein_tables(n, fft, chirp, filt);
+    }
+    const int line_slots = (fft_line_slots(fft.n) + 1) & ~1;
+    if (bl) filt.resize(line_slots, cplx(0.0, 0.0));
+    const int64_t nn = (int64_t)n * n;
+    std::vector<double2> A(nwin * nn), B(nwin * nn);
+    auto run = [&](LineFftParams P) {
+        P.n = n; P.bluestein = bl; P.fft = fft; P.tw = tw.data(); P.chirp = chirp.data(); P.filt = filt.data();
+        P.slot = slot.data(); P.line_slots = line_slots; P.lines_per_img = n; P.nlines = nwin * n;
+        emu_launch(3, 64, (size_t)2 * line_slots * 16, [&](const HostCtx &cx) { line_fft_body(cx, P); });
+    };
+    LineFftParams P;
+    memset(&P, 0, sizeof(P));
+    P.in_real = grid; P.in_es = 1; P.in_ls = nx; P.in_ld = nx; P.iy0 = iy0; P.ix0 = ix0;
+    P.out_cplx = A.data(); P.out_es = 1; P.out_ls = n; P.out_bs = nn; P.scale = 1.0;
+    run(P);
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = A.data(); P.in_es = n; P.in_ls = 1; P.in_bs = nn; P.out_cplx = B.data(); P.out_es = n; P.out_ls = 1; P.out_bs = nn;
+    P.scale = 1.0; P.mul = reinterpret_cast<const double2 *>(filter_re_im);
+    run(P);
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = B.data(); P.in_es = n; P.in_ls = 1; P.in_bs = nn; P.out_cplx = A.data(); P.out_es = n; P.out_ls = 1; P.out_bs = nn;
+    P.inverse = 1; P.scale = 1.0 / (double)n;
+    run(P);
+    memset(&P, 0, sizeof(P));
+    P.in_cplx = A.data(); P.in_es = 1; P.in_ls = n; P.in_bs = nn; P.out_real = out; P.out_es = 1; P.out_ls = n; P.out_bs = nn;
+    P.inverse = 1; P.scale = 1.0 / (double)n;
+    run(P);
+    return 0;
+}
+
 // fit with per-row prior means (the inner loop of CurieOptimise.sensitivity)
 int emu_fit_rows(const double *kh, int nk, const double *phi, int64_t nwin, const cb_fit_options *opt,
                  const double *prior_mu_rows, double *x_out, double *f_out) {

@@ -390,6 +390,49 @@ def test_fft_domain_filters_match_reference(grid, oracle, mag):
     assert x.shape == (4,) and np.all(np.isfinite(x))
 
 
+def test_filter_stage_recognised_in_batches(grid, oracle, mag, monkeypatch):
+    """process_subgrid=functools.partial(grid.upward_continuation / reduce_to_pole, ...) runs for the whole
+    centroid batch on the device (cb_fft2_filter_windows -> spectrum): same spectra as the reference sequence
+    subgrid -> filter -> radial_spectrum per window, same fit as the host-callback path, sliced or not."""
+    import functools
+    d, ext = mag
+    spec = oracle.GridSpec(d, *ext)
+    xc, yc = grid.create_centroid_list(100e3, 25e3, 30e3)
+    stages = [
+        (functools.partial(grid.upward_continuation, height=1500.0),
+         lambda n: oracle.upward_continuation_filter((n, n), grid.dx, grid.dy, 1500.0)),
+        (functools.partial(grid.reduce_to_pole, inc=-60.0, dec=12.0, sdec=20.0, sinc=50.0),
+         lambda n: oracle.reduce_to_pole_filter((n, n), grid.dx, grid.dy, -60.0, 12.0, 50.0, 20.0)),
+    ]
+    for stage, make_filter in stages:
+        assert grid._window_filter(stage, 101) is not None
+        k, phi, sig = grid._batch_spectra(100e3, xc, yc, np.hanning, stage, {})
+        phi, sig = phi.cpu().numpy(), sig.cpu().numpy()
+        for i in (0, 7, xc.size - 1):
+            win = oracle.fft_filter(oracle.cut_window(spec, 100e3, xc[i], yc[i]), make_filter(101))
+            k_o, phi_o, sig_o = oracle.radial_spectrum(win, spec.dx)
+            assert np.array_equal(k, k_o)
+            np.testing.assert_allclose(phi[i], phi_o, rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(sig[i], sig_o, rtol=1e-8, atol=1e-9)
+        # the same callable hidden in a lambda takes the host path: identical windows, identical fits
+        x_dev = grid.optimise_batch(100e3, xc[:6], yc[:6], process_subgrid=stage)
+        x_host = grid.optimise_batch(100e3, xc[:6], yc[:6], process_subgrid=lambda w: stage(w))
+        np.testing.assert_allclose(x_dev, x_host, rtol=1e-6, atol=1e-8)
+        # slicing by scratch budget does not change anything
+        monkeypatch.setattr(type(grid), "FILTER_CHUNK_BYTES", 101 * 101 * 40 * 5)
+        _, phi2, _ = grid._batch_spectra(100e3, xc, yc, np.hanning, stage, {})
+        monkeypatch.undo()
+        assert np.array_equal(phi2.cpu().numpy(), phi)
+    m = grid.curie_depth_maps(100e3, 50e3, 50e3, process_subgrid=stages[0][0])
+    xq, yq = grid.create_centroid_list(100e3, 50e3, 50e3)
+    ref = grid.optimise_batch(100e3, xq, yq, process_subgrid=stages[0][0])
+    assert np.array_equal(m["dz"].ravel(), ref[:, 2])
+    # partials that are not the window-only form fall back to the host path
+    assert grid._window_filter(functools.partial(grid.upward_continuation), 101) is None
+    assert grid._window_filter(functools.partial(grid.reduce_to_pole, -60.0, 12.0), 101) is None   # window would be `dec`
+    assert grid._window_filter(lambda w: w, 101) is None
+
+
 def test_tanaka_batch_matches_reference(pc, grid, oracle, mag):
     """CurieGrid.tanaka_batch = radial_spectrum(power=0.5) -> tanaka1999 -> ComputeTanaka per centroid."""
     d, ext = mag

@@ -294,3 +294,26 @@ def test_lattice_origins_match_centroid_lists(pc):
         xq, yq = np.meshgrid(x2, y2)
         assert message(_plans.lattice_origins, G, 60e3, x2, y2) == \
             message(_plans.window_origins, G, 60e3, xq.ravel(), yq.ravel())
+
+
+def test_process_subgrid_filter_recognition(pc):
+    """Only `functools.partial(<own bound reduce_to_pole / upward_continuation>, ...)` whose sole missing argument
+    is the window is turned into a device stage; everything else stays a host callback.  The operator is the
+    one the method itself would build."""
+    import functools
+    n = 64
+    G = pc.CurieOptimise(np.zeros((n, n)), 0.0, (n - 1) * 1000.0, 0.0, (n - 1) * 1000.0)
+    other = pc.CurieOptimise(np.zeros((n, n)), 0.0, (n - 1) * 1000.0, 0.0, (n - 1) * 1000.0)
+    from pycurious_b200.grid import _fftfreqs
+    f = G._window_filter(functools.partial(G.upward_continuation, height=750.0), 21)
+    kx, ky = _fftfreqs(G.dx, G.dy, (21, 21))
+    assert f.shape == (21, 21) and np.array_equal(f, np.exp(-750.0 * np.hypot(kx, ky)))
+    r1 = G._window_filter(functools.partial(G.reduce_to_pole, inc=-60.0, dec=12.0), 21)
+    r2 = G._window_filter(functools.partial(G.reduce_to_pole, inc=-60.0, dec=12.0, sinc=-60.0, sdec=12.0), 21)
+    assert r1.dtype == np.complex128 and np.array_equal(r1, r2) and r1[0, 0] == 0
+    for cb in (None, lambda w: w, functools.partial(G.upward_continuation), functools.partial(G.reduce_to_pole, -60.0, 12.0),
+               functools.partial(other.upward_continuation, height=5.0), functools.partial(G.remove_trend_linear),
+               functools.partial(G.upward_continuation, height=1.0, bogus=2)):
+        assert G._window_filter(cb, 21) is None
+    with pytest.warns(UserWarning, match="downward continuation"):
+        G._window_filter(functools.partial(G.upward_continuation, height=-1.0), 21)

@@ -60,4 +60,14 @@ xc, yc = G.create_centroid_list(200e3, 10e3, 10e3)
 sel = np.linspace(0, xc.size - 1, 2000).astype(int)
 ms, mom = timed(lambda: G.sensitivity_batch(200e3, xc[sel], yc[sel], 64, reduce="moments", seed=1, as_numpy=False), reps=2)
 res["sensitivity_2000x64"] = {"fits": 2000 * 64, "ms": ms, "fits_per_s": 2000 * 64 / ms * 1e3}
+# process_subgrid stage on the device: upward continuation of every window before its spectrum (20,000 windows)
+import functools
+sel = np.linspace(0, xc.size - 1, 20000).astype(int)
+stage = functools.partial(G.upward_continuation, height=1000.0)
+ms, _ = timed(lambda: G._batch_spectra(200e3, xc[sel], yc[sel], np.hanning, stage, {}), reps=2)
+res["config3_upward_continuation_spectrum_20000"] = {"windows": 20000, "ms": ms, "windows_per_s": 20000 / ms * 1e3}
+# map assembly: lattice on the device, MAP maps
+ms, m = timed(lambda: G.curie_depth_maps(200e3, 10e3, 10e3, as_numpy=False), reps=2)
+res["config3_curie_depth_maps"] = {"windows": int(m["beta"].numel()), "ms": ms,
+                                   "windows_per_s": int(m["beta"].numel()) / ms * 1e3}
 print(json.dumps(res, indent=1))
