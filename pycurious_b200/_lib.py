@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcurie_b200.so")
+LIB_PATH = os.environ.get("CB_LIB_PATH") or os.path.join(_HERE, "libcurie_b200.so")   # override: A/B builds
 
 CB_MAX_RADIX_PASSES = 12
 

@@ -217,7 +217,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
             const double t1 = (P.taper_r && has1) ? Ctx::ldg(P.taper_r + y1) : 1.0;
             const double pl0 = c0 + cy1 * ((double)y0 - ctr), pl1 = c0 + cy1 * ((double)y1 - ctr);
             bool fused = false;
-            if constexpr (Engine::PREFETCH) if (P.bluestein) {
+            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
                 fused = true;
                 // the first FFT pass pulls its inputs straight from the grid (coalesced: lane j reads
                 // x = j + t*SUB), the last one leaves the n live outputs in the line
@@ -294,7 +294,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
             const double2 *col = Gt + (int64_t)v * npad;
             double *out = Lh + (int64_t)v * n;
             bool fused = false;
-            if constexpr (Engine::PREFETCH) if (P.bluestein) {
+            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
                 fused = true;
                 auto ld = [&](int y) -> double2 {
                     if (y >= n) return cplx(0.0, 0.0);
@@ -389,7 +389,7 @@ CB_BODY void rowspec_body(const Ctx &cx, const SpectrumParams &P) {
         const double *r0 = P.grid + (int64_t)(P.row_lo + (has0 ? 2 * p : 0)) * P.ld + Ctx::ldg(P.group_ix0 + g);
         const double *r1 = has1 ? r0 + P.ld : r0;
         bool fused = false;
-        if constexpr (Engine::PREFETCH) if (P.bluestein) {
+        if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
             fused = true;
             auto ld = [&](int x) -> double2 {
                 if (x >= n) return cplx(0.0, 0.0);
@@ -529,7 +529,7 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
                 return P.bluestein ? cmul(z, rw) : cscale(z, rw.x);
             };
             bool fused = false;
-            if constexpr (Engine::PREFETCH) if (P.bluestein) {
+            if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
                 fused = true;
                 auto ld = [&](int y) -> double2 { return y < n ? element(y) : cplx(0.0, 0.0); };
                 const int span = Ctx::ldg(P.col_span + v);
