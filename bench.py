@@ -254,13 +254,15 @@ def run_gpu(args):
         def timed(fn, reps):
             fn()
             torch.cuda.synchronize()
-            a, b = ev(), ev()
-            a.record()
-            for _ in range(reps):
+            marks = [ev() for _ in range(reps + 1)]
+            marks[0].record()
+            for i in range(reps):
                 out_ = fn()
-            b.record()
+                marks[i + 1].record()
             torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps, out_
+            # median of the back-to-back launches: one slow repetition (allocator growth, a host hiccup between
+            # launches) does not move the per-stage figure
+            return float(np.median([marks[i].elapsed_time(marks[i + 1]) for i in range(reps)])), out_
         reps = max(3, args.steps)
         t_spec, (phi, sig) = timed(lambda: plan.run(g_dev, iy0, ix0, False, 2.0), reps)
         t_fit, (x, diag) = timed(lambda: grid._fit_device(plan.k, phi, x0, diagnostics=True), reps)
