@@ -121,13 +121,14 @@ class CurieOptimise(CurieGrid):
         kwargs = dict(kwargs)
         power = kwargs.pop("power", 2.0)
         lattice = xc_list if isinstance(xc_list, _plans.Lattice) else None
+        grid_t = self.device_grid()        # a pending upload (pinned host grid) overlaps the host-side origin work below
         if process_subgrid is None or self._is_detrend(process_subgrid):
             if lattice is not None:
                 iy0, ix0, n = self._origins_lattice_device(window, lattice.xs, lattice.ys)
             else:
                 iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
             plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
-            phi, sig = plan.run(self.device_grid(), iy0, ix0, process_subgrid is not None, power)
+            phi, sig = plan.run(grid_t, iy0, ix0, process_subgrid is not None, power)
             return plan.k, phi, sig
         n_probe = _plans.window_nodes(window, self.dx)[1] * 2 + 1
         filt = self._window_filter(process_subgrid, n_probe)
