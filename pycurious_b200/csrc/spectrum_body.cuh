@@ -104,70 +104,80 @@ CB_BODY void window_plane(const Ctx &cx, const SpectrumParams &P, const double *
 
 // Phase C: radial bins (grid.py:281-286), mean / population std of the members of each bin, one
 // warp per bin over the folded CSR.  The members are gathered through two dependent L2 loads (CSR
-// index, then the log-power), so the walk is software pipelined over 128-member chunks: the indices of
-// the NEXT chunk -- of this bin or of the warp's next bin -- are requested while the values of the
-// current one are in flight.  Sum and sum of squares are taken about a pivot member (the first one):
-// the population variance is shift invariant and the pivot removes the mean^2 cancellation.
+// index, then the log-power), so the walk over 128-member chunks is software pipelined two deep: while
+// chunk c is reduced, the values of chunk c+1 and the indices of chunk c+2 -- of this bin or of the
+// warp's next bins -- are in flight.  Sum and sum of squares are taken about a pivot member (the first
+// one): the population variance is shift invariant and the pivot removes the mean^2 cancellation.
+struct BinChunk { int b, lo, hi, eb; };
+
 template <class Ctx>
 CB_BODY void bin_phase(const Ctx &cx, const SpectrumParams &P, const double *Lh, int64_t w, int warp, int lane,
                        int nwarps) {
     constexpr int CHUNK = 4 * CB_WARP;
-    int b = warp;
-    if (b >= P.nbins) return;
-    int lo = Ctx::ldg(P.bin_ptr + b), hi = Ctx::ldg(P.bin_ptr + b + 1), eb = lo;
-    int idx[4];
+    if (warp >= P.nbins) return;
+    auto next_of = [&](BinChunk c) -> BinChunk {
+        c.eb += CHUNK;
+        if (c.eb >= c.hi) {
+            c.b += nwarps;
+            c.lo = c.hi = 0;
+            if (c.b < P.nbins) { c.lo = Ctx::ldg(P.bin_ptr + c.b); c.hi = Ctx::ldg(P.bin_ptr + c.b + 1); }
+            c.eb = c.lo;
+        }
+        return c;
+    };
+    auto load_idx = [&](const BinChunk &c, int (&idx)[4]) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int e = eb + j * CB_WARP + lane;
-        idx[j] = e < hi ? Ctx::ldg(P.bin_idx + e) : -1;
-    }
-    double s = 0.0, q = 0.0, pivot = 0.0;
-    while (b < P.nbins) {
-        double v[4];
+        for (int j = 0; j < 4; ++j) {
+            const int e = c.eb + j * CB_WARP + lane;
+            idx[j] = e < c.hi ? Ctx::ldg(P.bin_idx + e) : -1;
+        }
+    };
+    auto load_val = [&](const int (&idx)[4], double (&v)[4]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = idx[j] >= 0 ? Ctx::ldcg(Lh + idx[j]) : 0.0;
-        const bool head = eb == lo;
-        const bool last = eb + CHUNK >= hi;
-        int nb = b, nlo = lo, nhi = hi, neb = eb + CHUNK;
-        if (last) {
-            nb = b + nwarps;
-            nlo = nhi = 0;
-            if (nb < P.nbins) { nlo = Ctx::ldg(P.bin_ptr + nb); nhi = Ctx::ldg(P.bin_ptr + nb + 1); }
-            neb = nlo;
+    };
+    BinChunk c0{warp, Ctx::ldg(P.bin_ptr + warp), Ctx::ldg(P.bin_ptr + warp + 1), 0};
+    c0.eb = c0.lo;
+    int idx0[4], idx1[4];
+    double v0[4];
+    load_idx(c0, idx0);
+    BinChunk c1 = next_of(c0);
+    load_idx(c1, idx1);
+    load_val(idx0, v0);
+    double s = 0.0, q = 0.0, pivot = 0.0;
+    while (c0.b < P.nbins) {
+        const BinChunk c2 = next_of(c1);
+        int idx2[4];
+        double v1[4];
+        load_idx(c2, idx2);
+        load_val(idx1, v1);
+        if (c0.eb == c0.lo) {
+            pivot = cx.shfl(v0[0], 0);               // member `lo` (an empty bin has no pivot: 0)
+            if (!isfinite(pivot) || c0.lo >= c0.hi) pivot = 0.0;   // log(0) = -inf members: plain sums, numpy's -inf / nan result
         }
-        int nidx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int e = neb + j * CB_WARP + lane;
-            nidx[j] = e < nhi ? Ctx::ldg(P.bin_idx + e) : -1;
-        }
-        if (head) {
-            pivot = cx.shfl(v[0], 0);                // member `lo` (an empty bin has no pivot: 0)
-            if (!isfinite(pivot) || lo >= hi) pivot = 0.0;   // log(0) = -inf members: plain sums, numpy's -inf / nan result
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double d = idx[j] >= 0 ? v[j] - pivot : 0.0;
+            const double d = idx0[j] >= 0 ? v0[j] - pivot : 0.0;
             s += d;
             q = fma(d, d, q);
         }
-        if (last) {
+        if (c0.eb + CHUNK >= c0.hi) {                // last chunk of bin c0.b
             s = cx.warp_sum(s);
             q = cx.warp_sum(q);
-            const double cnt = (double)(hi - lo);
+            const double cnt = (double)(c0.hi - c0.lo);
             const double md = s / cnt;                  // mean - pivot
             const double mean = pivot + md;
             q -= s * md;                                // sum (x - mean)^2
             if (q < 0.0) q = 0.0;                       // (a nan stays a nan)
             if (lane == 0) {
-                P.phi[w * P.nbins + b] = P.power * mean;
-                P.sigma[w * P.nbins + b] = fabs(P.power) * sqrt(q / cnt);
+                P.phi[w * P.nbins + c0.b] = P.power * mean;
+                P.sigma[w * P.nbins + c0.b] = fabs(P.power) * sqrt(q / cnt);
             }
             s = q = 0.0;
         }
-        b = nb; lo = nlo; hi = nhi; eb = neb;
+        c0 = c1; c1 = c2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = nidx[j];
+        for (int j = 0; j < 4; ++j) { idx0[j] = idx1[j]; idx1[j] = idx2[j]; v0[j] = v1[j]; }
     }
 }
 
