@@ -34,6 +34,27 @@ struct DevCtx {
     template <class T> __device__ __forceinline__ static T ldg(const T *p) { return __ldg(p); }
     template <class T> __device__ __forceinline__ static T ldcg(const T *p) { return __ldcg(p); }
     template <class T> __device__ __forceinline__ static void stcg(T *p, T v) { __stcg(p, v); }
+    // Read-only views of arrays that live in SHARED memory but reach a non-inlined function through a plain
+    // pointer: the compiler would issue generic-space loads (LD.E plus descriptor moves) for them; the view
+    // converts the base once and reads with ld.shared.
+    struct SharedD2 {
+        unsigned a;
+        __device__ __forceinline__ double2 operator[](int i) const {
+            double2 v;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a + 16u * (unsigned)i));
+            return v;
+        }
+    };
+    struct SharedD {
+        unsigned a;
+        __device__ __forceinline__ double operator[](int i) const {
+            double v;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a + 8u * (unsigned)i));
+            return v;
+        }
+    };
+    __device__ __forceinline__ static SharedD2 shared_view(const double2 *p) { return SharedD2{(unsigned)__cvta_generic_to_shared(p)}; }
+    __device__ __forceinline__ static SharedD shared_view(const double *p) { return SharedD{(unsigned)__cvta_generic_to_shared(p)}; }
 };
 #endif
 
@@ -101,6 +122,7 @@ struct HostCtx {
     bool all(bool pred) const { return !any(!pred); }
     template <class T> static T ldg(const T *p) { return *p; }
     template <class T> static T ldcg(const T *p) { return *p; }
+    template <class T> static const T *shared_view(const T *p) { return p; }      // plain memory under emulation
     template <class T> static void stcg(T *p, T v) { *p = v; }
 };
 
@@ -127,6 +149,7 @@ struct SerialCtx {
     bool all(bool pred) const { return pred; }
     template <class T> static T ldg(const T *p) { return *p; }
     template <class T> static T ldcg(const T *p) { return *p; }
+    template <class T> static const T *shared_view(const T *p) { return p; }      // plain memory under emulation
     template <class T> static void stcg(T *p, T v) { *p = v; }
 };
 #endif

@@ -514,8 +514,8 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
 
     // first evaluation: forward difference in beta (see CB_FIT_CENTRAL_BELOW)
     model_coefs_warp(cx, W, S->pt, S->hb, 0, 2, lane);
-    model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
-    model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
+    model_eval_warp<false>(cx, W, 0, lane, W.p0, W.dz);
+    model_eval_warp<false>(cx, W, 1, lane, W.pp, nullptr);
     fit_reduce_full(cx, W, S, lane);
     if (lane == 0) { fit_accept_first(S); S->nfev = 2; }
 
@@ -534,11 +534,11 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
                 if (lane == 0) fit_trial_at_x(S);
                 cx.sync_warp();
                 model_coefs_warp(cx, W, S->pt, S->hb, 0, 3, lane);
-                model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
-                model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
+                model_eval_warp<false>(cx, W, 0, lane, W.p0, W.dz);
+                model_eval_warp<false>(cx, W, 1, lane, W.pp, nullptr);
                 extra = 3;
             }
-            model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
+            model_eval_warp<false>(cx, W, 2, lane, W.pm, nullptr);
             if (lane == 0) S->use_pm = 1;
             cx.sync_warp();
             fit_reduce_full(cx, W, S, lane);
@@ -557,7 +557,7 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
             const double dec = S->dec;
             if (S->move == 0.0) break;
             model_coefs_warp(cx, W, S->pt, 0.0, 0, 1, lane);
-            model_eval_warp(cx, W, 0, lane, W.p0, W.dz);
+            model_eval_warp<false>(cx, W, 0, lane, W.p0, W.dz);
             ++nls;
             double ft = slab_half_ssq(cx, W, lane);
             ft = isfinite(ft) ? ft + S->pen_t : CB_BIG_MISFIT;
@@ -580,8 +580,8 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
         // p0 and dPhi/ddz are already staged
         const int central = S->central;
         model_coefs_warp(cx, W, S->pt, S->hb, 1, central ? 2 : 1, lane);
-        model_eval_warp(cx, W, 1, lane, W.pp, nullptr);
-        if (central) model_eval_warp(cx, W, 2, lane, W.pm, nullptr);
+        model_eval_warp<false>(cx, W, 1, lane, W.pp, nullptr);
+        if (central) model_eval_warp<false>(cx, W, 2, lane, W.pm, nullptr);
         if (lane == 0) S->use_pm = central;
         cx.sync_warp();
         fit_reduce_full(cx, W, S, lane);

@@ -140,7 +140,7 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     // min_func of proposal l of the block, exact when <= bound (see model_eval_warp)
     auto misfit_of = [&](int l, double bound) -> double {
         const double pen = pens[l];
-        const double f = model_eval_warp(cx, W, l, lane, W.p0, nullptr, W.obs, bound - pen);
+        const double f = model_eval_warp<true>(cx, W, l, lane, W.p0, nullptr, W.obs, bound - pen);
         return isfinite(f) ? f + pen : CB_BIG_MISFIT;
     };
 

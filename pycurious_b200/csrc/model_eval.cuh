@@ -211,9 +211,12 @@ CB_NOINLINE_BODY double generic_point(const ModelCoef *m, double k, double logk,
 //   F  scale by e^-x resp. e^-2x, upward recurrence in the order, bracket, log
 // Returns 0.5 sum_i (Phi_i - obs_i)^2 when `obs` is given (0 otherwise); with a finite `bound` the
 // evaluation may stop early and return a partial sum that already exceeds the bound.
-template <class Ctx>
+// OBS = false (the fit: values and derivatives only) compiles the residual sums and bound checks out -- each
+// warp_sum is ten shuffles wrapped in warp-sync sequences inside a non-inlined function, a fifth of its size.
+template <bool OBS, class Ctx>
 CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int lane, double *out_phi,
-                                        double *out_ddz, const double *obs = nullptr, double bound = INFINITY) {
+                                        double *out_ddz, const double *obs_ = nullptr, double bound = INFINITY) {
+    const double *obs = OBS ? obs_ : nullptr;
     const EvalCoef &e = W.coef[idx];
     const ModelCoef &m = e.m;
     const int nk = W.nk, L = cx.team_lanes();
@@ -223,10 +226,11 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
         for (int i = lane; i < nk; i += L) {
             const double ph = generic_point(&m, Ctx::ldg(W.k + (i)), Ctx::ldg(W.logk + (i)), out_ddz ? out_ddz + i : nullptr);
             out_phi[i] = ph;
-            if (obs) { const double r = ph - obs[i]; accg = fma(r, r, accg); }
+            if (OBS && obs) { const double r = ph - obs[i]; accg = fma(r, r, accg); }
         }
         cx.sync_warp();
-        return obs ? 0.5 * cx.warp_sum(accg) : 0.0;
+        if (OBS && obs) return 0.5 * cx.warp_sum(accg);
+        return 0.0;
     }
     const double mu = m.ord.mu, a1 = e.a1, dz = m.dz;
 
@@ -252,7 +256,7 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
     // every chunk: 0.5 sum r^2 only grows, so a proposal whose partial misfit is already above the bound is
     // rejected without the Bessel work of the remaining points (Metropolis-Hastings rejects ~90 %).
     double acc = 0.0;
-    const bool bounded = obs != nullptr && bound < 1e300;
+    const bool bounded = OBS && obs != nullptr && bound < 1e300;
 
     // ---- S: the Bessel term cannot change the rounded bracket (no K_nu needed: done first) --------
 #pragma unroll 1
@@ -262,7 +266,7 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
         const double ph = over ? INFINITY : fma(-2.0 * k, m.zt, m.C) - (m.beta - 1.0) * Ctx::ldg(W.logk + (i)) + e.lgc;
         out_phi[i] = ph;
         if (out_ddz) out_ddz[i] = over ? NAN : 0.0;
-        if (obs) { const double r = ph - obs[i]; acc = fma(r, r, acc); }
+        if (OBS && obs) { const double r = ph - obs[i]; acc = fma(r, r, acc); }
     }
     if (bounded && nS < nk) {
         const double part = 0.5 * cx.warp_sum(acc);
@@ -338,10 +342,11 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
                 double p = e.hp * ee, q = e.hq * ei, c = 1.0;
                 const double x2 = 0.5 * Ctx::ldg(W.k + (i)) * dz, dd = x2 * x2;
                 double sum = ff, sum1 = p;
+                const auto RPQ = Ctx::shared_view(W.rpq);
 #pragma unroll 1
                 for (int j = 1; j < CB_TEMME_TAB; ++j) {
                     const double fj = (double)j;
-                    const double2 r = W.rpq[j];
+                    const double2 r = RPQ[j];
                     ff = (fj * ff + p + q) * (r.x * r.y);
                     c *= dd * Ctx::ldg(W.rn + (j));
                     p *= r.x;
@@ -360,15 +365,20 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
             const double xi = Ctx::ldg(W.k + (ii)) * dz;
             int N = (int)(12.0 + 140.0 * (Ctx::ldg(W.rk + (c0)) * e.rdz)) + 1;
             if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
-            double yp = 0.0, y = 1.0, S = W.CA[N].x;
+            // (x: weight of y_n in the normalising sum, y: recurrence coefficient); one shared load per step
+            const auto CA = Ctx::shared_view(W.CA);
+            double2 ca = CA[N];
+            double yp = 0.0, y = 1.0, S = ca.x;
             double bn = 2.0 * ((double)N + xi);
 #pragma unroll 2
             for (int n = N; n >= 1; --n) {
-                const double ym = fma(bn, y, W.CA[n].y * yp);
+                const double2 cm = CA[n - 1];
+                const double ym = fma(bn, y, ca.y * yp);
                 yp = y;
                 y = ym;
-                S = fma(W.CA[n - 1].x, y, S);
+                S = fma(cm.x, y, S);
                 bn -= 2.0;
+                ca = cm;
             }
             if (i < c1) {
                 const double invx = Ctx::ldg(W.rk + (ii)) * e.rdz;
@@ -400,7 +410,7 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
             out_phi[i] = ph;
             // k [ (Gamma/4 (1 - e2) + hx K_{nu-1} e^-x) / br - 1 ] with the subtraction done analytically
             if (out_ddz) out_ddz[i] = k * fma(hx, a + b, -2.0 * qg * e2) / br;
-            if (obs) { const double r = ph - obs[i]; acc = fma(r, r, acc); }
+            if (OBS && obs) { const double r = ph - obs[i]; acc = fma(r, r, acc); }
         }
         c0 = c1;
         if (bounded && c0 < nS) {
@@ -409,7 +419,8 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
         }
     }
     cx.sync_warp();
-    return obs ? 0.5 * cx.warp_sum(acc) : 0.0;
+    if (OBS && obs) return 0.5 * cx.warp_sum(acc);
+    return 0.0;
 }
 
 // 0.5 sum (p0 - obs)^2 over the slab (every lane returns the total).
@@ -428,7 +439,7 @@ CB_BODY double slab_half_ssq(const Ctx &cx, const WarpSlab &W, int lane) {
 template <class Ctx>
 CB_BODY double misfit_slab(const Ctx &cx, const WarpSlab &W, const double *x, const Priors &pr, int lane) {
     model_coefs_warp(cx, W, x, 0.0, 0, 1, lane);
-    const double f = model_eval_warp(cx, W, 0, lane, W.p0, nullptr, W.obs);
+    const double f = model_eval_warp<true>(cx, W, 0, lane, W.p0, nullptr, W.obs);
     if (!isfinite(f)) return CB_BIG_MISFIT;
     return f + prior_penalty(pr, x);
 }
@@ -440,7 +451,7 @@ CB_BODY double misfit_slab_bounded(const Ctx &cx, const WarpSlab &W, const doubl
                                    double bound) {
     const double pen = prior_penalty(pr, x);
     model_coefs_warp(cx, W, x, 0.0, 0, 1, lane);
-    const double f = model_eval_warp(cx, W, 0, lane, W.p0, nullptr, W.obs, bound - pen);
+    const double f = model_eval_warp<true>(cx, W, 0, lane, W.p0, nullptr, W.obs, bound - pen);
     if (!isfinite(f)) return CB_BIG_MISFIT;
     return f + pen;
 }

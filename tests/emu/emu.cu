@@ -435,14 +435,14 @@ void emu_model_eval(const double *kh, int nk, const double *x, double *phi, doub
         WarpSlab W = warp_slab_carve(sm.data(), nk, true, kh, ktab.data());
         warp_slab_load(cx, W, zero.data(), 0);
         model_coefs_warp(cx, W, x, 0.0, 0, 1, 0);
-        model_eval_warp(cx, W, 0, 0, W.p0, W.dz);
+        model_eval_warp<false>(cx, W, 0, 0, W.p0, W.dz);
         for (int i = 0; i < nk; ++i) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
     } else {
         emu_launch(1, 32, warp_slab_doubles(nk, true) * sizeof(double), [&](const HostCtx &cx) {
             WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()), nk, true, kh, ktab.data());
             warp_slab_load(cx, W, zero.data(), cx.tid());
             model_coefs_warp(cx, W, x, 0.0, 0, 1, cx.tid());
-            model_eval_warp(cx, W, 0, cx.tid(), W.p0, W.dz);
+            model_eval_warp<false>(cx, W, 0, cx.tid(), W.p0, W.dz);
             for (int i = cx.tid(); i < nk; i += 32) { phi[i] = W.p0[i]; ddz[i] = W.dz[i]; }
         });
     }
