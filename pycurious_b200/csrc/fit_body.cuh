@@ -394,7 +394,8 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
         const bool fp = isfinite(pp), fm = use_pm && isfinite(pm);
         W.kb[i] = (fp && fm) ? (pp - pm) * rh2 : (fp ? (pp - p0) * rh : (fm ? (p0 - pm) * rh : 0.0));
         W.res[i] = p0 - W.obs[i];
-    }
+        W.pm[i] = Ctx::ldg(W.k + (i));        // Phi(beta - hb) is consumed: the slot now stages k, so that all five
+    }                                         // vectors of pass 2 are in shared memory (ld.shared, no descriptors)
     if (lane == 0) S->one = 1.0;
     cx.sync_warp();
     const bool split = (L == 32);
@@ -412,13 +413,14 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
             va = a + 1;
             vb = t - (a * 4 - (a * (a - 1)) / 2) + a + 1;
         }
-        const double *pa = va == 0 ? W.res : (va == 1 ? W.kb : (va == 2 ? W.k : (va == 3 ? W.dz : &S->one)));
-        const double *pb = vb == 0 ? W.res : (vb == 1 ? W.kb : (vb == 2 ? W.k : (vb == 3 ? W.dz : &S->one)));
+        const double *pa = va == 0 ? W.res : (va == 1 ? W.kb : (va == 2 ? W.pm : (va == 3 ? W.dz : &S->one)));
+        const double *pb = vb == 0 ? W.res : (vb == 1 ? W.kb : (vb == 2 ? W.pm : (vb == 3 ? W.dz : &S->one)));
         const int sa = va == 4 ? 0 : 1, sb = vb == 4 ? 0 : 1;
+        const auto A = Ctx::shared_view(pa), B = Ctx::shared_view(pb);
         double acc = 0.0;
         if (q < 15) {
-#pragma unroll 1
-            for (int i = lo; i < hi; ++i) acc = fma(pa[i * sa], pb[i * sb], acc);
+#pragma unroll 4
+            for (int i = lo; i < hi; ++i) acc = fma(A[i * sa], B[i * sb], acc);
         }
         if (split) acc += cx.shfl_xor(acc, 16);
         acc *= (va == 2 ? -2.0 : 1.0) * (vb == 2 ? -2.0 : 1.0);

@@ -70,6 +70,7 @@ struct WarpSlab {          // views into one warp's shared-memory slab
     double *res;                        // [nk] fit only: residuals during the reduction
     double2 *CA;                        // [CB_MILLER_NMAX + 1] (C_n, a_{n+1}) of the order being evaluated
     double2 *rpq;                       // [CB_TEMME_TAB] (1/(j-mu), 1/(j+mu))
+    double *rnj;                        // [CB_TEMME_TAB] 1/j (shared copy of rn for the Temme loop)
     EvalCoef *coef;                     // [ncoef]: CB_MAX_ORDERS (fit) or CB_MH_BLOCK (MCMC) parameter vectors
     double *scratch;                    // solver state (fit) behind the tables
     int nk;
@@ -81,7 +82,7 @@ struct WarpSlab {          // views into one warp's shared-memory slab
 #define CB_SLAB_COEF_DOUBLES ((int)((sizeof(EvalCoef) + 7) / 8))
 
 CB_HD int warp_slab_doubles(int nk, bool fit, int scratch_doubles = 0, int ncoef = CB_MAX_ORDERS) {
-    int n = (fit ? 7 : 3) * nk + 2 * (CB_MILLER_NMAX + 1) + 2 * CB_TEMME_TAB +
+    int n = (fit ? 7 : 3) * nk + 2 * (CB_MILLER_NMAX + 1) + 3 * CB_TEMME_TAB +
             ncoef * CB_SLAB_COEF_DOUBLES + scratch_doubles;
     return (n + 1) & ~1;      // keep every slab 16-byte aligned
 }
@@ -123,6 +124,7 @@ CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh,
     double *t = base;
     W.CA = reinterpret_cast<double2 *>(t); t += 2 * (CB_MILLER_NMAX + 1);
     W.rpq = reinterpret_cast<double2 *>(t); t += 2 * CB_TEMME_TAB;
+    W.rnj = t; t += CB_TEMME_TAB;
     W.coef = reinterpret_cast<EvalCoef *>(t); t += ncoef * CB_SLAB_COEF_DOUBLES;
     W.obs = t; W.p0 = t + nk; W.kb = t + 2 * nk;
     t += 3 * nk;
@@ -317,8 +319,10 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
     }
     if (nT > 0) {
 #pragma unroll 1
-        for (int j = 1 + lane; j < CB_TEMME_TAB; j += L)
+        for (int j = 1 + lane; j < CB_TEMME_TAB; j += L) {
             W.rpq[j] = make_double2(1.0 / ((double)j - mu), 1.0 / ((double)j + mu));
+            W.rnj[j] = Ctx::ldg(W.rn + (j));
+        }
     }
     cx.sync_warp();
 
@@ -343,12 +347,13 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
                 const double x2 = 0.5 * Ctx::ldg(W.k + (i)) * dz, dd = x2 * x2;
                 double sum = ff, sum1 = p;
                 const auto RPQ = Ctx::shared_view(W.rpq);
+                const auto RNJ = Ctx::shared_view(W.rnj);
 #pragma unroll 1
                 for (int j = 1; j < CB_TEMME_TAB; ++j) {
                     const double fj = (double)j;
                     const double2 r = RPQ[j];
                     ff = (fj * ff + p + q) * (r.x * r.y);
-                    c *= dd * Ctx::ldg(W.rn + (j));
+                    c *= dd * RNJ[j];
                     p *= r.x;
                     q *= r.y;
                     const double del = c * ff;
