@@ -558,7 +558,9 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
             cx.sync_warp();
             const double dec = S->dec;
             if (S->move == 0.0) break;
-            model_coefs_warp(cx, W, S->pt, 0.0, 0, 1, lane);
+            // coefficients of the trial point AND of its beta +- hb neighbours in one call (one lane each, same
+            // instruction count as the trial alone): the derivative evaluations of an accepted trial need no second pass
+            model_coefs_warp(cx, W, S->pt, S->hb, 0, S->central ? 3 : 2, lane);
             model_eval_warp<false>(cx, W, 0, lane, W.p0, W.dz);
             ++nls;
             double ft = slab_half_ssq(cx, W, lane);
@@ -581,7 +583,6 @@ CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
         // derivatives at the accepted point: beta + hb (and beta - hb once the central difference is on);
         // p0 and dPhi/ddz are already staged
         const int central = S->central;
-        model_coefs_warp(cx, W, S->pt, S->hb, 1, central ? 2 : 1, lane);
         model_eval_warp<false>(cx, W, 1, lane, W.pp, nullptr);
         if (central) model_eval_warp<false>(cx, W, 2, lane, W.pm, nullptr);
         if (lane == 0) S->use_pm = central;

@@ -64,6 +64,7 @@ for f in os.listdir(tmp):
 
 def line_map(func):
     out, cur, active = {}, None, False
+    func = "_Z%d%s" % (len(func), func)      # mangled prefix: "fit_kernel" must not match "misfit_kernel"
     for text in dis.values():
         if func not in text:
             continue
