@@ -83,7 +83,9 @@ CB_HD double philox_uniform(uint64_t t, uint32_t ph, uint32_t k0, uint32_t k1) {
 }
 
 // slab of one chain: model arrays, CB_MH_BLOCK coefficient slots, the block's proposals / uniforms / penalties
-CB_HD int mh_slab_doubles(int nk) { return warp_slab_doubles(nk, false, 6 * CB_MH_BLOCK, CB_MH_BLOCK); }
+CB_HD int mh_slab_doubles(int nk) { return warp_slab_doubles(nk, false, 7 * CB_MH_BLOCK, CB_MH_BLOCK); }
+
+#define CB_NEG_LOG_P_FLOOR 227.95592420641054      /* -ln(1e-99), the floor of optimise.py:621 in log space */
 
 template <class Ctx>
 CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
@@ -100,6 +102,7 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     double *props = W.scratch;                  // [CB_MH_BLOCK][4] proposals of the current block
     double *us = props + 4 * CB_MH_BLOCK;       // [CB_MH_BLOCK] acceptance uniforms
     double *pens = us + CB_MH_BLOCK;            // [CB_MH_BLOCK] prior penalties of the proposals
+    double *nlu = pens + CB_MH_BLOCK;           // [CB_MH_BLOCK] -ln(u), for the early-rejection bound
 
     const cb_mh_options &o = P.opt;
     Priors pr;
@@ -133,6 +136,7 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
             for (int j = 0; j < 4; ++j) { x1[j] = x[j] + z[j] * scale[j]; props[4 * l + j] = x1[j]; }
             pens[l] = prior_penalty(pr, x1);
             us[l] = phase ? philox_uniform((uint64_t)(t0 + l), phase, k0, k1) : 0.0;
+            nlu[l] = phase ? -log(us[l]) : 0.0;
         }
         cx.sync_warp();
         model_coefs_lanes(cx, W, props, n, lane);
@@ -169,9 +173,27 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     }
 
     // ---- sampling (optimise.py:613-631): accept iff u <= min(exp(-f1) / max(P0, 1e-99), 1) ----
-    P0 = exp(-misfit_slab(cx, W, x, pr, lane));
+    double fcur = misfit_slab(cx, W, x, pr, lane);            // min_func of the current state (= -ln P0 above the floor)
+    P0 = exp(-fcur);
     int64_t nacc = 0;
-    double mean[5] = {0, 0, 0, 0, 0}, m2[5] = {0, 0, 0, 0, 0};   // Welford accumulators (mode 1)
+    // Moments (mode 1): the state is recorded once per step but changes on ~10 % of them, so the run of
+    // `rep` identical samples is folded in at once (Chan's pairwise update) when the state moves.
+    double mean[5] = {0, 0, 0, 0, 0}, m2[5] = {0, 0, 0, 0, 0};
+    int64_t nrec = 0, rep = 0;
+    auto fold = [&]() {
+        if (rep == 0) return;
+        const double v[5] = {x[0], x[1], x[2], x[3], x[1] + x[2]};
+        const double tot = (double)(nrec + rep);
+        const double wgt = (double)rep / tot, cross = (double)nrec * wgt;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const double dlt = v[j] - mean[j];
+            mean[j] = fma(dlt, wgt, mean[j]);
+            m2[j] = fma(dlt * dlt, cross, m2[j]);
+        }
+        nrec += rep;
+        rep = 0;
+    };
     double *chain_out = P.out + w * 4 * o.nsim;
     for (int64_t t0 = 0; t0 < o.nsim;) {
         const int n = (int)(o.nsim - t0 < CB_MH_BLOCK ? o.nsim - t0 : CB_MH_BLOCK);
@@ -181,7 +203,9 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
             const int64_t t = t0 + l;
             const double u = us[l];
             P0 = fmax(P0, 1e-99);
-            const double need = -log(u * P0);                 // exp(-f1)/P0 >= u  <=>  f1 <= -ln(u P0)
+            // exp(-f1)/P0 >= u  <=>  f1 <= -ln(u P0) = -ln u + min(f_current, -ln 1e-99); the bound only gates
+            // the early rejection (1e-6 margin), the reference's own test below decides inside it
+            const double need = nlu[l] + fmin(fcur, CB_NEG_LOG_P_FLOOR);
             const double bound = need + 1e-6 * fmax(1.0, fabs(need));
             const double f1 = misfit_of(l, bound);
             bool take = false;
@@ -191,9 +215,11 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
                 take = u <= fmin(P1 / P0, 1.0);
             }
             if (take) {
+                if (o.reduce_mode != 0) fold();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[j] = props[4 * l + j];
                 P0 = P1;
+                fcur = f1;
                 ++nacc;
             }
             if (o.reduce_mode == 0) {
@@ -202,19 +228,13 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
                     for (int j = 0; j < 4; ++j) chain_out[j * o.nsim + t] = x[j];
                 }
             } else {
-                const double v[5] = {x[0], x[1], x[2], x[3], x[1] + x[2]};
-                const double inv = 1.0 / (double)(t + 1);
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const double dlt = v[j] - mean[j];
-                    mean[j] += dlt * inv;
-                    m2[j] = fma(dlt, v[j] - mean[j], m2[j]);
-                }
+                ++rep;
             }
             if (take) { used = l + 1; break; }
         }
         t0 += used;
     }
+    if (o.reduce_mode != 0) fold();
     if (lane == 0) {
         if (o.reduce_mode != 0) {
             double *mo = P.out + w * 10;
