@@ -211,7 +211,8 @@ int cb_spectrum_batch(const cb_spectrum_plan *plan, const double *grid_dev, int6
 int64_t cb_spectrum_rowspec_bytes(const cb_spectrum_plan *plan, int ngroups, int row_lo, int row_hi) {
     if (!plan || ngroups < 0 || row_hi < row_lo) return 0;
     const int64_t nrows = ((int64_t)(row_hi - row_lo) + 1) & ~1LL;
-    return (int64_t)ngroups * plan->hp.nvh * nrows * 16 + 256;
+    // row spectra [ngroups][nvh][nrows] + per-row sums for the detrend plane [ngroups][nrows], both complex128
+    return (int64_t)ngroups * (plan->hp.nvh + 1) * nrows * 16 + 512;
 }
 
 int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan, const double *grid_dev, int64_t ny, int64_t nx,
@@ -250,6 +251,10 @@ int cb_spectrum_batch_shared_rows(const cb_spectrum_plan *plan, const double *gr
     P.row_lo = row_lo; P.nrows_valid = row_hi - row_lo; P.nrows = (P.nrows_valid + 1) & ~1;
     P.rt = reinterpret_cast<double2 *>(((uintptr_t)rowspec_dev + 255) & ~(uintptr_t)255);
     P.plane_t0 = plan->d_plane_t0; P.plane_t1 = plan->d_plane_t1;
+    if (P.detrend) {
+        const uintptr_t rs = (uintptr_t)(P.rt + (int64_t)ngroups * hp.nvh * P.nrows);
+        P.rowsum = reinterpret_cast<double2 *>((rs + 255) & ~(uintptr_t)255);
+    }
     const int64_t items = (int64_t)ngroups * (P.nrows / 2);
     const int row_grid = (int)std::min<int64_t>((items + hp.teams - 1) / hp.teams, plan->grid_max);
     plan->row_kernel<<<row_grid, hp.threads, (size_t)hp.smem_bytes, (cudaStream_t)stream>>>(P);

@@ -60,6 +60,7 @@ struct SpectrumParams {
     int32_t nrows_valid;           // rows [row_lo, row_lo + nrows_valid) exist in the grid
     double2 *rt;                   // [ngroups][nvh][nrows] half spectra of (grid row x column taper)
     const double2 *plane_t0, *plane_t1;   // [nvh] x-transforms of taper_c and (x - ctr) taper_c (detrend)
+    double2 *rowsum;               // [ngroups][nrows] (sum_x d, sum_x (x - ctr) d) of each row segment (detrend) or NULL
 };
 
 CB_HD double2 bluestein_out(const double2 *buf, const double2 *chirp, int k) {
@@ -86,6 +87,36 @@ CB_BODY void window_plane(const Ctx &cx, const SpectrumParams &P, const double *
         s0 += r0;
         sx += rx;
         sy = fma((double)y - ctr, r0, sy);
+    }
+    s0 = cx.warp_sum(s0);
+    sx = cx.warp_sum(sx);
+    sy = cx.warp_sum(sy);
+    if (lane == 0) { s_red[warp] = s0; s_red[32 + warp] = sx; s_red[64 + warp] = sy; }
+    cx.sync_block();
+    s0 = sx = sy = 0.0;
+    for (int i = 0; i < nwarps; ++i) { s0 += s_red[i]; sx += s_red[32 + i]; sy += s_red[64 + i]; }
+    const double nn = (double)n;
+    const double sxx = nn * nn * (nn * nn - 1.0) / 12.0;   // sum over the window of (x-ctr)^2
+    c0 = s0 / (nn * nn);
+    cx1 = sx / sxx;
+    cy1 = sy / sxx;
+    cx.sync_block();
+}
+
+// The same plane from the per-row sums rowspec_body leaves for every (group, grid row): the windows of a group
+// share their row segments exactly like they share the row spectra, so a window adds n pairs instead of reading
+// its n^2 nodes again.  `rs` points at the window's first row.
+template <class Ctx>
+CB_BODY void window_plane_rows(const Ctx &cx, const SpectrumParams &P, const double2 *rs, double *s_red, int warp,
+                               int lane, int nwarps, double &c0, double &cx1, double &cy1) {
+    const int n = P.n;
+    const double ctr = 0.5 * (double)(n - 1);
+    double s0 = 0.0, sx = 0.0, sy = 0.0;
+    for (int y = warp * CB_WARP + lane; y < n; y += nwarps * CB_WARP) {
+        const double2 r = Ctx::ldcg(rs + y);
+        s0 += r.x;
+        sx += r.y;
+        sy = fma((double)y - ctr, r.x, sy);
     }
     s0 = cx.warp_sum(s0);
     sx = cx.warp_sum(sx);
@@ -398,6 +429,22 @@ CB_BODY void rowspec_body(const Ctx &cx, const SpectrumParams &P) {
         const bool has0 = 2 * p < P.nrows_valid, has1 = 2 * p + 1 < P.nrows_valid;
         const double *r0 = P.grid + (int64_t)(P.row_lo + (has0 ? 2 * p : 0)) * P.ld + Ctx::ldg(P.group_ix0 + g);
         const double *r1 = has1 ? r0 + P.ld : r0;
+        if (P.rowsum) {                          // detrend: zeroth and first moment of both row segments
+            const double ctr = 0.5 * (double)(n - 1);
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            for (int x = lane; x < n; x += CB_WARP) {
+                const double av = has0 ? Ctx::ldg(r0 + x) : 0.0, bv = has1 ? Ctx::ldg(r1 + x) : 0.0;
+                const double xc = (double)x - ctr;
+                a0 += av; a1 = fma(xc, av, a1);
+                b0 += bv; b1 = fma(xc, bv, b1);
+            }
+            a0 = cx.warp_sum(a0); a1 = cx.warp_sum(a1); b0 = cx.warp_sum(b0); b1 = cx.warp_sum(b1);
+            if (lane == 0) {
+                double2 *rs = P.rowsum + (int64_t)g * P.nrows + 2 * p;
+                rs[0] = cplx(a0, a1);
+                rs[1] = cplx(b0, b1);
+            }
+        }
         bool fused = false;
         if constexpr (Engine::FUSED_SPAN > 0) if (P.bluestein) {
             fused = true;
@@ -471,7 +518,10 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
         const int iy0 = P.iy0[w], g = P.group_of_win[w];
         double c0 = 0.0, cx1 = 0.0, cy1 = 0.0;
         if (P.detrend)
-            window_plane(cx, P, P.grid + (int64_t)iy0 * P.ld + P.ix0[w], s_red, warp, lane, nwarps, c0, cx1, cy1);
+        {
+            if (P.rowsum) window_plane_rows(cx, P, P.rowsum + (int64_t)g * P.nrows + (iy0 - P.row_lo), s_red, warp, lane, nwarps, c0, cx1, cy1);
+            else window_plane(cx, P, P.grid + (int64_t)iy0 * P.ld + P.ix0[w], s_red, warp, lane, nwarps, c0, cx1, cy1);
+        }
         const double2 *rt_w = P.rt + ((int64_t)g * nvh) * P.nrows + (iy0 - P.row_lo);
         if constexpr (Engine::PREFETCH) if (P.bluestein) {
             // Static engines: the raw row-spectrum slice of the NEXT column is requested before the current

@@ -190,6 +190,8 @@ int emu_spectrum_shared(int nw, int nbins, const double *taper_r, const double *
     std::vector<double> lh((size_t)nblocks * 2 * hp.lh_stride);
     P.rt = rt.data(); P.lh = lh.data(); P.lh_stride = 2 * hp.lh_stride; P.lh_half = hp.lh_stride;
     P.plane_t0 = hp.plane_t0.data(); P.plane_t1 = hp.plane_t1.data();
+    std::vector<double2> rowsum((size_t)P.ngroups * P.nrows);
+    if (detrend) P.rowsum = rowsum.data();
     (void)ny;
     const bool generic = max_teams < 0 || !hp.bluestein;
     if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 8>>(nblocks, hp, P);
