@@ -151,6 +151,7 @@ class CurieOptimise(CurieGrid):
         return plan.k, phi, sig
 
     FILTER_CHUNK_BYTES = 6 << 30     # device scratch per slice of the filtered-window path
+    SENSITIVITY_ROWS = 1 << 22       # perturbed spectra held at once by curie_depth_maps(uncertainty='sensitivity')
 
     def _batch_spectra_filtered(self, window, xc_list, yc_list, lattice, filt, taper, power, kwargs):
         """Spectra of reduce_to_pole / upward_continuation windows: windows are filtered on the device in slices
@@ -256,7 +257,7 @@ class CurieOptimise(CurieGrid):
             std = torch.empty((rows * cols, 5), dtype=torch.float64, device="cuda")
             if seed is None:
                 seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
-            step = max(1, (1 << 22) // max(int(nsim), 1))        # bound the perturbed-spectra slab
+            step = max(1, self.SENSITIVITY_ROWS // max(int(nsim), 1))        # bound the perturbed-spectra slab
             for a in range(0, rows * cols, step):
                 b = min(a + step, rows * cols)
                 smp = self._sensitivity_device(k, phi[a:b], sig[a:b], nsim, x0, seed, chain_offset=a)

@@ -562,7 +562,7 @@ def test_parallelise_routine_containers(grid):
         grid.optimise_routine(100e3, [10e3], [150e3])
 
 
-def test_curie_depth_maps_equal_notebook_workflow(grid):
+def test_curie_depth_maps_equal_notebook_workflow(grid, monkeypatch):
     """curie_depth_maps (lattice expanded on the device, maps as views of the solver output) against the
     reference's notebook sequence create_centroid_list -> optimise_routine -> reshape -> zt + dz, and its
     two uncertainty modes against the batched sensitivity / Metropolis-Hastings calls with the same streams."""
@@ -581,6 +581,11 @@ def test_curie_depth_maps_equal_notebook_workflow(grid):
     np.testing.assert_allclose(ms["curie_depth_std"].ravel(), (smp[:, :, 1] + smp[:, :, 2]).std(axis=1),
                                rtol=1e-12, atol=1e-14)
     assert np.array_equal(ms["beta"], m["beta"])
+    monkeypatch.setattr(type(grid), "SENSITIVITY_ROWS", 24 * 7)              # seven windows per slice: same streams
+    ms2 = grid.curie_depth_maps(100e3, 40e3, 50e3, uncertainty="sensitivity", nsim=24, seed=11)
+    monkeypatch.undo()
+    for name in ("beta_std", "zt_std", "dz_std", "C_std", "curie_depth_std"):
+        assert np.array_equal(ms2[name], ms[name]), name
 
     grid.add_prior(beta=(3.0, 1.0), zt=(1.0, 1.0), dz=(20.0, 10.0), C=(-20.0, 5.0))
     try:
