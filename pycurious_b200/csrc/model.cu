@@ -12,9 +12,11 @@ extern __shared__ double cb_dyn_smem_d[];
 // bound (one long serial chain per window): throughput scales with resident warps, so the slab is kept
 // at ~9 KB (window-independent tables live in global memory) and registers at 80 for 24 CTAs per SM.
 #define CB_FIT_WARPS 1
+#ifndef CB_FIT_CTAS_PER_SM
 #define CB_FIT_CTAS_PER_SM 24
+#endif
 #ifndef CB_MH_CTAS_PER_SM
-#define CB_MH_CTAS_PER_SM 32
+#define CB_MH_CTAS_PER_SM 24
 #endif
 
 __global__ void __launch_bounds__(256) besselk_kernel(const double *nu, const double *x, int64_t n, double *out) {
