@@ -36,7 +36,9 @@
 #define CB_TEMME_TAB 28
 #define CB_SKIP_LOG 43.0                      /* > 60 ln 2 + ln(4 sqrt(pi/4)) */
 #define CB_COSH_OVERFLOW 710.4758600739439    /* np.cosh overflows above this */
-#define CB_MH_BLOCK 8                         /* proposals prepared together by the MCMC kernel */
+#ifndef CB_MH_BLOCK
+#define CB_MH_BLOCK 8
+#endif                         /* proposals prepared together by the MCMC kernel */
 #define CB_MAX_ORDERS 3                       /* parameter vectors evaluated per call group: x, x+h e_beta, x-h e_beta */
 
 #if defined(__CUDACC__) && !defined(CB_EMU)
