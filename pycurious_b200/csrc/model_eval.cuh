@@ -346,15 +346,16 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
     }
     cx.sync_warp();
 
-    // ---- chunks of up to L points, each entirely in the Temme class [0,nT) or the Miller class [nT,nS):
+    // ---- chunks of up to L consecutive points of [0,nS): a lane's point is in the Temme class (i < nT) or the
+    //      Miller class; the chunk that straddles nT runs both branches (lanes diverge) and shares ONE phase F.
     //      K_mu, K_mu+1 (phase T or M), then scale / raise the order / bracket (phase F) ----------------
     const double qg = 0.25 * m.gnu;
     const int nl = m.ord.nl;
 #pragma unroll 1
     for (int c0 = 0; c0 < nS;) {
-        const bool temme = c0 < nT;
-        const int c1 = temme ? (c0 + L < nT ? c0 + L : nT) : (c0 + L < nS ? c0 + L : nS);
+        const int c1 = c0 + L < nS ? c0 + L : nS;
         const int i = c0 + lane;
+        const bool temme = i < nT;
         if (temme) {
             if (i < c1) {
                 const double d = -(Ctx::ldg(W.logk + (i)) + m.lhalfdz);      // ln(2/x)
@@ -384,11 +385,12 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
                 out_phi[i] = sum;                       // K_mu; phase F turns it into Phi in place
                 W.kb[i] = sum1 * (2.0 * Ctx::ldg(W.rk + (i)) * e.rdz);
             }
-        } else {
-            // Miller backward recurrence, trip count uniform over the chunk (from its smallest x: k ascending)
+        } else if (c1 > nT) {
+            // Miller backward recurrence, trip count uniform over the chunk's Miller points (from the smallest
+            // x among them: k ascending)
             const int ii = i < c1 ? i : c1 - 1;
             const double xi = Ctx::ldg(W.k + (ii)) * dz;
-            int N = (int)(12.0 + 140.0 * (Ctx::ldg(W.rk + (c0)) * e.rdz)) + 1;
+            int N = (int)(12.0 + 140.0 * (Ctx::ldg(W.rk + (c0 > nT ? c0 : nT)) * e.rdz)) + 1;
             if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
             // (x: weight of y_n in the normalising sum, y: recurrence coefficient); one shared load per step
             const auto CA = Ctx::shared_view(W.CA);
