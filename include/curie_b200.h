@@ -124,7 +124,9 @@ int cb_spectrum_batch(const cb_spectrum_plan *plan,
  *                         (group, iy0) makes concurrently resident CTAs read overlapping rows (L2 hits)
  *   [row_lo, row_hi)      grid rows to transform for every group; every window needs
  *                         row_lo <= iy0[w] and iy0[w] + nw <= row_hi
- *   rowspec_dev           cb_spectrum_rowspec_bytes(plan, ngroups, row_lo, row_hi) bytes of scratch
+ *   rowspec_dev           cb_spectrum_rowspec_bytes(plan, ngroups, row_lo, row_hi) bytes of scratch: the row
+ *                         spectra [ngroups][nw/2+1][rows] and, for detrend, the per-row sums (sum d,
+ *                         sum (x - xbar) d) [ngroups][rows] from which every window's plane is assembled
  * Worth it when nwin * nw is well above ngroups * (row_hi - row_lo), i.e. when rows are reused.
  */
 int64_t cb_spectrum_rowspec_bytes(const cb_spectrum_plan *plan, int ngroups, int row_lo, int row_hi);
