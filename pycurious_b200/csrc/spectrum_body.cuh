@@ -17,6 +17,7 @@
 #pragma once
 #include "exec_ctx.cuh"
 #include "fft_engine.cuh"
+#include "fastlog.cuh"
 
 struct SpectrumParams {
     // input
@@ -346,7 +347,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                 const int span = Ctx::ldg(P.col_span + v);
                 const int lo_end = (span & 0xffff) == 0xffff ? -1 : (span & 0xffff), hi_start = (int)((unsigned)span >> 16);
                 auto sk = [&](int u, double2 z) {
-                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, cb_half_log(fma(z.x, z.x, z.y * z.y)));
                 };
                 Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
             }
@@ -370,7 +371,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                 for (int u = lane; u < n; u += CB_WARP) {
                     // |chirp| = 1, so the modulus needs no post-multiply
                     const double2 z = P.bluestein ? buf[CB_PAD(u)] : buf[CB_PAD(Ctx::ldg(P.slot + u))];
-                    Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    Ctx::stcg(out + u, cb_half_log(fma(z.x, z.x, z.y * z.y)));
                 }
             }
             cx.sync_warp();
@@ -563,7 +564,7 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
                 const int span = Ctx::ldg(P.col_span + v);
                 const int lo_end = (span & 0xffff) == 0xffff ? -1 : (span & 0xffff), hi_start = (int)((unsigned)span >> 16);
                 auto sk = [&](int u, double2 z) {
-                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, cb_half_log(fma(z.x, z.x, z.y * z.y)));
                 };
                 Engine::convolve_pre(cx, buf, s_tw, s_filt, lane, cur, sk);
                 cx.sync_warp();
@@ -595,7 +596,7 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
                 const int span = Ctx::ldg(P.col_span + v);
                 const int lo_end = (span & 0xffff) == 0xffff ? -1 : (span & 0xffff), hi_start = (int)((unsigned)span >> 16);
                 auto sk = [&](int u, double2 z) {
-                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, cb_half_log(fma(z.x, z.x, z.y * z.y)));
                 };
                 Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
             }
@@ -606,7 +607,7 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
                 else Engine::forward(cx, buf, s_tw, P.fft, lane);
                 for (int u = lane; u < n; u += CB_WARP) {
                     const double2 z = P.bluestein ? buf[CB_PAD(u)] : buf[CB_PAD(Ctx::ldg(P.slot + u))];
-                    Ctx::stcg(out + u, 0.5 * log(fma(z.x, z.x, z.y * z.y)));
+                    Ctx::stcg(out + u, cb_half_log(fma(z.x, z.x, z.y * z.y)));
                 }
             }
             cx.sync_warp();

@@ -450,6 +450,11 @@ void emu_model_eval(const double *kh, int nk, const double *x, double *phi, doub
     }
 }
 
+// the spectrum kernels' 0.5 ln(x) (host build of the same algorithm: float-rounded reciprocal seed)
+void emu_half_log(const double *x, int64_t n, double *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = cb_half_log(x[i]);
+}
+
 void emu_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {
     U32x4 r = philox4x32_10(c0, c1, c2, c3, k0, k1);
     for (int i = 0; i < 4; ++i) out[i] = r.v[i];

@@ -363,6 +363,36 @@ def test_mh_body_reproduces_reference_chain(emu):
     np.testing.assert_allclose(mom[5:], full.std(axis=1), rtol=1e-10, atol=1e-12)
 
 
+def test_half_log_within_an_ulp_and_special_values(emu):
+    """cb_half_log (argument reduction + minimax polynomial + Newton reciprocal) against numpy's log over the
+    whole double range, around powers of two and sqrt(2) (the reduction's branch points), and the values that
+    take the library path: 0 -> -inf (grid.py:283 relies on it), subnormals, inf, nan, negatives."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([
+        np.exp(rng.uniform(-700.0, 700.0, 200000)),
+        rng.uniform(0.5, 2.0, 200000),
+        np.ldexp(1.0 + rng.uniform(-1e-9, 1e-9, 20000), rng.integers(-1000, 1000, 20000)),
+        np.sqrt(2.0) * (1.0 + rng.uniform(-1e-12, 1e-12, 20000)),
+        np.array([1.0, 2.0, 0.5, np.nextafter(1.0, 2.0), np.nextafter(1.0, 0.0), 2.2250738585072014e-308,
+                  1.7976931348623157e308])])
+    out = np.empty_like(x)
+    emu.emu_half_log(P(x), C.c_int64(x.size), P(out))
+    ref = 0.5 * np.log(x)
+    err = np.abs(out - ref)
+    ulp = np.spacing(np.abs(ref))
+    near1 = np.abs(x - 1.0) < 1e-3                     # the result itself is tiny there: absolute bound
+    assert np.all(err[~near1] <= 1.0 * ulp[~near1] + 0.0), float((err[~near1] / ulp[~near1]).max())
+    assert np.all(err[near1] <= 2e-19 + 1.0 * ulp[near1])
+    sp = np.array([0.0, -0.0, 5e-324, 1e-310, np.inf, np.nan, -1.0])
+    o2 = np.empty_like(sp)
+    emu.emu_half_log(P(sp), C.c_int64(sp.size), P(o2))
+    with np.errstate(all="ignore"):
+        r2 = 0.5 * np.log(sp)
+    assert np.array_equal(np.isnan(o2), np.isnan(r2))
+    ok = ~np.isnan(r2)
+    assert np.array_equal(o2[ok], r2[ok])
+
+
 def test_philox_device_function(emu, oracle):
     out = np.empty(4, dtype=np.uint32)
     for ctr, key in (((0, 0, 0, 0), (0, 0)), ((0xffffffff,) * 4, (0xffffffff,) * 2),
