@@ -58,7 +58,7 @@ def optimise_routine_sharded(grid, window, xc_list, yc_list, dst=0, **kwargs):
     full = gather_blocks(local, n, dst=dst)
     if full is None:
         return None
-    return list(np.ascontiguousarray(full.cpu().numpy().T))
+    return list(full.t().contiguous().cpu().numpy())           # transposed on the device: four (n,) rows
 
 
 def metropolis_hastings_sharded(grid, window, xc_list, yc_list, nsim, burnin, dst=0, **kwargs):

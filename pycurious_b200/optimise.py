@@ -300,8 +300,8 @@ class CurieOptimise(CurieGrid):
             b.apply_defaults()
             a = b.arguments
             k, phi, _ = self._batch_spectra(window, xc_list, yc_list, a["taper"], a["process_subgrid"], a["kwargs"])
-            x = self._fit_device(k, phi, (a["beta"], a["zt"], a["dz"], a["C"])).cpu().numpy()
-            return list(np.ascontiguousarray(x.T))
+            x = self._fit_device(k, phi, (a["beta"], a["zt"], a["dz"], a["C"]))
+            return list(x.t().contiguous().cpu().numpy())          # transposed on the device: four (n,) rows
 
         if self._is_own(func, "metropolis_hastings"):
             b = inspect.signature(CurieOptimise.metropolis_hastings).bind(self, window, 0.0, 0.0, *args, **kwargs)
