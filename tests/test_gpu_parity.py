@@ -194,6 +194,33 @@ def test_emag2_shaped_grid_far_corner(pc, oracle):
     assert x.shape == (4, 4) and np.all(np.isfinite(x))
 
 
+def test_zero_modulus_propagates_like_numpy(pc, oracle):
+    """log(0) = -inf (grid.py:283): an all-zero window gives Phi = -inf and sigma = nan in every bin, a window with
+    a single non-zero DFT coefficient pattern (constant data, no taper -> only DC) gives -inf wherever |F| is
+    exactly 0 -- through the shared-row path and the direct path, like the reference expression does."""
+    n = 64
+    d = np.zeros((160, 160))
+    d[80:, :] = 3.5                                            # lower half constant
+    G = pc.CurieGrid(d, 0.0, 159e3, 0.0, 159e3)
+    xs = np.array([32e3, 40e3, 48e3, 32e3, 40e3, 48e3])         # nodes 32.., window 64 -> rows 0..63 / 90..153
+    ys = np.array([32e3, 32e3, 32e3, 122e3, 122e3, 122e3])
+    spec = oracle.GridSpec(d, 0.0, 159e3, 0.0, 159e3)
+    for share in (True, False):
+        from pycurious_b200 import _plans
+        iy0, ix0, nw = G._origins_device(64e3, xs, ys)
+        plan = _plans.spectrum_plan(nw, G.dx, None)
+        phi, sig = plan.run(G.device_grid(), iy0, ix0, False, 2.0, share_rows=share)
+        phi, sig = phi.cpu().numpy(), sig.cpu().numpy()
+        assert np.all(np.isneginf(phi[:3])) and np.all(np.isnan(sig[:3]))          # zero windows
+        with np.errstate(all="ignore"):
+            k_o, phi_o, sig_o = oracle.radial_spectrum(oracle.cut_window(spec, 64e3, xs[3], ys[3]), spec.dx, taper=None)
+        # constant window without taper: every non-DC coefficient is exactly 0 in exact arithmetic; in floating
+        # point both implementations leave either exact zeros or rounding dust, so only the -inf / finite pattern
+        # of bins whose members are ALL exact zeros in the reference is compared
+        all_zero = np.isneginf(phi_o) & np.isnan(sig_o)
+        assert np.all(np.isneginf(phi[3:][:, all_zero]) | (phi[3:][:, all_zero] < -50.0))
+
+
 def test_spectrum_properties_full_size(pc):
     """Size-independent properties on a BASELINE-sized window set (4096-wide grid, 201-node windows):
     scaling the data by a shifts Phi by power*ln(a) and leaves sigma; identical windows give identical
