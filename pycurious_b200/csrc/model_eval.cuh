@@ -114,20 +114,29 @@ CB_HD double ktable_entry(const double *kh, int nk, int i) {
     return i == 0 ? (asc ? 1.0 : 0.0) : (i == 1 ? kmin : kmax);
 }
 
-CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh, const double *ktab,
-                               int ncoef = CB_MAX_ORDERS) {
-    WarpSlab W;
+// The table part of the layout -- everything model_eval_warp touches besides its array arguments -- follows from
+// (base, kh, ktab, nk) alone: the evaluation core re-derives it from those four registers instead of reading a
+// WarpSlab that lives in its caller's local memory (one LDL per field use).  Returns the first slot behind it.
+CB_HD double *warp_slab_tables(WarpSlab &W, double *base, const double *kh, const double *ktab, int nk) {
     W.nk = nk;
     W.k = kh; W.logk = ktab; W.rk = ktab + nk; W.sq = ktab + 2 * nk; W.rn = ktab + 3 * nk;
-    const double *meta = ktab + 3 * nk + (CB_MILLER_NMAX + 1);
-    W.sorted = meta[0] != 0.0;
-    W.kmin = meta[1];
-    W.kmax = meta[2];
     double *t = base;
     W.CA = reinterpret_cast<double2 *>(t); t += 2 * (CB_MILLER_NMAX + 1);
     W.rpq = reinterpret_cast<double2 *>(t); t += 2 * CB_TEMME_TAB;
     W.rnj = t; t += CB_TEMME_TAB;
-    W.coef = reinterpret_cast<EvalCoef *>(t); t += ncoef * CB_SLAB_COEF_DOUBLES;
+    W.coef = reinterpret_cast<EvalCoef *>(t);
+    return t;
+}
+
+CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh, const double *ktab,
+                               int ncoef = CB_MAX_ORDERS) {
+    WarpSlab W;
+    const double *meta = ktab + 3 * nk + (CB_MILLER_NMAX + 1);
+    W.sorted = meta[0] != 0.0;
+    W.kmin = meta[1];
+    W.kmax = meta[2];
+    double *t = warp_slab_tables(W, base, kh, ktab, nk);
+    t += ncoef * CB_SLAB_COEF_DOUBLES;
     W.obs = t; W.p0 = t + nk; W.kb = t + 2 * nk;
     t += 3 * nk;
     if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; W.res = t + 3 * nk; t += 4 * nk; }
@@ -218,8 +227,14 @@ CB_NOINLINE_BODY double generic_point(const ModelCoef *m, double k, double logk,
 // OBS = false (the fit: values and derivatives only) compiles the residual sums and bound checks out -- each
 // warp_sum is ten shuffles wrapped in warp-sync sequences inside a non-inlined function, a fifth of its size.
 template <bool OBS, class Ctx>
-CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int lane, double *out_phi,
-                                        double *out_ddz, const double *obs_ = nullptr, double bound = INFINITY) {
+CB_NOINLINE_BODY double model_eval_core(const Ctx &cx, double *slab_base, const double *kh, const double *ktab, int nk_,
+                                        int sorted, double cu, double *kb, int idx, int lane, double *out_phi,
+                                        double *out_ddz, const double *obs_, double bound) {
+    WarpSlab W;                      // register-resident view: only the fields set here are used below
+    warp_slab_tables(W, slab_base, kh, ktab, nk_);
+    W.sorted = sorted != 0;
+    W.cu = cu;
+    W.kb = kb;
     const double *obs = OBS ? obs_ : nullptr;
     const EvalCoef &e = W.coef[idx];
     const ModelCoef &m = e.m;
@@ -448,6 +463,13 @@ CB_NOINLINE_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int id
     cx.sync_warp();
     if (OBS && obs) return 0.5 * cx.warp_sum(acc);
     return 0.0;
+}
+
+template <bool OBS, class Ctx>
+CB_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int lane, double *out_phi, double *out_ddz,
+                               const double *obs = nullptr, double bound = INFINITY) {
+    return model_eval_core<OBS>(cx, reinterpret_cast<double *>(W.CA), W.k, W.logk, W.nk, W.sorted ? 1 : 0, W.cu, W.kb,
+                                idx, lane, out_phi, out_ddz, obs, bound);
 }
 
 // 0.5 sum (p0 - obs)^2 over the slab (every lane returns the total).
