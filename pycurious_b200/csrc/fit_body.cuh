@@ -382,8 +382,16 @@ CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
 // Pass 1 stages r and the central difference in beta, lane-parallel over the points; in pass 2
 // lane q < 15 (and lane 16+q for the second half of the points) owns ONE of the 15 products and
 // walks the points with broadcast-free strided reads -- no 15-wide butterfly, ~100 instructions.
+// The arrays arrive as one pointer (obs: the arrays obs, p0, kb, pp, pm, dz, res follow each other nk apart) and
+// the k table, not as a WarpSlab reference: see model_eval_core.
+struct FitSlabView { const double *k; double *obs, *p0, *kb, *pp, *pm, *dz, *res; int nk; };
+
 template <class Ctx>
-CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState *S, int lane) {
+CB_NOINLINE_BODY void fit_reduce_core(const Ctx &cx, const double *kh, double *obs0, int nk_, FitState *S, int lane) {
+    FitSlabView W;
+    W.k = kh; W.nk = nk_;
+    W.obs = obs0; W.p0 = obs0 + nk_; W.kb = obs0 + 2 * nk_; W.pp = obs0 + 3 * nk_; W.pm = obs0 + 4 * nk_;
+    W.dz = obs0 + 5 * nk_; W.res = obs0 + 6 * nk_;
     const int L = cx.team_lanes(), nk = W.nk;
     const double hb = S->hb;
     const double rh = 1.0 / hb, rh2 = 0.5 * rh;
@@ -460,6 +468,11 @@ CB_NOINLINE_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState
         }
     }
     cx.sync_warp();
+}
+
+template <class Ctx>
+CB_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState *S, int lane) {
+    fit_reduce_core(cx, W.k, W.obs, W.nk, S, lane);
 }
 
 template <class Ctx>

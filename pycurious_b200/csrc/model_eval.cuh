@@ -176,24 +176,33 @@ CB_HD EvalCoef eval_coef_make(double beta, double zt, double dz, double C) {
 // Coefficients of `count` parameter vectors x + off[idx] e_beta, idx = first .. first+count-1, with
 // off = (0, +hb, -hb): lane l computes vector first+l (the lanes run the same code on different data).
 template <class Ctx>
-CB_NOINLINE_BODY void model_coefs_warp(const Ctx &cx, const WarpSlab &W, const double *x, double hb, int first,
-                                       int count, int lane) {
+CB_NOINLINE_BODY void model_coefs_core(const Ctx &cx, EvalCoef *coef, const double *x, double hb, int first, int count,
+                                       int lane) {
     const int L = cx.team_lanes();
     for (int l = lane; l < count; l += L) {
         const int idx = first + l;
         const double beta = x[0] + (idx == 1 ? hb : (idx == 2 ? -hb : 0.0));
-        W.coef[idx] = eval_coef_make(beta, x[1], x[2], x[3]);
+        coef[idx] = eval_coef_make(beta, x[1], x[2], x[3]);
     }
     cx.sync_warp();
+}
+template <class Ctx>
+CB_BODY void model_coefs_warp(const Ctx &cx, const WarpSlab &W, const double *x, double hb, int first, int count,
+                              int lane) {
+    model_coefs_core(cx, W.coef, x, hb, first, count, lane);      // (pointer argument: see model_eval_core)
 }
 
 // Coefficients of `count` unrelated parameter vectors props[l][0..3] -> slot l, one lane each (the
 // Metropolis-Hastings kernel prepares a block of proposals at once).
 template <class Ctx>
-CB_NOINLINE_BODY void model_coefs_lanes(const Ctx &cx, const WarpSlab &W, const double *props, int count, int lane) {
+CB_NOINLINE_BODY void model_coefs_lanes_core(const Ctx &cx, EvalCoef *coef, const double *props, int count, int lane) {
     const int L = cx.team_lanes();
-    for (int l = lane; l < count; l += L) W.coef[l] = eval_coef_make(props[4 * l], props[4 * l + 1], props[4 * l + 2], props[4 * l + 3]);
+    for (int l = lane; l < count; l += L) coef[l] = eval_coef_make(props[4 * l], props[4 * l + 1], props[4 * l + 2], props[4 * l + 3]);
     cx.sync_warp();
+}
+template <class Ctx>
+CB_BODY void model_coefs_lanes(const Ctx &cx, const WarpSlab &W, const double *props, int count, int lane) {
+    model_coefs_lanes_core(cx, W.coef, props, count, lane);
 }
 
 // 2^-e for |v| = m 2^e, m in [1, 2) (1.0 for zero, subnormal, inf or nan): an exact scale factor.
