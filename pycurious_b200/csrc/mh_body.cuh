@@ -7,6 +7,7 @@
 // counter = (step, block, phase); the stream is replicated on the host by
 // oracle/curie_oracle.py:PhiloxStream so that chains are step-comparable.
 #pragma once
+#include <stddef.h>
 #include "model_eval.cuh"
 
 struct MhParams {
@@ -83,7 +84,7 @@ CB_HD double philox_uniform(uint64_t t, uint32_t ph, uint32_t k0, uint32_t k1) {
 }
 
 // slab of one chain: model arrays, CB_MH_BLOCK coefficient slots, the block's proposals / uniforms / penalties
-CB_HD int mh_slab_doubles(int nk) { return warp_slab_doubles(nk, false, 7 * CB_MH_BLOCK, CB_MH_BLOCK); }
+CB_HD int mh_slab_doubles(int nk) { return warp_slab_doubles(nk, false, 7 * CB_MH_BLOCK + 10, CB_MH_BLOCK); }
 
 #define CB_NEG_LOG_P_FLOOR 227.95592420641054      /* -ln(1e-99), the floor of optimise.py:621 in log space */
 
@@ -103,17 +104,18 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     double *us = props + 4 * CB_MH_BLOCK;       // [CB_MH_BLOCK] acceptance uniforms
     double *pens = us + CB_MH_BLOCK;            // [CB_MH_BLOCK] prior penalties of the proposals
     double *nlu = pens + CB_MH_BLOCK;           // [CB_MH_BLOCK] -ln(u), for the early-rejection bound
+    double *mom = nlu + CB_MH_BLOCK;            // [10] running mean / M2 of (beta, zt, dz, C, zt+dz), lane 0's
 
     const cb_mh_options &o = P.opt;
-    Priors pr;
-    double x[4], scale[4];
+    // Priors and proposal scales are read from the kernel parameters where they are used: state that lives in
+    // registers across the calls of the evaluation core is saved to and restored from local memory around every
+    // call, so the chain carries only x, P0 and f (the moments sit in shared memory, see `fold`).
+    const Priors &pr = *reinterpret_cast<const Priors *>(o.prior_mu);
+    static_assert(offsetof(cb_mh_options, prior_sigma) == offsetof(cb_mh_options, prior_mu) + 4 * sizeof(double),
+                  "Priors mirrors cb_mh_options.prior_mu / prior_sigma");
+    double x[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        pr.mu[j] = o.prior_mu[j];
-        pr.sigma[j] = o.prior_sigma[j];
-        scale[j] = o.x_scale[j];
-        x[j] = P.x0_dev ? P.x0_dev[w * 4 + j] : o.x0[j];
-    }
+    for (int j = 0; j < 4; ++j) x[j] = P.x0_dev ? P.x0_dev[w * 4 + j] : o.x0[j];
     const uint64_t chain = o.chain_offset + (uint64_t)w;
     const uint32_t k0 = (uint32_t)(o.seed ^ chain), k1 = (uint32_t)((o.seed >> 32) ^ (chain >> 32));
 
@@ -133,7 +135,7 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
             double z[4], x1[4];
             philox_normal4((uint64_t)(t0 + l), phase, k0, k1, z);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { x1[j] = x[j] + z[j] * scale[j]; props[4 * l + j] = x1[j]; }
+            for (int j = 0; j < 4; ++j) { x1[j] = x[j] + z[j] * o.x_scale[j]; props[4 * l + j] = x1[j]; }
             pens[l] = prior_penalty(pr, x1);
             us[l] = phase ? philox_uniform((uint64_t)(t0 + l), phase, k0, k1) : 0.0;
             nlu[l] = phase ? -log(us[l]) : 0.0;
@@ -178,18 +180,21 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
     int64_t nacc = 0;
     // Moments (mode 1): the state is recorded once per step but changes on ~10 % of them, so the run of
     // `rep` identical samples is folded in at once (Chan's pairwise update) when the state moves.
-    double mean[5] = {0, 0, 0, 0, 0}, m2[5] = {0, 0, 0, 0, 0};
+    if (lane == 0)
+        for (int j = 0; j < 10; ++j) mom[j] = 0.0;
     int64_t nrec = 0, rep = 0;
     auto fold = [&]() {
         if (rep == 0) return;
-        const double v[5] = {x[0], x[1], x[2], x[3], x[1] + x[2]};
-        const double tot = (double)(nrec + rep);
-        const double wgt = (double)rep / tot, cross = (double)nrec * wgt;
+        if (lane == 0) {
+            const double v[5] = {x[0], x[1], x[2], x[3], x[1] + x[2]};
+            const double tot = (double)(nrec + rep);
+            const double wgt = (double)rep / tot, cross = (double)nrec * wgt;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const double dlt = v[j] - mean[j];
-            mean[j] = fma(dlt, wgt, mean[j]);
-            m2[j] = fma(dlt * dlt, cross, m2[j]);
+            for (int j = 0; j < 5; ++j) {
+                const double dlt = v[j] - mom[j];
+                mom[j] = fma(dlt, wgt, mom[j]);
+                mom[5 + j] = fma(dlt * dlt, cross, mom[5 + j]);
+            }
         }
         nrec += rep;
         rep = 0;
@@ -240,8 +245,8 @@ CB_BODY void mh_body(const Ctx &cx, const MhParams &P) {
             double *mo = P.out + w * 10;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-                mo[j] = mean[j];
-                mo[5 + j] = o.nsim > 0 ? sqrt(m2[j] / (double)o.nsim) : NAN;
+                mo[j] = mom[j];
+                mo[5 + j] = o.nsim > 0 ? sqrt(mom[5 + j] / (double)o.nsim) : NAN;
             }
         }
         if (P.accepted) P.accepted[w] = nacc;
