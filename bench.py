@@ -415,7 +415,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="windows in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mcmc-steps", type=int, default=2000, help="MH steps per chain in the MCMC leg (0 = skip)")
-    ap.add_argument("--mcmc-chains", type=int, default=148 * 64, help="chains (= windows) in the MCMC leg")
+    ap.add_argument("--mcmc-chains", type=int, default=148 * 24 * 4,
+                    help="chains (= windows) in the MCMC leg: four full waves of 24 single-warp CTAs on 148 SMs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
