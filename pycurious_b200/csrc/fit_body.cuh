@@ -391,7 +391,7 @@ CB_NOINLINE_BODY void fit_reduce_core(const Ctx &cx, const double *kh, double *o
     FitSlabView W;
     W.k = kh; W.nk = nk_;
     W.obs = obs0; W.p0 = obs0 + nk_; W.kb = obs0 + 2 * nk_; W.pp = obs0 + 3 * nk_; W.pm = obs0 + 4 * nk_;
-    W.dz = obs0 + 5 * nk_; W.res = obs0 + 6 * nk_;
+    W.dz = obs0 + 5 * nk_; W.res = W.pm;
     const int L = cx.team_lanes(), nk = W.nk;
     const double hb = S->hb;
     const double rh = 1.0 / hb, rh2 = 0.5 * rh;
@@ -401,9 +401,8 @@ CB_NOINLINE_BODY void fit_reduce_core(const Ctx &cx, const double *kh, double *o
         const double p0 = W.p0[i], pp = W.pp[i], pm = use_pm ? W.pm[i] : 0.0;
         const bool fp = isfinite(pp), fm = use_pm && isfinite(pm);
         W.kb[i] = (fp && fm) ? (pp - pm) * rh2 : (fp ? (pp - p0) * rh : (fm ? (p0 - pm) * rh : 0.0));
-        W.res[i] = p0 - W.obs[i];
-        W.pm[i] = Ctx::ldg(W.k + (i));        // Phi(beta - hb) is consumed: the slot now stages k, so that all five
-    }                                         // vectors of pass 2 are in shared memory (ld.shared, no descriptors)
+        W.res[i] = p0 - W.obs[i];             // Phi(beta - hb) is consumed: its slot holds the residuals for pass 2
+    }
     if (lane == 0) S->one = 1.0;
     cx.sync_warp();
     const bool split = (L == 32);
@@ -421,10 +420,9 @@ CB_NOINLINE_BODY void fit_reduce_core(const Ctx &cx, const double *kh, double *o
             va = a + 1;
             vb = t - (a * 4 - (a * (a - 1)) / 2) + a + 1;
         }
-        const double *pa = va == 0 ? W.res : (va == 1 ? W.kb : (va == 2 ? W.pm : (va == 3 ? W.dz : &S->one)));
-        const double *pb = vb == 0 ? W.res : (vb == 1 ? W.kb : (vb == 2 ? W.pm : (vb == 3 ? W.dz : &S->one)));
+        const double *A = va == 0 ? W.res : (va == 1 ? W.kb : (va == 2 ? W.k : (va == 3 ? W.dz : &S->one)));
+        const double *B = vb == 0 ? W.res : (vb == 1 ? W.kb : (vb == 2 ? W.k : (vb == 3 ? W.dz : &S->one)));
         const int sa = va == 4 ? 0 : 1, sb = vb == 4 ? 0 : 1;
-        const auto A = Ctx::shared_view(pa), B = Ctx::shared_view(pb);
         double acc = 0.0;
         if (q < 15) {
 #pragma unroll 4

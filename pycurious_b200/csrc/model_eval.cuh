@@ -84,7 +84,7 @@ struct WarpSlab {          // views into one warp's shared-memory slab
 #define CB_SLAB_COEF_DOUBLES ((int)((sizeof(EvalCoef) + 7) / 8))
 
 CB_HD int warp_slab_doubles(int nk, bool fit, int scratch_doubles = 0, int ncoef = CB_MAX_ORDERS) {
-    int n = (fit ? 7 : 3) * nk + 2 * (CB_MILLER_NMAX + 1) + 3 * CB_TEMME_TAB +
+    int n = (fit ? 6 : 3) * nk + 2 * (CB_MILLER_NMAX + 1) + 3 * CB_TEMME_TAB +
             ncoef * CB_SLAB_COEF_DOUBLES + scratch_doubles;
     return (n + 1) & ~1;      // keep every slab 16-byte aligned
 }
@@ -139,7 +139,7 @@ CB_HD WarpSlab warp_slab_carve(double *base, int nk, bool fit, const double *kh,
     t += ncoef * CB_SLAB_COEF_DOUBLES;
     W.obs = t; W.p0 = t + nk; W.kb = t + 2 * nk;
     t += 3 * nk;
-    if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; W.res = t + 3 * nk; t += 4 * nk; }
+    if (fit) { W.pp = t; W.pm = t + nk; W.dz = t + 2 * nk; W.res = W.pm; t += 3 * nk; }   // res reuses the spent pm slot
     else { W.pp = W.pm = W.dz = W.res = nullptr; }
     W.scratch = t;
     W.cu = 0.0;
