@@ -105,6 +105,19 @@ template <> struct Dft<5> {
     }
 };
 
+// 10 = 2 x 5 with coprime factors: Good-Thomas index maps n = (5 n1 + 2 n2) mod 10, k = (5 k1 + 6 k2) mod 10 turn
+// the 10-point DFT into five 2-point and two 5-point DFTs without any twiddle factor.
+template <> struct Dft<10> {
+    CB_HD static void run(double2 *v) {
+        double2 e[5] = {cadd(v[0], v[5]), cadd(v[2], v[7]), cadd(v[4], v[9]), cadd(v[6], v[1]), cadd(v[8], v[3])};
+        double2 o[5] = {csub(v[0], v[5]), csub(v[2], v[7]), csub(v[4], v[9]), csub(v[6], v[1]), csub(v[8], v[3])};
+        Dft<5>::run(e);
+        Dft<5>::run(o);
+        v[0] = e[0]; v[6] = e[1]; v[2] = e[2]; v[8] = e[3]; v[4] = e[4];
+        v[5] = o[0]; v[1] = o[1]; v[7] = o[2]; v[3] = o[3]; v[9] = o[4];
+    }
+};
+
 template <> struct Dft<8> {
     CB_HD static void run(double2 *v) {
         const double H = 0.70710678118654752440;   // sqrt(1/2)
@@ -194,6 +207,7 @@ CB_HD void bluestein_mid_pass(double2 *buf, const double2 *filt, int n, int lane
     case 3: { constexpr int RR = 3; CALL; } break; \
     case 4: { constexpr int RR = 4; CALL; } break; \
     case 5: { constexpr int RR = 5; CALL; } break; \
+    case 10: { constexpr int RR = 10; CALL; } break; \
     default: { constexpr int RR = 8; CALL; } break; \
     }
 

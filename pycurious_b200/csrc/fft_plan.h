@@ -32,6 +32,10 @@ static inline std::vector<int> smooth_radices(int N) {
     if (c2 == 1) r.push_back(2);
     for (int i = 0; i < c5; ++i) r.push_back(5);
     for (int i = 0; i < c3; ++i) r.push_back(3);
+    // 640 = 8 * 8 * 10: the (2, 5) tail becomes one twiddle-free radix-10 pass (Dft<10>), three passes instead of
+    // four -- the Bluestein length of the 301-node windows of BASELINE config 5.  Only this length, so that every
+    // other size keeps the plan its static engine was built for.
+    if (N == 640) { r.clear(); r.push_back(8); r.push_back(8); r.push_back(10); }
     return r;
 }
 

@@ -41,7 +41,7 @@ class MhOpt(C.Structure):
 
 # ------------------------------------------------------------------------------------ FFT engine
 @pytest.mark.parametrize("n", [4, 5, 6, 8, 9, 10, 15, 16, 25, 27, 30, 64, 100, 101, 125, 128, 129, 151, 201, 240,
-                               256, 301, 305, 401, 625, 1000])
+                               256, 301, 305, 320, 401, 625, 640, 1000])
 def test_fft_engine_matches_numpy(emu, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
@@ -62,8 +62,9 @@ def test_fft_engine_matches_numpy(emu, n):
 
 
 def test_plan_choices_for_baseline_windows(emu, oracle):
-    """none of BASELINE's windows is smooth -> Bluestein on 256 / 320 / 512 / 625."""
-    want = {101: 256, 129: 320, 201: 512, 301: 625}
+    """none of BASELINE's windows is smooth -> Bluestein on 256 / 320 / 512 / 640 (= 8.8.10, three
+    passes with the twiddle-free radix-10 butterfly, instead of 625 = 5^4)."""
+    want = {101: 256, 129: 320, 201: 512, 301: 640}
     for nw, M in want.items():
         _, dk, edges = oracle.taper_and_bins(nw, nw, 1000.0, None)
         _, masks = oracle.radial_bin_masks(nw, dk, edges)
@@ -154,7 +155,7 @@ def test_shared_row_spectra_path_matches_oracle(emu, oracle, mag, nw, taper, det
 
 
 def test_spectrum_static_and_generic_engines_agree(emu, oracle, mag):
-    """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 5.5.5.5) against the runtime-radix engine."""
+    """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 8.8.10) against the runtime-radix engine."""
     d = np.ascontiguousarray(mag[0])
     for nw in (101, 129, 201, 301):
         origins = [(2, 3)]

@@ -164,7 +164,7 @@ def test_window_size_sweep_both_paths(pc, oracle, nw):
 
 def test_emag2_shaped_grid_far_corner(pc, oracle):
     """BASELINE config 5 geometry: a 21600 x 10800 node grid (1.87 GB).  Windows in the far corner address
-    elements beyond 2^31 bytes; all three window sizes (101 / 201 / 301 nodes -> Bluestein 256 / 512 / 625),
+    elements beyond 2^31 bytes; all three window sizes (101 / 201 / 301 nodes -> Bluestein 256 / 512 / 640),
     scattered (direct path) and on a small lattice (shared row spectra)."""
     ny, nx = 10800, 21600
     rng = np.random.default_rng(99)

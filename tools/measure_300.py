@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Spectrum-only and fit-only timings of the 300 km (nw=301, Bluestein 625) windows of config 5 on a 4096^2 grid."""
+"""Spectrum-only and fit-only timings of the 300 km (nw=301, Bluestein 640) windows of config 5 on a 4096^2 grid."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
