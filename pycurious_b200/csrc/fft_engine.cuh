@@ -386,8 +386,8 @@ struct StaticFft {
     static constexpr int FUSED_SPAN = HALF * (N / R0);   // the engine serves windows with n <= FUSED_SPAN
 
     static constexpr int NIT = (N / R0 + CB_WARP - 1) / CB_WARP;    // first-pass butterflies per lane
-    // a second line's inputs fit in registers beside the transform only while they are <= 8 complex values
-    static constexpr bool PREFETCH = FUSED_SPAN > 0 && NIT * HALF <= 8;
+    // a second line's inputs are held in registers beside the transform (12 complex values spill a little and still pay)
+    static constexpr bool PREFETCH = FUSED_SPAN > 0 && NIT * HALF <= 12;
     // line index of input (it, t) of lane `lane` in the first pass
     CB_HD static int input_index(int it, int t, int lane) { return it * CB_WARP + lane + t * (N / R0); }
 
