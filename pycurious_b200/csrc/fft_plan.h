@@ -52,6 +52,9 @@ static inline int bluestein_length(int n) {
         std::vector<int> r = smooth_radices(M);
         if (r.empty() || (int)r.size() > CB_MAX_PASS) continue;
         double c = plan_cost(M, r);
+        // lengths served by a compile-time engine (fft_engine.cuh: 8.8.4, 8.8.5, 8.8.8, 8.8.10 with fused, pruned
+        // first / last passes) run ~1.5x faster per streamed point than the runtime-radix engine
+        if (!(M == 256 || M == 320 || M == 512 || M == 640)) c *= 1.5;
         if (!best || c < best_cost) { best = M; best_cost = c; }
     }
     return best;

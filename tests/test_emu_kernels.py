@@ -64,7 +64,8 @@ def test_fft_engine_matches_numpy(emu, n):
 def test_plan_choices_for_baseline_windows(emu, oracle):
     """none of BASELINE's windows is smooth -> Bluestein on 256 / 320 / 512 / 640 (= 8.8.10, three
     passes with the twiddle-free radix-10 butterfly, instead of 625 = 5^4)."""
-    want = {101: 256, 129: 320, 201: 512, 301: 640}
+    want = {101: 256, 129: 320, 201: 512, 301: 640,
+            175: 512, 151: 320, 281: 640}      # off-list sizes go to a compile-time engine's length too (not 360 / 576)
     for nw, M in want.items():
         _, dk, edges = oracle.taper_and_bins(nw, nw, 1000.0, None)
         _, masks = oracle.radial_bin_masks(nw, dk, edges)
