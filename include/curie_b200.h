@@ -52,6 +52,14 @@ int cb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_op
  * Synchronous; *tflops_out = 2 * DFMA/s / 1e12. */
 int cb_fp64_fma_peak(double *tflops_out);
 
+/* Page-lock / release a caller-owned HOST buffer in place (cudaHostRegisterPortable).  The reference reads
+ * `self.data` live on every call (pycurious/grid.py:142-155); the drop-in therefore uploads the rows a call
+ * needs from the caller's own array each time, and registering that array makes the upload an asynchronous
+ * full-speed DMA with no staging copy.  Registering twice is not an error; failure (read-only mapping,
+ * pinned-memory limit) is reported and the caller falls back to a pageable copy. */
+int cb_host_register(void *host, int64_t bytes);
+int cb_host_unregister(void *host);
+
 /* ------------------------------------------------------------------------
  * Spectrum stage:  CurieGrid.subgrid -> [remove_trend_linear] -> radial_spectrum
  * replaces pycurious/grid.py:112-157 (window gather), :199-216 (plane detrend),

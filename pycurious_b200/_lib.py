@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CB_LIB_PATH") or os.path.join(_HERE, "libcurie_b200.so")   # override: A/B builds
 
 CB_MAX_RADIX_PASSES = 12
+MAX_NK = 512            # radial bins per spectrum the fit / MCMC / misfit kernels hold in a warp slab (csrc/model.cu)
 
 
 class CurieB200Error(RuntimeError):
@@ -50,6 +51,8 @@ SIGNATURES = {
     "cb_last_error": (C.c_char_p, []),
     "cb_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I64)]),
     "cb_fp64_fma_peak": (_I, [C.POINTER(_D)]),
+    "cb_host_register": (_I, [_VP, _I64]),
+    "cb_host_unregister": (_I, [_VP]),
     "cb_spectrum_plan_create": (_I, [_I, _I, _VP, _VP, _VP, _VP, C.POINTER(_VP)]),
     "cb_spectrum_plan_destroy": (_I, [_VP]),
     "cb_spectrum_plan_get_info": (_I, [_VP, C.POINTER(SpectrumPlanInfo)]),

@@ -46,6 +46,34 @@ int cb_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_op
 
 int cb_fp64_fma_peak(double *tflops_out);
 
+// Page-lock a caller-owned host buffer in place (portable: valid for every device of the process) so that
+// uploads from it run asynchronously at full PCIe speed without a staging copy.
+int cb_host_register(void *host, int64_t bytes) {
+    CB_REQUIRE(host != nullptr && bytes > 0, "cb_host_register: NULL buffer or bytes <= 0");
+    int rc = cb_check_device();
+    if (rc) return rc;
+    cudaError_t e = cudaHostRegister(host, (size_t)bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return CB_OK; }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cb_set_error("cudaHostRegister(%lld bytes): %s", (long long)bytes, cudaGetErrorString(e));
+        return CB_ERR_CUDA;
+    }
+    return CB_OK;
+}
+
+int cb_host_unregister(void *host) {
+    CB_REQUIRE(host != nullptr, "cb_host_unregister: NULL buffer");
+    cudaError_t e = cudaHostUnregister(host);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (e == cudaErrorHostMemoryNotRegistered || e == cudaErrorCudartUnloading || e == cudaErrorContextIsDestroyed) return CB_OK;
+        cb_set_error("cudaHostUnregister: %s", cudaGetErrorString(e));
+        return CB_ERR_CUDA;
+    }
+    return CB_OK;
+}
+
 }  // extern "C"
 
 // 16 independent DFMA chains per thread, 4096 iterations: 2 * 16 * 4096 flop per thread.

@@ -46,85 +46,141 @@ class CurieGrid(object):
         # grid.py:109 hands 1.0 to np.allclose as rtol; kept as is
         if not np.allclose(dx, dy, 1.0):
             raise ValueError("node spacing should be identical {}".format((dx, dy)))
-        self._dev_grid = None
-        self._dev_src = None
+        self._held = {}           # device index -> (resident whole-grid tensor, the ndarray it was taken from)
+        self._hold = False
+        self._registered = None   # (ndarray weakref, pinned?) of the last host registration attempt
+        self._pending = []        # upload events the host must wait for before the caller may touch self.data again
 
     # ------------------------------------------------------------------ device residency
-    def device_grid(self):
-        """float64 CUDA copy of `self.data` (uploaded once, re-uploaded if `self.data` is rebound)."""
+    # The reference reads `self.data` live on every call (grid.py:142-155).  So does this class: every call
+    # uploads what it needs from the caller's own array -- the row band its windows cover, or the single window --
+    # and in-place edits of `grid.data` are always seen.  The array is page-locked in place once
+    # (cb_host_register) so that the upload is an asynchronous DMA at PCIe speed (4096^2 float64: ~3 ms).
+    # Residency across calls is an explicit opt-in: `hold_device()`.
+    REGISTER_MIN_BYTES = 8 << 20
+
+    def _host_f64(self):
+        """self.data as a C-contiguous float64 array (self.data itself when it already is one), page-locked."""
+        d = self.data
+        if not (isinstance(d, np.ndarray) and d.dtype == np.float64 and d.flags.c_contiguous):
+            return np.ascontiguousarray(d, dtype=np.float64)
+        reg = self._registered
+        if (reg is None or reg[0]() is not d) and d.nbytes >= self.REGISTER_MIN_BYTES:
+            import weakref
+            _lib.require_cuda()
+            lib = _lib.load()
+            ok = lib.cb_host_register(d.ctypes.data, d.nbytes) == 0
+            if ok:
+                weakref.finalize(d, lib.cb_host_unregister, d.ctypes.data)
+            self._registered = (weakref.ref(d), ok)
+        return d
+
+    def _is_me(self, obj):
+        """`obj` is this grid (or the grid a per-device worker copy of it stands for)."""
+        return obj is self or obj is getattr(self, "_origin", None)
+
+    def _upload(self, host_block):
+        """Asynchronous copy of a contiguous host block to the current device; the event is settled (waited
+        for on the host) before a public method returns, so the caller may modify `self.data` afterwards."""
         torch = _lib.require_cuda()
-        if (self._dev_grid is None or self._dev_src is not self.data
-                or self._dev_grid.device.index != torch.cuda.current_device()):
-            if getattr(self, "_pinned", None) is not None and self._pinned_src is self.data:
-                self._dev_grid = self._pinned.to("cuda", non_blocking=True)
-            else:
-                host = np.ascontiguousarray(self.data, dtype=np.float64)
-                self._dev_grid = torch.from_numpy(host).cuda()
-            self._dev_src = self.data
-        return self._dev_grid
+        t = torch.from_numpy(host_block)
+        if t.is_pinned():
+            dev = t.to("cuda", non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending.append(ev)
+            return dev
+        return t.cuda()
+
+    def _settle(self):
+        while self._pending:
+            self._pending.pop().synchronize()
+
+    def device_grid(self):
+        """float64 CUDA copy of the whole `self.data` on the current device.  A snapshot: it is reused by
+        later calls only after `hold_device()`, and then until `invalidate_device()` / `hold_device(False)`
+        or until `self.data` is rebound."""
+        torch = _lib.require_cuda()
+        dev = torch.cuda.current_device()
+        hit = self._held.get(dev)
+        if hit is not None and hit[1] is self.data and self._hold:
+            return hit[0]
+        g = self._upload(self._host_f64())
+        if self._hold:
+            self._held[dev] = (g, self.data)
+        return g
+
+    def hold_device(self, hold=True):
+        """Opt in to device residency: batch calls reuse one resident copy of the grid instead of uploading
+        the rows they need on every call.  The caller then promises not to modify `self.data` in place (or to
+        call `invalidate_device()` after doing so); rebinding `self.data` is detected."""
+        self._hold = bool(hold)
+        if not hold:
+            self._held = {}
+        return self
 
     def pin_host(self):
-        """Stage `self.data` in page-locked host memory so that uploads run at full PCIe speed
-        (used by bench.py's end-to-end leg; optional)."""
-        torch = _lib.require_cuda()
-        host = np.ascontiguousarray(self.data, dtype=np.float64)
-        self._pinned = torch.from_numpy(host).pin_memory()
-        self._pinned_src = self.data
+        """Page-lock `self.data` in place now (it otherwise happens on the first upload)."""
+        self._host_f64()
         return self
 
     def invalidate_device(self):
-        """Call after modifying `self.data` in place."""
-        self._dev_grid = None
+        """Drop the resident copies (after modifying `self.data` in place while holding the device copy)."""
+        self._held = {}
 
-    def _locate_view(self, arr):
-        """If `arr` is a square, unit-stride view into self.data (what subgrid returns), give its
-        top-left node so the resident device grid can be used instead of an upload."""
-        d = self.data
-        if (not isinstance(arr, np.ndarray) or arr.ndim != 2 or arr.dtype != d.dtype or d.dtype != np.float64
-                or not d.flags.c_contiguous or arr.strides != d.strides or arr.size == 0):
-            return None
-        off = arr.__array_interface__["data"][0] - d.__array_interface__["data"][0]
-        if off < 0 or off % d.itemsize:
-            return None
-        off //= d.itemsize
-        j0, i0 = divmod(off, self.nx)
-        if j0 + arr.shape[0] > self.ny or i0 + arr.shape[1] > self.nx:
-            return None
-        if not np.shares_memory(arr, d):
-            return None
-        return int(j0), int(i0)
+    def _device_region(self, iy0, ix0, n):
+        """Device tensor holding every node the windows at host origins (iy0, ix0) of edge n touch, plus its
+        (row, column) offset in the grid.  Holding: the resident grid.  Otherwise the covering row band is
+        uploaded straight from `self.data` (contiguous), or -- when the windows span less than half the
+        columns -- the covering rectangle (a small host copy first)."""
+        if self._hold:
+            return self.device_grid(), 0, 0
+        host = self._host_f64()
+        r0, r1 = int(iy0.min()), int(iy0.max()) + n
+        c0, c1 = int(ix0.min()), int(ix0.max()) + n
+        if 2 * (c1 - c0) < self.nx:
+            return self._upload(np.ascontiguousarray(host[r0:r1, c0:c1])), r0, c0
+        return self._upload(host[r0:r1]), r0, 0
 
     def _as_device_windows(self, subgrid):
-        """(grid tensor, iy0, ix0) describing one host array as a single device window."""
+        """(grid tensor, iy0, ix0) describing one host array as a single device window (always uploaded:
+        the reference works on the array it is handed)."""
         torch = _lib.require_cuda()
-        loc = self._locate_view(subgrid)
-        if loc is not None:
-            g = self.device_grid()
-            j0, i0 = loc
-        else:
-            g = torch.from_numpy(np.ascontiguousarray(subgrid, dtype=np.float64)).cuda()
-            j0 = i0 = 0
-        iy0 = torch.tensor([j0], dtype=torch.int32, device="cuda")
-        ix0 = torch.tensor([i0], dtype=torch.int32, device="cuda")
+        g = torch.from_numpy(np.ascontiguousarray(subgrid, dtype=np.float64)).cuda()
+        iy0 = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ix0 = torch.zeros(1, dtype=torch.int32, device="cuda")
         return g, iy0, ix0
 
-    def _origins_device(self, window, xc_list, yc_list):
+    def _origins_tensors(self, iy0, ix0, r0, c0):
         torch = _lib.require_cuda()
-        iy0, ix0, n = _plans.window_origins(self, window, xc_list, yc_list)
+        if r0:
+            iy0 = iy0 - np.int32(r0)
+        if c0:
+            ix0 = ix0 - np.int32(c0)
         iy0_t, ix0_t = torch.from_numpy(iy0).cuda(), torch.from_numpy(ix0).cuda()
         iy0_t._cb_host, ix0_t._cb_host = iy0, ix0      # the spectrum plan groups windows by ix0 on the host
-        return (iy0_t, ix0_t, n)
+        return iy0_t, ix0_t
 
-    def _origins_lattice_device(self, window, xs, ys):
-        """_origins_device for the lattice xs x ys: only the per-axis nodes cross to the device, the
+    def _windows_device(self, window, xc_list, yc_list):
+        """(grid tensor, iy0, ix0, n): the device region the centroids' windows live in and their origins
+        relative to it."""
+        iy0, ix0, n = _plans.window_origins(self, window, xc_list, yc_list)
+        g, r0, c0 = self._device_region(iy0, ix0, n)
+        iy0_t, ix0_t = self._origins_tensors(iy0, ix0, r0, c0)
+        return g, iy0_t, ix0_t, n
+
+    def _windows_lattice_device(self, window, xs, ys):
+        """_windows_device for the lattice xs x ys: only the per-axis nodes cross to the device, the
         (rows*cols) origin arrays are expanded there."""
         torch = _lib.require_cuda()
         iyu, ixu, n = _plans.lattice_origins(self, window, xs, ys)
+        g, r0, c0 = self._device_region(iyu, ixu, n)
+        iyu, ixu = iyu - np.int32(r0), ixu - np.int32(c0)
         rows, cols = iyu.size, ixu.size
         iy0_t = torch.from_numpy(iyu).cuda().repeat_interleave(cols)
         ix0_t = torch.from_numpy(ixu).cuda().repeat(rows)
         iy0_t._cb_host, ix0_t._cb_host = np.repeat(iyu, cols), np.tile(ixu, rows)
-        return (iy0_t, ix0_t, n)
+        return g, iy0_t, ix0_t, n
 
     def centroid_lattice(self, window, spacingX=None, spacingY=None):
         """The two axes (xs, ys) of create_centroid_list's meshgrid (grid.py:159-195, before the ravel)."""
@@ -236,7 +292,7 @@ class CurieGrid(object):
         if not isinstance(process_subgrid, functools.partial):
             return None
         f = process_subgrid.func
-        if not (inspect.ismethod(f) and f.__self__ is self):
+        if not (inspect.ismethod(f) and self._is_me(f.__self__)):
             return None
         try:
             if f.__func__ is CurieGrid.upward_continuation:
@@ -264,11 +320,10 @@ class CurieGrid(object):
             return None                       # arguments do not bind: let the host path raise the caller's error
         return None
 
-    def _filter_windows_device(self, filt, iy0_t, ix0_t, n):
-        """Stack [nwin, n, n] (cuda) of the windows at (iy0, ix0) after real(ifft2(filt * fft2(window)))."""
+    def _filter_windows_device(self, filt, g, iy0_t, ix0_t, n):
+        """Stack [nwin, n, n] (cuda) of the windows of `g` at (iy0, ix0) after real(ifft2(filt * fft2(window)))."""
         torch = _lib.require_cuda()
         lib = _lib.load()
-        g = self.device_grid()
         nwin = int(iy0_t.numel())
         plan = _plans.fft_plan(n)
         f_t = torch.from_numpy(np.ascontiguousarray(filt, dtype=np.complex128).view(np.float64)).cuda()
@@ -308,17 +363,19 @@ class CurieGrid(object):
                               as_numpy=True, **kwargs):
         """radial_spectrum for many centroids in one launch: returns (k, Phi[n, nbins], sigma[n, nbins]).
         `detrend=True` is `process_subgrid=self.remove_trend_linear` fused into the gather."""
-        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+        g, iy0, ix0, n = self._windows_device(window, xc_list, yc_list)
         plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
-        phi, sig = plan.run(self.device_grid(), iy0, ix0, detrend, power)
+        phi, sig = plan.run(g, iy0, ix0, detrend, power)
         if as_numpy:
-            return plan.k.copy(), phi.cpu().numpy(), sig.cpu().numpy()
+            phi, sig = phi.cpu().numpy(), sig.cpu().numpy()
+        self._settle()
         return plan.k.copy(), phi, sig
 
     def azimuthal_spectrum_batch(self, window, xc_list, yc_list, *, taper=np.hanning, power=2.0, theta=5.0,
                                  **kwargs):
-        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
-        kbins, S, dtheta = self._azimuthal_device(self.device_grid(), iy0, ix0, n, taper, power, theta, **kwargs)
+        g, iy0, ix0, n = self._windows_device(window, xc_list, yc_list)
+        kbins, S, dtheta = self._azimuthal_device(g, iy0, ix0, n, taper, power, theta, **kwargs)
+        self._settle()
         return kbins, S.cpu().numpy(), dtheta
 
     def tanaka_batch(self, window, xc_list, yc_list, *, kmin_range=(0.05, 0.2), kmax_range=(0.05, 0.2),
@@ -327,26 +384,29 @@ class CurieGrid(object):
         (grid.py:603-699), all on the device.  Returns an (n, 8) array with columns
         Ztr, btr, dZtr, Zor, bor, dZor, Zb, eZb."""
         torch = _lib.require_cuda()
-        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+        g, iy0, ix0, n = self._windows_device(window, xc_list, yc_list)
         plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
-        phi, sig = plan.run(self.device_grid(), iy0, ix0, detrend, 0.5)
+        phi, sig = plan.run(g, iy0, ix0, detrend, 0.5)
         k_t = torch.from_numpy(np.ascontiguousarray(plan.k)).cuda()
         out = torch.empty((phi.shape[0], 8), dtype=torch.float64, device="cuda")
         _lib.check(_lib.load().cb_tanaka_batch(k_t.data_ptr(), k_t.numel(), phi.data_ptr(), sig.data_ptr(),
                                                phi.shape[0], float(kmin_range[0]), float(kmin_range[1]),
                                                float(kmax_range[0]), float(kmax_range[1]), out.data_ptr(),
                                                _lib.stream_ptr(torch)))
-        return out.cpu().numpy() if as_numpy else out
+        out = out.cpu().numpy() if as_numpy else out
+        self._settle()
+        return out
 
     def remove_trend_linear_batch(self, window, xc_list, yc_list):
         torch = _lib.require_cuda()
-        iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
-        g = self.device_grid()
+        g, iy0, ix0, n = self._windows_device(window, xc_list, yc_list)
         out = torch.empty((iy0.numel(), n, n), dtype=torch.float64, device="cuda")
         _lib.check(_lib.load().cb_detrend_batch(g.data_ptr(), g.shape[0], g.shape[1], g.stride(0), n,
                                                 iy0.data_ptr(), ix0.data_ptr(), iy0.numel(), out.data_ptr(),
                                                 _lib.stream_ptr(torch)))
-        return out.cpu().numpy()
+        out = out.cpu().numpy()
+        self._settle()
+        return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -5,8 +5,11 @@ Mirrors the reference's pycurious/optimise.py (v1.1.1): same class, constructor,
 (`bounds`, `prior`, `prior_pdf`, `max_processors`), method signatures, return containers and
 errors.  Where the reference forks `max_processors` workers
 and calls scipy per centroid (optimise.py:386-424), this class launches one kernel for the
-whole centroid list; `max_processors` is kept as an attribute and validated, but no process is
-ever forked (CUDA contexts do not survive fork).
+whole centroid list.  `max_processors` keeps its meaning of "how many workers": the batch fans out
+over min(max_processors, visible GPUs) devices, one host thread per device (no process is ever
+forked: CUDA contexts do not survive fork), and under an initialised `torch.distributed` process
+group (one process per GPU) the same calls shard over the ranks by themselves
+(pycurious_b200/distributed.py).
 
 Differences that are deliberate and documented in DESIGN.md:
   * the optimiser is a bounded quasi-Newton method on the device (csrc/fit_body.cuh), not
@@ -18,15 +21,18 @@ from __future__ import annotations
 
 import ctypes as C
 import inspect
+import threading
 import warnings
 from multiprocessing import cpu_count
 
 import numpy as np
 
 from . import _lib, _plans
+from . import distributed as _pdist
 from .grid import CurieGrid
 
 _KEYS = ("beta", "zt", "dz", "C")
+_RVS_LOCK = threading.Lock()
 
 
 class CurieOptimise(CurieGrid):
@@ -35,14 +41,20 @@ class CurieOptimise(CurieGrid):
     Attributes:
         bounds : list of (lower, upper) for beta, zt, dz, C; None = unbounded
         prior, prior_pdf : dicts keyed by 'beta', 'zt', 'dz', 'C'
-        max_processors : kept for compatibility (validated, never used to fork)
+        max_processors : number of workers (optimise.py:116); here GPUs of this process, capped by the
+                         visible device count
+        shard : True (default) lets batch calls spread over GPUs / ranks; False keeps them on the
+                current device
     """
+
+    MIN_WINDOWS_PER_DEVICE = 2048    # below this a second device costs more (threads, plans, uploads) than it saves
 
     def __init__(self, grid, xmin, xmax, ymin, ymax, **kwargs):
         super(CurieOptimise, self).__init__(grid, xmin, xmax, ymin, ymax)
         self.reset_priors()
         self.bounds = [(0.0, None), (0.0, None), (0.0, None), (None, None)]
         self.max_processors = kwargs.pop("max_processors", cpu_count())
+        self.shard = True
 
     # ------------------------------------------------------------------ priors (optimise.py:120-194)
     def add_prior(self, **kwargs):
@@ -108,9 +120,85 @@ class CurieOptimise(CurieGrid):
                                          mu.ctypes.data, sg.ctypes.data, out.data_ptr(), _lib.stream_ptr(torch)))
         return float(out.item())
 
+    # ------------------------------------------------------------------ fan-out over devices / ranks
+    def _shadow(self):
+        """Per-thread stand-in for `self` on another device: shares the data, priors and bounds, owns its
+        upload bookkeeping."""
+        import copy
+        sh = copy.copy(self)
+        sh._pending = []
+        sh._origin = getattr(self, "_origin", self)
+        return sh
+
+    def _to_host(self, t):
+        """Device tensor -> numpy array through page-locked memory (asynchronous copy + one stream sync)."""
+        import torch
+        if not t.is_cuda:
+            return t.contiguous().numpy()
+        host = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
+
+    def _run_blocks(self, n, block, shard=None, as_numpy=True, min_per_worker=None, transpose=False):
+        """Evaluate `block(obj, lo, hi)` -> device tensor (hi-lo, ...) over range(n) in contiguous blocks and
+        return the concatenation in reference order ((C, n) instead of (n, C) with `transpose`).
+
+          * inside torch.distributed (world > 1): this rank's block, then one all-gather: every rank returns
+            the full result (the reference's fan-out, optimise.py:386-444, across processes)
+          * else over min(max_processors, visible GPUs) devices of this process, one host thread each, every
+            device writing its block of one page-locked result array
+          * else on the current device."""
+        import torch
+        if shard is None:
+            shard = self.shard
+        tr = (lambda t: t.t()) if transpose else (lambda t: t)
+        if shard and _pdist.is_distributed():
+            import torch.distributed as dist
+            lo, hi = _pdist.shard_range(n, dist.get_rank(), dist.get_world_size())
+            full = tr(_pdist.gather_blocks(block(self, lo, hi), n, dst=None))
+            out = self._to_host(full) if as_numpy else full
+            self._settle()
+            return out
+        floor = self.MIN_WINDOWS_PER_DEVICE if min_per_worker is None else min_per_worker
+        ndev = _pdist.device_workers(self.max_processors, n, floor) if shard else 1
+        if ndev > 1:
+            box = {}
+            lock = threading.Lock()
+
+            def work(lo, hi, dev):
+                sh = self._shadow()
+                t = block(sh, lo, hi)
+                with lock:                     # the first block to finish fixes the result's trailing shape
+                    if "host" not in box:
+                        shape = (n,) + tuple(t.shape[1:])
+                        box["host"] = torch.empty(shape[::-1] if transpose else shape, dtype=t.dtype, pin_memory=True)
+                dst = box["host"][..., lo:hi] if transpose else box["host"][lo:hi]
+                dst.copy_(tr(t))
+                sh._settle()
+
+            _pdist.fan_out_devices(ndev, n, work)
+            return box["host"].numpy() if as_numpy else box["host"].cuda()
+        t = tr(block(self, 0, n))
+        out = self._to_host(t) if as_numpy else t
+        self._settle()
+        return out
+
+    def _shared_seed(self, seed):
+        """A concrete seed: the caller's, or one drawn from numpy's global RNG (so np.random.seed makes runs
+        reproducible) -- drawn once per call and, across ranks, taken from rank 0."""
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
+            if self.shard and _pdist.is_distributed():
+                import torch.distributed as dist
+                box = [seed]
+                dist.broadcast_object_list(box, src=0)
+                seed = int(box[0])
+        return int(seed)
+
     # ------------------------------------------------------------------ spectra for a centroid batch
     def _is_detrend(self, process_subgrid):
-        return (inspect.ismethod(process_subgrid) and process_subgrid.__self__ is self
+        return (inspect.ismethod(process_subgrid) and self._is_me(process_subgrid.__self__)
                 and process_subgrid.__func__ is CurieGrid.remove_trend_linear)
 
     def _batch_spectra(self, window, xc_list, yc_list, taper, process_subgrid, kwargs):
@@ -121,14 +209,13 @@ class CurieOptimise(CurieGrid):
         kwargs = dict(kwargs)
         power = kwargs.pop("power", 2.0)
         lattice = xc_list if isinstance(xc_list, _plans.Lattice) else None
-        grid_t = self.device_grid()        # a pending upload (pinned host grid) overlaps the host-side origin work below
         if process_subgrid is None or self._is_detrend(process_subgrid):
             if lattice is not None:
-                iy0, ix0, n = self._origins_lattice_device(window, lattice.xs, lattice.ys)
+                g, iy0, ix0, n = self._windows_lattice_device(window, lattice.xs, lattice.ys)
             else:
-                iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+                g, iy0, ix0, n = self._windows_device(window, xc_list, yc_list)
             plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
-            phi, sig = plan.run(grid_t, iy0, ix0, process_subgrid is not None, power)
+            phi, sig = plan.run(g, iy0, ix0, process_subgrid is not None, power)
             return plan.k, phi, sig
         n_probe = _plans.window_nodes(window, self.dx)[1] * 2 + 1
         filt = self._window_filter(process_subgrid, n_probe)
@@ -159,9 +246,9 @@ class CurieOptimise(CurieGrid):
         its own (one window per n rows)."""
         torch = _lib.require_cuda()
         if lattice is not None:
-            iy0, ix0, n = self._origins_lattice_device(window, lattice.xs, lattice.ys)
+            g, iy0, ix0, n = self._windows_lattice_device(window, lattice.xs, lattice.ys)
         else:
-            iy0, ix0, n = self._origins_device(window, xc_list, yc_list)
+            g, iy0, ix0, n = self._windows_device(window, xc_list, yc_list)
         plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
         nwin = int(iy0.numel())
         phi = torch.empty((nwin, plan.nbins), dtype=torch.float64, device="cuda")
@@ -169,7 +256,7 @@ class CurieOptimise(CurieGrid):
         step = max(1, int(self.FILTER_CHUNK_BYTES // (n * n * 40)))      # 2 complex scratch planes + the real stack
         for a in range(0, nwin, step):
             b = min(a + step, nwin)
-            stack = self._filter_windows_device(filt, iy0[a:b].contiguous(), ix0[a:b].contiguous(), n)
+            stack = self._filter_windows_device(filt, g, iy0[a:b].contiguous(), ix0[a:b].contiguous(), n)
             sy = torch.arange(b - a, dtype=torch.int32, device="cuda") * n
             sx = torch.zeros(b - a, dtype=torch.int32, device="cuda")
             p, s = plan.run(stack.view((b - a) * n, n), sy, sx, False, power, share_rows=False)
@@ -180,6 +267,9 @@ class CurieOptimise(CurieGrid):
     def _fit_device(self, k, phi_t, x0, x0_dev=None, max_iter=0, gtol=0.0, ftol=0.0, diagnostics=False):
         torch = _lib.require_cuda()
         n = phi_t.shape[0]
+        if len(k) > _lib.MAX_NK:
+            raise ValueError("windows with more than {} radial bins (about {} nodes) are not supported by the fit "
+                             "kernel; got {} bins".format(_lib.MAX_NK, 2 * _lib.MAX_NK + 5, len(k)))
         opt = _lib.FitOptions()
         lb, ub = self._bound_arrays()
         mu, sg = self._prior_arrays()
@@ -200,11 +290,16 @@ class CurieOptimise(CurieGrid):
             return x_t, dict(f=f_t, niter=it_t, status=st_t, nfev=nf_t)
         return x_t
 
+    def _fit_block(self, window, xc_list, yc_list, x0, taper, process_subgrid, kwargs):
+        k, phi, _ = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
+        return self._fit_device(k, phi, x0)
+
     def optimise(self, window, xc, yc, beta=3.0, zt=1.0, dz=10.0, C=5.0, taper=np.hanning,
                  process_subgrid=None, **kwargs):
         """Optimal (beta, zt, dz, C) for one centroid; ndarray (4,) like `res.x` (optimise.py:232-301)."""
-        k, phi, _ = self._batch_spectra(window, [xc], [yc], taper, process_subgrid, kwargs)
-        return self._fit_device(k, phi, (beta, zt, dz, C))[0].cpu().numpy()
+        x = self._fit_block(window, [xc], [yc], (beta, zt, dz, C), taper, process_subgrid, kwargs)[0].cpu().numpy()
+        self._settle()
+        return x
 
     def optimise_routine(self, window, xc_list, yc_list, beta=3.0, zt=1.0, dz=10.0, C=5.0, taper=np.hanning,
                          process_subgrid=None, **kwargs):
@@ -213,26 +308,31 @@ class CurieOptimise(CurieGrid):
                                         process_subgrid, **kwargs)
 
     def optimise_batch(self, window, xc_list, yc_list, *, beta=3.0, zt=1.0, dz=10.0, C=5.0, taper=np.hanning,
-                       process_subgrid=None, diagnostics=False, as_numpy=True, **kwargs):
-        """Batched fit returning an (n, 4) array (and optionally solver diagnostics)."""
+                       process_subgrid=None, diagnostics=False, as_numpy=True, shard=None, _rows_out=False, **kwargs):
+        """Batched fit returning an (n, 4) array (and optionally solver diagnostics, current device only)."""
         self._check_lists(xc_list, yc_list)
-        k, phi, _ = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
-        res = self._fit_device(k, phi, (beta, zt, dz, C), diagnostics=diagnostics)
+        x0 = (beta, zt, dz, C)
         if diagnostics:
-            x, diag = res
+            k, phi, _ = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
+            x, diag = self._fit_device(k, phi, x0, diagnostics=True)
             if as_numpy:
-                return x.cpu().numpy(), {kk: v.cpu().numpy() for kk, v in diag.items()}
+                x, diag = x.cpu().numpy(), {kk: v.cpu().numpy() for kk, v in diag.items()}
+            self._settle()
             return x, diag
-        return res.cpu().numpy() if as_numpy else res
+        xc_a, yc_a = np.asarray(xc_list), np.asarray(yc_list)
+        return self._run_blocks(len(xc_a), lambda o, lo, hi: o._fit_block(window, xc_a[lo:hi], yc_a[lo:hi], x0, taper,
+                                                                          process_subgrid, kwargs),
+                                shard=shard, as_numpy=as_numpy, transpose=_rows_out)
 
     # ------------------------------------------------------------------ map assembly
     def curie_depth_maps(self, window, spacingX=None, spacingY=None, *, beta=3.0, zt=1.0, dz=10.0, C=5.0,
                          taper=np.hanning, process_subgrid=None, uncertainty=None, nsim=100, burnin=1000,
-                         x_scale=None, seed=None, as_numpy=True, **kwargs):
+                         x_scale=None, seed=None, as_numpy=True, shard=None, **kwargs):
         """The map workflow of the reference's notebooks in one call: create_centroid_list(window, spacingX,
         spacingY) -> optimise_routine -> reshape to the centroid lattice -> Curie depth zt + dz, optionally
         with uncertainty maps.  The centroid lists are never formed: the lattice axes go to the device and the
-        window origins are expanded there; the (rows, cols) maps are views of the solver's (n, 4) output.
+        window origins are expanded there; the (rows, cols) maps are views of the solver's output.  Several
+        GPUs / ranks split the lattice by whole rows.
 
         uncertainty=None           MAP maps only
         uncertainty='sensitivity'  + population std over `nsim` perturbed re-fits per window (optimise.py:635-725)
@@ -245,34 +345,45 @@ class CurieOptimise(CurieGrid):
         if uncertainty not in (None, "sensitivity", "mcmc"):
             raise ValueError("uncertainty must be None, 'sensitivity' or 'mcmc'")
         xs, ys = self.centroid_lattice(window, spacingX, spacingY)
-        lat = _plans.Lattice(xs, ys)
-        rows, cols = lat.shape
-        k, phi, sig = self._batch_spectra(window, lat, lat, taper, process_subgrid, kwargs)
+        rows, cols = ys.size, xs.size
         x0 = (beta, zt, dz, C)
-        x = self._fit_device(k, phi, x0)
+        if uncertainty is not None:
+            seed = self._shared_seed(seed)
+
+        def block(o, rlo, rhi):                         # lattice rows [rlo, rhi) -> (rhi-rlo, cols, K)
+            lat = _plans.Lattice(xs, ys[rlo:rhi])
+            k, phi, sig = o._batch_spectra(window, lat, lat, taper, process_subgrid, kwargs)
+            x = o._fit_device(k, phi, x0)
+            parts = [x, (x[:, 1] + x[:, 2]).unsqueeze(1)]
+            nloc = x.shape[0]
+            if uncertainty == "sensitivity":
+                std = torch.empty((nloc, 5), dtype=torch.float64, device="cuda")
+                step = max(1, o.SENSITIVITY_ROWS // max(int(nsim), 1))        # bound the perturbed-spectra slab
+                for a in range(0, nloc, step):
+                    b = min(a + step, nloc)
+                    smp = o._sensitivity_device(k, phi[a:b], sig[a:b], nsim, x0, seed, chain_offset=rlo * cols + a)
+                    smp = torch.cat([smp, (smp[..., 1] + smp[..., 2]).unsqueeze(-1)], dim=-1)
+                    std[a:b] = smp.std(dim=1, unbiased=False)
+                parts.append(std)
+            elif uncertainty == "mcmc":
+                mom, acc = o._mh_device(k, phi, nsim, burnin, x_scale, x0, x, seed, 1, chain_offset=rlo * cols)
+                parts += [mom, acc.to(torch.float64).unsqueeze(1)]
+            return torch.cat(parts, dim=1).view(rhi - rlo, cols, -1)
+
+        # the per-device floor is in windows: rows * cols
+        allc = self._run_blocks(rows, block, shard=shard, as_numpy=as_numpy,
+                                min_per_worker=max(1, -(-self.MIN_WINDOWS_PER_DEVICE // max(cols, 1))))
         names = ("beta", "zt", "dz", "C", "curie_depth")
-        cols5 = torch.cat([x, (x[:, 1] + x[:, 2]).unsqueeze(1)], dim=1)
-        maps = {nm: cols5[:, j].reshape(rows, cols) for j, nm in enumerate(names)}
+        maps = {nm: allc[:, :, j] for j, nm in enumerate(names)}
         if uncertainty == "sensitivity":
-            std = torch.empty((rows * cols, 5), dtype=torch.float64, device="cuda")
-            if seed is None:
-                seed = int(np.random.randint(0, 2 ** 62, dtype=np.int64))
-            step = max(1, self.SENSITIVITY_ROWS // max(int(nsim), 1))        # bound the perturbed-spectra slab
-            for a in range(0, rows * cols, step):
-                b = min(a + step, rows * cols)
-                smp = self._sensitivity_device(k, phi[a:b], sig[a:b], nsim, x0, seed, chain_offset=a)
-                smp = torch.cat([smp, (smp[..., 1] + smp[..., 2]).unsqueeze(-1)], dim=-1)
-                std[a:b] = smp.std(dim=1, unbiased=False)
             for j, nm in enumerate(names):
-                maps[nm + "_std"] = std[:, j].reshape(rows, cols)
+                maps[nm + "_std"] = allc[:, :, 5 + j]
         elif uncertainty == "mcmc":
-            mom, acc = self._mh_device(k, phi, nsim, burnin, x_scale, x0, x, seed, 1)
-            self.last_accepted = acc
             for j, nm in enumerate(names):
-                maps[nm + "_mean"] = mom[:, j].reshape(rows, cols)
-                maps[nm + "_std"] = mom[:, 5 + j].reshape(rows, cols)
-        if as_numpy:
-            maps = {nm: v.cpu().numpy() for nm, v in maps.items()}
+                maps[nm + "_mean"] = allc[:, :, 5 + j]
+                maps[nm + "_std"] = allc[:, :, 10 + j]
+            acc = allc[:, :, 15].reshape(-1)
+            self.last_accepted = acc.astype(np.int64) if as_numpy else acc.to(torch.int64)
         maps["xc"], maps["yc"] = xs, ys
         return maps
 
@@ -285,9 +396,10 @@ class CurieOptimise(CurieGrid):
     def parallelise_routine(self, window, xc_list, yc_list, func, *args, **kwargs):
         """Evaluate `func(window, xc, yc, *args, **kwargs)` for every centroid.
 
-        `self.optimise` and `self.metropolis_hastings` are recognised and run as ONE batched device
-        launch over the whole list; any other callable runs as a plain serial loop (the reference's
-        `max_processors == 1` branch) -- nothing is ever forked.  Output containers follow the
+        `self.optimise`, `self.metropolis_hastings` and `self.sensitivity` are recognised and run as batched
+        device launches over the whole list -- spread over min(max_processors, visible GPUs) devices, or over
+        the ranks of an initialised torch.distributed group; any other callable runs as a plain serial loop
+        (the reference's `max_processors == 1` branch) -- nothing is ever forked.  Output containers follow the
         reference: 1-D results -> list of 4 arrays (n,); 2-D results -> list[4] of list[n] arrays."""
         n = len(xc_list)
         self._check_lists(xc_list, yc_list)
@@ -299,9 +411,9 @@ class CurieOptimise(CurieGrid):
             b = inspect.signature(CurieOptimise.optimise).bind(self, window, 0.0, 0.0, *args, **kwargs)
             b.apply_defaults()
             a = b.arguments
-            k, phi, _ = self._batch_spectra(window, xc_list, yc_list, a["taper"], a["process_subgrid"], a["kwargs"])
-            x = self._fit_device(k, phi, (a["beta"], a["zt"], a["dz"], a["C"]))
-            return list(x.t().contiguous().cpu().numpy())          # transposed on the device: four (n,) rows
+            x = self.optimise_batch(window, xc_list, yc_list, beta=a["beta"], zt=a["zt"], dz=a["dz"], C=a["C"],
+                                    taper=a["taper"], process_subgrid=a["process_subgrid"], _rows_out=True, **a["kwargs"])
+            return list(x)                  # transposed on the device: four (n,) rows
 
         if self._is_own(func, "metropolis_hastings"):
             b = inspect.signature(CurieOptimise.metropolis_hastings).bind(self, window, 0.0, 0.0, *args, **kwargs)
@@ -343,6 +455,9 @@ class CurieOptimise(CurieGrid):
     def _mh_device(self, k, phi_t, nsim, burnin, x_scale, x0, x0_dev, seed, reduce_mode, chain_offset=0):
         torch = _lib.require_cuda()
         n = phi_t.shape[0]
+        if len(k) > _lib.MAX_NK:
+            raise ValueError("windows with more than {} radial bins are not supported by the MCMC kernel; got {}"
+                             .format(_lib.MAX_NK, len(k)))
         opt = _lib.MhOptions()
         mu, sg = self._prior_arrays()
         xs = np.ones(4) if x_scale is None else np.asarray(x_scale, dtype=np.float64)
@@ -368,30 +483,52 @@ class CurieOptimise(CurieGrid):
         Burn-in is the reference's tempered greedy climb; bounds are not applied, as in the reference."""
         k, phi, _ = self._batch_spectra(window, [xc], [yc], taper, process_subgrid, kwargs)
         out, _ = self._mh_device(k, phi, nsim, burnin, x_scale, (beta, zt, dz, C), None, seed, 0)
-        return list(out[0].cpu().numpy())
+        res = list(out[0].cpu().numpy())
+        self._settle()
+        return res
 
     def metropolis_hastings_batch(self, window, xc_list, yc_list, nsim, burnin, *, x_scale=None, beta=3.0, zt=1.0,
                                   dz=10.0, C=5.0, x0=None, taper=np.hanning, process_subgrid=None, seed=None,
-                                  reduce="moments", chain_offset=0, as_numpy=True, **kwargs):
-        """One chain per centroid in a single launch.
+                                  reduce="moments", chain_offset=0, as_numpy=True, shard=None, **kwargs):
+        """One chain per centroid in batched launches.
         reduce='chains'  -> array (n, 4, nsim)
         reduce='moments' -> array (n, 10): mean then std of (beta, zt, dz, C, zt+dz), streamed on the device
-        `x0` (n, 4) gives per-window starting points (e.g. the MAP estimates)."""
+        `x0` (n, 4) gives per-window starting points (e.g. the MAP estimates).  The chain id of a window is
+        chain_offset + its index in the list, so the result does not depend on how many GPUs share the list."""
         torch = _lib.require_cuda()
         self._check_lists(xc_list, yc_list)
         if reduce not in ("moments", "chains"):
             raise ValueError("reduce must be 'moments' or 'chains'")
-        k, phi, _ = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
-        x0_dev = None
+        n = len(xc_list)
+        x0_h = None
         if x0 is not None:
-            x0_dev = x0 if hasattr(x0, "data_ptr") else torch.from_numpy(
-                np.ascontiguousarray(x0, dtype=np.float64)).cuda()
-            if tuple(x0_dev.shape) != (phi.shape[0], 4):
+            if tuple(getattr(x0, "shape", np.shape(x0))) != (n, 4):
                 raise ValueError("x0 must have shape (n, 4)")
-        out, acc = self._mh_device(k, phi, nsim, burnin, x_scale, (beta, zt, dz, C), x0_dev, seed,
-                                   0 if reduce == "chains" else 1, chain_offset)
-        self.last_accepted = acc
-        return out.cpu().numpy() if as_numpy else out
+            x0_h = x0
+        seed = self._shared_seed(seed)
+        xc_a, yc_a = np.asarray(xc_list), np.asarray(yc_list)
+        mode = 0 if reduce == "chains" else 1
+        start = (beta, zt, dz, C)
+
+        def block(o, lo, hi):
+            k, phi, _ = o._batch_spectra(window, xc_a[lo:hi], yc_a[lo:hi], taper, process_subgrid, kwargs)
+            x0_dev = None
+            if x0_h is not None:
+                part = x0_h[lo:hi]
+                x0_dev = (part.to("cuda") if hasattr(part, "data_ptr") else
+                          torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64)).cuda()).contiguous()
+                assert x0_dev.dtype == torch.float64
+            out, acc = o._mh_device(k, phi, nsim, burnin, x_scale, start, x0_dev, seed, mode, chain_offset + lo)
+            # the acceptance counts ride along as one more column
+            return torch.cat([out.reshape(hi - lo, -1), acc.to(torch.float64).unsqueeze(1)], dim=1)
+
+        res = self._run_blocks(n, block, shard=shard, as_numpy=as_numpy)
+        acc = res[:, -1]
+        self.last_accepted = acc.astype(np.int64) if as_numpy else acc.to(torch.int64)
+        res = res[:, :-1]
+        if mode == 0:
+            res = res.reshape(n, 4, int(nsim))
+        return np.ascontiguousarray(res) if as_numpy else res.contiguous()
 
     # ------------------------------------------------------------------ sensitivity (optimise.py:635-725)
     def _sensitivity_device(self, k, phi_t, sig_t, nsim, x0, seed, chain_offset=0):
@@ -410,10 +547,11 @@ class CurieOptimise(CurieGrid):
         mu_rows = None
         if any(self.prior_pdf[key] is not None for key in _KEYS):
             mu = np.full((n * nsim, 4), np.nan)
-            for j, key in enumerate(_KEYS):
-                pdf = self.prior_pdf[key]
-                if pdf is not None:
-                    mu[:, j] = np.asarray(pdf.rvs(size=n * nsim), dtype=np.float64)
+            with _RVS_LOCK:                       # scipy's rvs draws from numpy's global RNG
+                for j, key in enumerate(_KEYS):
+                    pdf = self.prior_pdf[key]
+                    if pdf is not None:
+                        mu[:, j] = np.asarray(pdf.rvs(size=n * nsim), dtype=np.float64)
             mu_rows = torch.from_numpy(mu).cuda()
         opt = _lib.FitOptions()
         lb, ub = self._bound_arrays()
@@ -436,20 +574,31 @@ class CurieOptimise(CurieGrid):
         in one launch.  `seed=None` takes the seed from numpy's global RNG."""
         k, phi, sig = self._batch_spectra(window, [xc], [yc], taper, process_subgrid, kwargs)
         x = self._sensitivity_device(k, phi, sig, nsim, (beta, zt, dz, C), seed)
-        return list(np.ascontiguousarray(x[0].cpu().numpy().T))
+        res = list(np.ascontiguousarray(x[0].cpu().numpy().T))
+        self._settle()
+        return res
 
     def sensitivity_batch(self, window, xc_list, yc_list, nsim, *, beta=3.0, zt=1.0, dz=10.0, C=5.0,
                           taper=np.hanning, process_subgrid=None, seed=None, reduce="samples", chain_offset=0,
-                          as_numpy=True, **kwargs):
-        """sensitivity for every centroid in one launch of n*nsim fits.
+                          as_numpy=True, shard=None, **kwargs):
+        """sensitivity for every centroid in batched launches of n*nsim fits.
         reduce='samples' -> (n, nsim, 4);  reduce='moments' -> (n, 8): mean then std (population) of
         (beta, zt, dz, C) over the simulations -- the uncertainty maps of the reference's notebooks."""
+        torch = _lib.require_cuda()
         self._check_lists(xc_list, yc_list)
         if reduce not in ("samples", "moments"):
             raise ValueError("reduce must be 'samples' or 'moments'")
-        k, phi, sig = self._batch_spectra(window, xc_list, yc_list, taper, process_subgrid, kwargs)
-        x = self._sensitivity_device(k, phi, sig, nsim, (beta, zt, dz, C), seed, chain_offset)
-        if reduce == "moments":
-            import torch
-            x = torch.cat([x.mean(dim=1), x.std(dim=1, unbiased=False)], dim=1)
-        return x.cpu().numpy() if as_numpy else x
+        seed = self._shared_seed(seed)
+        xc_a, yc_a = np.asarray(xc_list), np.asarray(yc_list)
+        start = (beta, zt, dz, C)
+
+        def block(o, lo, hi):
+            k, phi, sig = o._batch_spectra(window, xc_a[lo:hi], yc_a[lo:hi], taper, process_subgrid, kwargs)
+            x = o._sensitivity_device(k, phi, sig, nsim, start, seed, chain_offset + lo)
+            if reduce == "moments":
+                return torch.cat([x.mean(dim=1), x.std(dim=1, unbiased=False)], dim=1)
+            return x
+
+        # one device holds n * nsim fits: the per-device floor is in fits
+        return self._run_blocks(len(xc_a), block, shard=shard, as_numpy=as_numpy,
+                                min_per_worker=max(1, self.MIN_WINDOWS_PER_DEVICE // max(int(nsim), 1)))

@@ -751,3 +751,138 @@ def test_c_abi_rejects_bad_arguments(pc, grid):
         grid.optimise_routine(300e3, [grid.xmin + 1e3], [grid.ymin + 1e3])
     with pytest.raises(ValueError, match="same size"):
         grid.optimise_routine(100e3, [150e3, 160e3], [150e3])
+
+
+# --------------------------------------------------------------------------- the reference's smoke tests
+def test_reference_routines_smoke(pc, mag):
+    """tests/test_routines.py:22-59 of the reference: every routine once, in one object lifetime."""
+    d, (xmin, xmax, ymin, ymax) = mag
+    xc, yc = 0.5 * (xmin + xmax), 0.5 * (ymin + ymax)
+    max_window = 300e3
+    cpd = pc.CurieGrid(d, xmin, xmax, ymin, ymax)
+    assert cpd.subgrid(max_window, xc, yc).shape == (301, 301)
+    assert cpd.create_centroid_list(0.1 * max_window)[0].size > 0
+    assert cpd.remove_trend_linear(cpd.data).shape == d.shape
+    k, Phi, sPhi = cpd.radial_spectrum(cpd.data)
+    assert k.shape == Phi.shape == sPhi.shape and np.all(np.isfinite(Phi))
+    kb, S, th = cpd.azimuthal_spectrum(cpd.data)
+    assert S.shape == (th.size, kb.size) and np.all(np.isfinite(S))
+    assert np.all(np.isfinite(cpd.reduce_to_pole(cpd.data, 30.0, 30.0)))
+    assert np.all(np.isfinite(cpd.upward_continuation(cpd.data, 10e3)))
+
+    cpo = pc.CurieOptimise(d, xmin, xmax, ymin, ymax)
+    xc_list, yc_list = cpo.create_centroid_list(0.5 * max_window, spacingX=5e3, spacingY=5e3)
+    assert xc_list.size == 961
+    cpo.add_prior(beta=(3.0, 0.5))
+    x = cpo.optimise(0.5 * max_window, xc_list[0], yc_list[0])
+    assert x.shape == (4,) and np.all(np.isfinite(x))
+    res = cpo.optimise_routine(0.5 * max_window, xc_list, yc_list)
+    assert len(res) == 4 and all(r.shape == (961,) and np.all(np.isfinite(r)) for r in res)
+    np.testing.assert_allclose([r[0] for r in res], x, rtol=1e-9)
+    mh = cpo.metropolis_hastings(0.5 * max_window, xc_list[0], yc_list[0], 100, 10)
+    assert len(mh) == 4 and all(c.shape == (100,) and np.all(np.isfinite(c)) for c in mh)
+    sens = cpo.sensitivity(0.5 * max_window, xc_list[0], yc_list[0], 100)
+    assert len(sens) == 4 and all(c.shape == (100,) and np.all(np.isfinite(c)) for c in sens)
+
+
+def test_min_func_under_scipy_tnc(grid, oracle):
+    """tests/test_optimise.py:63-208 of the reference: its hard-coded 49-point spectrum, `min_func` driven by
+    scipy's TNC from the host (one device evaluation per call).  Goldens: the reference itself on the same
+    vectors (tests/golden/make_golden_tnc.py)."""
+    from scipy.optimize import minimize
+    g = load_golden("tnc.npz")
+    k, S, x0 = g["k"], g["S"], g["x0"]
+    sigma_S = np.ones_like(S)
+    np.testing.assert_allclose(grid.min_func(x0, k, S, sigma_S), float(g["f0"]), rtol=1e-12)
+    np.testing.assert_allclose(grid.min_func(g["x_tnc"], k, S, sigma_S), float(g["f_tnc"]), rtol=1e-10)
+    np.testing.assert_allclose(grid.min_func(g["x_lbfgsb"], k, S, sigma_S), float(g["f_lbfgsb"]), rtol=1e-10)
+    res = minimize(grid.min_func, x0, args=(k, S, sigma_S), method="TNC",
+                   bounds=list(zip(np.zeros_like(x0), [None] * 4)))
+    assert np.all(np.isfinite(res.x)), res.x
+    assert res.fun < 2.0                      # from 3545 at x0 into the valley the reference reaches (0.75 - 0.76)
+    # the device solver on the same spectrum: never worse than either reference optimiser
+    import torch
+    x = grid._fit_device(k, torch.from_numpy(S[None, :].copy()).cuda(), tuple(x0)).cpu().numpy()[0]
+    f_us = oracle.misfit(x, k, S)
+    assert f_us <= float(g["f_lbfgsb"]) * (1 + 1e-9) and f_us <= float(g["f_tnc"])
+    assert x[1] == 0.0                        # zt pinned on its bound, like the reference's result
+
+
+# --------------------------------------------------------------------------- live data, residency, several GPUs
+def test_in_place_edits_of_data_are_seen(pc, mag):
+    """The reference reads `grid.data` live (grid.py:142-155): in-place edits between two calls must show."""
+    d, ext = mag
+    G = pc.CurieOptimise(d.copy(), *ext)
+    xc, yc = G.create_centroid_list(100e3, 50e3, 50e3)
+    k, phi1, sig1 = G.radial_spectrum_batch(100e3, xc, yc)
+    x1 = np.stack(G.optimise_routine(100e3, xc, yc), axis=1)
+    keep = G.data
+    G.data *= 2.0                                        # same ndarray object
+    assert G.data is keep
+    _, phi2, sig2 = G.radial_spectrum_batch(100e3, xc, yc)
+    np.testing.assert_allclose(phi2, phi1 + 2.0 * np.log(2.0), rtol=1e-12)
+    np.testing.assert_allclose(sig2, sig1, rtol=1e-9)
+    x2 = np.stack(G.optimise_routine(100e3, xc, yc), axis=1)
+    np.testing.assert_allclose(x2[:, 3], x1[:, 3] + 2.0 * np.log(2.0), rtol=1e-5)     # C absorbs the scale
+    np.testing.assert_allclose(x2[:, :3], x1[:, :3], rtol=1e-3, atol=1e-6)
+    s = G.subgrid(100e3, xc[3], yc[3])                   # a view: edits through it show in both directions
+    _, p_a, _ = G.radial_spectrum(s)
+    s *= 0.5
+    _, p_b, _ = G.radial_spectrum(s)
+    np.testing.assert_allclose(p_b, p_a - 2.0 * np.log(2.0), rtol=1e-12)
+    # opt-in residency: a held copy is a snapshot until it is invalidated
+    G.hold_device()
+    _, h1, _ = G.radial_spectrum_batch(100e3, xc, yc)
+    G.data += 1000.0
+    _, h2, _ = G.radial_spectrum_batch(100e3, xc, yc)
+    assert np.array_equal(h1, h2)
+    G.invalidate_device()
+    _, h3, _ = G.radial_spectrum_batch(100e3, xc, yc)
+    assert not np.array_equal(h1, h3)
+    G.hold_device(False)
+    _, h4, _ = G.radial_spectrum_batch(100e3, xc, yc)
+    assert np.array_equal(h3, h4)
+
+
+def test_region_upload_equals_resident_grid(pc, mag):
+    """Row-band / rectangle uploads (the default) give the same bits as the resident whole grid."""
+    d, ext = mag
+    G = pc.CurieOptimise(d, *ext)
+    H = pc.CurieOptimise(d, *ext).hold_device()
+    cases = [G.create_centroid_list(100e3, 10e3, 10e3),                      # lattice: whole-width band
+             (np.array([60.5e3, 70e3, 81e3]), np.array([250e3, 240e3, 251e3])),   # a corner: rectangle
+             (np.array([152e3]), np.array([152e3]))]                              # single window
+    for xc, yc in cases:
+        a = G.radial_spectrum_batch(100e3, xc, yc)
+        b = H.radial_spectrum_batch(100e3, xc, yc)
+        assert all(np.array_equal(u, v) for u, v in zip(a, b))
+        assert np.array_equal(G.optimise_batch(100e3, xc, yc), H.optimise_batch(100e3, xc, yc))
+    m1 = G.curie_depth_maps(100e3, 20e3, 20e3)
+    m2 = H.curie_depth_maps(100e3, 20e3, 20e3)
+    assert all(np.array_equal(m1[key], m2[key]) for key in m1)
+
+
+def test_max_processors_fans_out_over_gpus(pc, mag):
+    """`CurieOptimise(..., max_processors=N)` (optimise.py:116) spreads a centroid list over min(N, visible GPUs)
+    devices, one host thread each; results are identical to the one-GPU run, in reference order."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two visible GPUs")
+    d, ext = mag
+    one = pc.CurieOptimise(d, *ext, max_processors=1)
+    many = pc.CurieOptimise(d, *ext, max_processors=ndev)
+    many.MIN_WINDOWS_PER_DEVICE = 8
+    xc, yc = one.create_centroid_list(100e3, 10e3, 10e3)
+    r1, rn = one.optimise_routine(100e3, xc, yc), many.optimise_routine(100e3, xc, yc)
+    assert all(np.array_equal(a, b) for a, b in zip(r1, rn))
+    for g in (one, many):
+        g.add_prior(beta=(3.0, 1.0), dz=(20.0, 10.0))
+    m1 = one.metropolis_hastings_batch(100e3, xc, yc, 300, 50, x_scale=[0.25, 0.1, 1.0, 0.5], seed=7)
+    mn = many.metropolis_hastings_batch(100e3, xc, yc, 300, 50, x_scale=[0.25, 0.1, 1.0, 0.5], seed=7)
+    assert np.array_equal(m1, mn) and np.array_equal(one.last_accepted, many.last_accepted)
+    c1 = one.curie_depth_maps(100e3, 10e3, 10e3, uncertainty="mcmc", nsim=200, burnin=50, seed=3)
+    cn = many.curie_depth_maps(100e3, 10e3, 10e3, uncertainty="mcmc", nsim=200, burnin=50, seed=3)
+    assert all(np.array_equal(c1[key], cn[key]) for key in c1)
+    ch = many.parallelise_routine(100e3, xc[:40], yc[:40], many.metropolis_hastings, 50, 10, seed=5)
+    assert len(ch) == 4 and len(ch[0]) == 40 and ch[0][0].shape == (50,)

@@ -108,7 +108,6 @@ def test_subgrid_and_centroids_match_reference(pc, mag):
     for (xc, yc), (j0, i0, nn) in zip(pts[:50], org[:50]):
         s = G.subgrid(100e3, xc, yc)
         assert s.shape == (nn, nn) and np.shares_memory(s, G.data)
-        assert G._locate_view(s) == (j0, i0)
     rng = np.random.default_rng(0)
     q = rng.uniform(ext[0], ext[1], 2000)
     want = np.array([np.abs(G.xcoords - v).argmin() for v in q])
@@ -317,3 +316,30 @@ def test_process_subgrid_filter_recognition(pc):
         assert G._window_filter(cb, 21) is None
     with pytest.warns(UserWarning, match="downward continuation"):
         G._window_filter(functools.partial(G.upward_continuation, height=-1.0), 21)
+
+
+def test_device_region_covers_windows(monkeypatch, mag):
+    """CurieGrid._device_region: the uploaded row band / rectangle plus the shifted origins address exactly the
+    nodes `subgrid` would return (host logic only: the upload is replaced by a CPU tensor)."""
+    import torch
+    import pycurious_b200 as pc
+    from pycurious_b200 import _lib, _plans
+    d, ext = mag
+    G = pc.CurieGrid(d, *ext)
+    monkeypatch.setattr(_lib, "require_cuda", lambda: torch)
+    monkeypatch.setattr(pc.CurieGrid, "_upload", lambda self, block: torch.from_numpy(np.ascontiguousarray(block)))
+    monkeypatch.setattr(pc.CurieGrid, "_origins_tensors",
+                        lambda self, iy0, ix0, r0, c0: (iy0 - np.int32(r0), ix0 - np.int32(c0)))
+    cases = [G.create_centroid_list(100e3, 25e3, 25e3),
+             (np.array([60.5e3, 70e3, 81e3]), np.array([250e3, 240e3, 251e3])),
+             (np.array([152e3]), np.array([152e3])),
+             (np.array([50.5e3, 250.5e3]), np.array([50.5e3, 250.5e3]))]
+    shapes = []
+    for xc, yc in cases:
+        g, iy0, ix0, n = G._windows_device(100e3, xc, yc)
+        shapes.append(tuple(g.shape))
+        for i in range(len(xc)):
+            win = g[int(iy0[i]):int(iy0[i]) + n, int(ix0[i]):int(ix0[i]) + n].numpy()
+            assert np.array_equal(win, G.subgrid(100e3, xc[i], yc[i]))
+    assert shapes[0] == (301, 305) and shapes[2] == (101, 101) and shapes[3] == (301, 305)
+    assert shapes[1][0] < 120 and shapes[1][1] < 130
