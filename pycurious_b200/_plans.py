@@ -186,11 +186,31 @@ class SpectrumPlan:
                                                C.byref(handle)))
         self.handle = handle
         self._finalizer = weakref.finalize(self, lib.cb_spectrum_plan_destroy, handle)
-        nbytes = int(lib.cb_spectrum_workspace_bytes(handle))
-        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        self._ws_bytes = int(lib.cb_spectrum_workspace_bytes(handle))
         self.device = torch.cuda.current_device()
-        self._rowspec = None
+        # scratch (per-CTA slabs, shared row spectra) belongs to the stream it is used on: two run() calls under
+        # different torch.cuda.stream contexts must not share it
+        self._scratch = {}
         self.last_path = "direct"
+
+    def _stream_scratch(self, torch, stream, rowspec_bytes=0):
+        """[workspace, rowspec] of the CUDA stream `stream` (created / grown on demand)."""
+        sc = self._scratch.get(stream)
+        if sc is None:
+            if len(self._scratch) >= 8:                 # a caller cycling through many streams: drop the idle ones
+                torch.cuda.synchronize()
+                self._scratch.clear()
+            sc = [torch.empty(self._ws_bytes, dtype=torch.uint8, device="cuda"), None]
+            self._scratch[stream] = sc
+        if rowspec_bytes and (sc[1] is None or sc[1].numel() < rowspec_bytes):
+            sc[1] = None
+            sc[1] = torch.empty(rowspec_bytes, dtype=torch.uint8, device="cuda")
+        return sc
+
+    @property
+    def workspace(self):
+        torch = _lib.require_cuda()
+        return self._stream_scratch(torch, _lib.stream_ptr(torch))[0]
 
     def info(self):
         info = _lib.SpectrumPlanInfo()
@@ -286,10 +306,11 @@ class SpectrumPlan:
             except AttributeError:
                 pass
         if prep is None or prep == "direct":
+            ws = self._stream_scratch(torch, stream)[0]
             _lib.check(lib.cb_spectrum_batch(
                 self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0), iy0_t.data_ptr(), ix0_t.data_ptr(), n,
                 1 if detrend else 0, float(power), phi.data_ptr(), sig.data_ptr(),
-                self.workspace.data_ptr(), self.workspace.numel(), stream))
+                ws.data_ptr(), ws.numel(), stream))
             self.last_path = "direct"
             return phi, sig
 
@@ -299,15 +320,13 @@ class SpectrumPlan:
             ix_c = ix0_t if whole else c["ix_c"]
             out_phi = phi if whole else torch.empty((int(iy_c.numel()), self.nbins), dtype=torch.float64, device="cuda")
             out_sig = sig if whole else torch.empty_like(out_phi)
-            if self._rowspec is None or self._rowspec.numel() < c["need"]:
-                self._rowspec = None
-                self._rowspec = torch.empty(c["need"], dtype=torch.uint8, device="cuda")
+            ws, rowspec = self._stream_scratch(torch, stream, c["need"])
             _lib.check(lib.cb_spectrum_batch_shared_rows(
                 self.handle, grid_t.data_ptr(), ny, nx, grid_t.stride(0), iy_c.data_ptr(), ix_c.data_ptr(),
                 int(iy_c.numel()), c["gof_t"].data_ptr(), c["gix_t"].data_ptr(), c["ngroups"], c["order_t"].data_ptr(),
                 c["lo"], c["hi"], 1 if detrend else 0,
-                float(power), out_phi.data_ptr(), out_sig.data_ptr(), self._rowspec.data_ptr(), self._rowspec.numel(),
-                self.workspace.data_ptr(), self.workspace.numel(), stream))
+                float(power), out_phi.data_ptr(), out_sig.data_ptr(), rowspec.data_ptr(), rowspec.numel(),
+                ws.data_ptr(), ws.numel(), stream))
             if not whole:
                 phi.index_copy_(0, c["sel_t"], out_phi)
                 sig.index_copy_(0, c["sel_t"], out_sig)

@@ -28,6 +28,18 @@ int cb_check_device();   // CB_OK or CB_ERR_NO_DEVICE
         }                                                                          \
     } while (0)
 
+// CB_CUDA_TRY that runs `cleanup` before returning (owned allocations on an error path)
+#define CB_CUDA_TRY_OR(expr, cleanup)                                              \
+    do {                                                                           \
+        cudaError_t _e = (expr);                                                   \
+        if (_e != cudaSuccess) {                                                   \
+            cb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                         __FILE__, __LINE__);                                      \
+            cleanup;                                                               \
+            return CB_ERR_CUDA;                                                    \
+        }                                                                          \
+    } while (0)
+
 #define CB_REQUIRE(cond, msg)                                                      \
     do {                                                                           \
         if (!(cond)) {                                                             \

@@ -70,8 +70,8 @@ int cb_fft_plan_create(int n, cb_fft_plan **out) {
     if (p->bluestein) filt.resize(p->line_slots, cplx(0.0, 0.0));
     int dev = 0;
     cudaDeviceProp prop;
-    CB_CUDA_TRY(cudaGetDevice(&dev));
-    CB_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    CB_CUDA_TRY_OR(cudaGetDevice(&dev), delete p);
+    CB_CUDA_TRY_OR(cudaGetDeviceProperties(&prop, dev), delete p);
     p->sm_count = prop.multiProcessorCount;
     const int64_t line_bytes = (int64_t)p->line_slots * 16;
     const int teams = (int)std::min<int64_t>(16, (int64_t)prop.sharedMemPerBlockOptin / line_bytes);
@@ -88,8 +88,8 @@ int cb_fft_plan_create(int n, cb_fft_plan **out) {
         cb_fft_plan_destroy(p);
         return rc;
     }
-    CB_CUDA_TRY(cudaFuncSetAttribute(line_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)prop.sharedMemPerBlockOptin));
+    CB_CUDA_TRY_OR(cudaFuncSetAttribute(line_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)prop.sharedMemPerBlockOptin), cb_fft_plan_destroy(p));
     *out = p;
     return CB_OK;
 }

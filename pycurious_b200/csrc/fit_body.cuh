@@ -19,7 +19,8 @@
 //
 // The reference's stopping point is set by its own noisy forward-difference gradient (factr 1e7,
 // pgtol 1e-5); this solver converges to the same bounded minimum more tightly, so on windows where
-// the reference is converged the parameters agree to ~1e-5 relative (tests/test_fit_parity.py).
+// the reference is converged the parameters agree to ~1e-5 relative (tests/test_gpu_parity.py::_check_fit,
+// tests/test_gpu_config3.py; reference self-sensitivity on the rest: tests/golden/make_golden_cfg3.py).
 #pragma once
 #include "model_eval.cuh"
 

@@ -132,17 +132,23 @@ int cb_azimuthal_tail_batch(const double *sinogram_dev, int nw, int ntheta, int6
     double *d_taper = nullptr;
     if (taper_host) {
         CB_CUDA_TRY(cudaMallocAsync((void **)&d_taper, (size_t)nw * sizeof(double), (cudaStream_t)stream));
-        CB_CUDA_TRY(cudaMemcpyAsync(d_taper, taper_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice,
-                                    (cudaStream_t)stream));
+        CB_CUDA_TRY_OR(cudaMemcpyAsync(d_taper, taper_host, (size_t)nw * sizeof(double), cudaMemcpyHostToDevice,
+                                       (cudaStream_t)stream), cudaFreeAsync(d_taper, (cudaStream_t)stream));
     }
     AzTailParams P{sinogram_dev, nw, ntheta, nkb, nwin, d_taper, power, S_dev};
     const int nk = 1 + 2 * nkb;
     const size_t smem = (size_t)nk * sizeof(double2) + (size_t)nw * sizeof(double);
-    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(az_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    auto drop = [&]() { if (d_taper) cudaFreeAsync(d_taper, (cudaStream_t)stream); };
+    if (smem > 48 * 1024)
+        CB_CUDA_TRY_OR(cudaFuncSetAttribute(az_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), drop());
     const int64_t grid = nwin * ntheta;
-    CB_REQUIRE(grid <= 2147483647LL, "batch too large for one launch");
+    if (grid > 2147483647LL) {
+        drop();
+        cb_set_error("invalid argument: batch too large for one launch");
+        return CB_ERR_INVALID;
+    }
     az_tail_kernel<<<(int)grid, 128, smem, (cudaStream_t)stream>>>(P);
-    CB_CUDA_TRY(cudaGetLastError());
+    CB_CUDA_TRY_OR(cudaGetLastError(), drop());
     if (d_taper) CB_CUDA_TRY(cudaFreeAsync(d_taper, (cudaStream_t)stream));
     return CB_OK;
 }

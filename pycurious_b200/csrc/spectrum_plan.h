@@ -124,7 +124,8 @@ static inline bool spectrum_plan_build_host(SpectrumHostPlan &hp, int nw, int nb
             else hi_start[v] = std::min(hi_start[v], u);
         }
         hp.col_span.resize(hp.nvh);
-        for (int v = 0; v < hp.nvh; ++v) hp.col_span[v] = (lo_end[v] < 0 ? 0xffff : lo_end[v]) | (hi_start[v] << 16);
+        for (int v = 0; v < hp.nvh; ++v)
+            hp.col_span[v] = (int32_t)((uint32_t)(lo_end[v] < 0 ? 0xffff : lo_end[v]) | ((uint32_t)hi_start[v] << 16));
     }
 
     hp.line_slots = (fft_line_slots(hp.fft.n) + 1) & ~1;

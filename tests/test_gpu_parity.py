@@ -886,3 +886,24 @@ def test_max_processors_fans_out_over_gpus(pc, mag):
     assert all(np.array_equal(c1[key], cn[key]) for key in c1)
     ch = many.parallelise_routine(100e3, xc[:40], yc[:40], many.metropolis_hastings, 50, 10, seed=5)
     assert len(ch) == 4 and len(ch[0]) == 40 and ch[0][0].shape == (50,)
+
+
+def test_two_streams_do_not_share_scratch(pc, mag):
+    """Spectrum plans are cached per (size, taper, device); their scratch is per CUDA stream, so batches issued
+    under two torch.cuda.stream contexts may overlap on the device."""
+    import torch
+    d, ext = mag
+    G = pc.CurieOptimise(d, *ext)
+    xa, ya = G.create_centroid_list(100e3, 4e3, 4e3)
+    xb, yb = xa[::-1].copy(), ya[::-1].copy()
+    _, pa, sa = G.radial_spectrum_batch(100e3, xa, ya)
+    _, pb, sb = G.radial_spectrum_batch(100e3, xb, yb, detrend=True)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            _, qa, ta = G.radial_spectrum_batch(100e3, xa, ya, as_numpy=False)
+        with torch.cuda.stream(s2):
+            _, qb, tb = G.radial_spectrum_batch(100e3, xb, yb, detrend=True, as_numpy=False)
+        torch.cuda.synchronize()
+        assert np.array_equal(qa.cpu().numpy(), pa) and np.array_equal(ta.cpu().numpy(), sa)
+        assert np.array_equal(qb.cpu().numpy(), pb) and np.array_equal(tb.cpu().numpy(), sb)

@@ -226,14 +226,17 @@ def test_bench_contract_keys():
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
-    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    want = "reference" if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "pycurious", "optimise.py")) else "port"
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == want
+    assert d["scaling"] == "strong" and d["config"]["windows_total"] > 0
     src = open(os.path.join(ROOT, "bench.py")).read()
     gpu_line = src[src.index('line = {"metric": METRIC'):src.index("emit(json.dumps(line))")]
     code = "\n".join(l.split("#")[0] for l in gpu_line.splitlines())       # a comment must not swallow a key
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "stages",
-                "cpu_baseline", "mcmc"):
+                "cpu_baseline", "mcmc", "weak", "check", "config2", "config5"):
         assert '"%s"' % key in code, key
+    assert "NCCL_DEBUG" not in "\n".join(l for l in src.splitlines() if "environ" in l)     # NCCL's log stays as the caller set it
 
 
 def test_lattice_fast_path_equals_generic_rule(pc):
