@@ -161,6 +161,11 @@ class CurieGrid(object):
         iy0_t._cb_host, ix0_t._cb_host = iy0, ix0      # the spectrum plan groups windows by ix0 on the host
         return iy0_t, ix0_t
 
+    def _origins_device(self, window, xc_list, yc_list):
+        """(iy0, ix0, n) as device tensors relative to the WHOLE grid (to be paired with `device_grid()`)."""
+        iy0, ix0, n = _plans.window_origins(self, window, xc_list, yc_list)
+        return self._origins_tensors(iy0, ix0, 0, 0) + (n,)
+
     def _windows_device(self, window, xc_list, yc_list):
         """(grid tensor, iy0, ix0, n): the device region the centroids' windows live in and their origins
         relative to it."""
