@@ -135,9 +135,10 @@ class CurieGrid(object):
         columns -- the covering rectangle (a small host copy first)."""
         if self._hold:
             return self.device_grid(), 0, 0
+        return self._upload_box(int(iy0.min()), int(iy0.max()) + n, int(ix0.min()), int(ix0.max()) + n)
+
+    def _upload_box(self, r0, r1, c0, c1):
         host = self._host_f64()
-        r0, r1 = int(iy0.min()), int(iy0.max()) + n
-        c0, c1 = int(ix0.min()), int(ix0.max()) + n
         if 2 * (c1 - c0) < self.nx:
             return self._upload(np.ascontiguousarray(host[r0:r1, c0:c1])), r0, c0
         return self._upload(host[r0:r1]), r0, 0
@@ -168,9 +169,23 @@ class CurieGrid(object):
 
     def _windows_device(self, window, xc_list, yc_list):
         """(grid tensor, iy0, ix0, n): the device region the centroids' windows live in and their origins
-        relative to it."""
-        iy0, ix0, n = _plans.window_origins(self, window, xc_list, yc_list)
-        g, r0, c0 = self._device_region(iy0, ix0, n)
+        relative to it.  The region follows from the extreme centroids alone, so its upload is started first
+        and runs while the host resolves the origins of the whole list."""
+        if self._hold:
+            iy0, ix0, n = _plans.window_origins(self, window, xc_list, yc_list)
+            g, r0, c0 = self.device_grid(), 0, 0
+        else:
+            xa, ya = np.atleast_1d(np.asarray(xc_list, dtype=np.float64)), np.atleast_1d(np.asarray(yc_list, dtype=np.float64))
+            if xa.size == 0 or xa.size != ya.size:
+                raise ValueError("xc_list and yc_list must be non-empty and the same size")
+            try:
+                ends_y, ends_x, n = _plans.window_origins(self, window, np.array([xa.min(), xa.max()]),
+                                                          np.array([ya.min(), ya.max()]))
+            except ValueError:                      # let the full pass name the first offending centroid
+                _plans.window_origins(self, window, xa, ya)
+                raise
+            g, r0, c0 = self._upload_box(int(ends_y[0]), int(ends_y[1]) + n, int(ends_x[0]), int(ends_x[1]) + n)
+            iy0, ix0, n = _plans.window_origins(self, window, xa, ya)
         iy0_t, ix0_t = self._origins_tensors(iy0, ix0, r0, c0)
         return g, iy0_t, ix0_t, n
 
