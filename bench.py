@@ -385,10 +385,18 @@ def run_gpu(args):
     # ---- check: the gathered multi-GPU result equals what ONE GPU computes for the same windows ---------------
     check = None
     if world > 1 and rank == 0:
-        sel = np.unique(np.concatenate([np.arange(a, min(a + 64, nwin)) for a in
-                                        [pdist.shard_range(nwin, r, world)[0] for r in range(world)] +
-                                        [pdist.shard_range(nwin, r, world)[1] - 64 for r in range(world)]]))
-        solo = grid.optimise_batch(WINDOW, xc[sel], yc[sel], shard=False)
+        # two whole lattice rows on either side of every block boundary, computed by rank 0 alone through the same
+        # kernels (shared row spectra forced: 780 windows would otherwise take the scattered-window path, whose
+        # spectra differ in the last bits)
+        cols = int(np.flatnonzero(xc[1:] == xc[0])[0]) + 1
+        cuts = sorted({pdist.shard_range(nwin, r, world)[0] for r in range(1, world)})
+        sel = np.unique(np.concatenate([np.arange(max(0, (c // cols - 2) * cols), min(nwin, (c // cols + 2) * cols))
+                                        for c in cuts]))
+        os.environ["CB_SPEC_SHARE_ROWS"] = "1"
+        try:
+            solo = grid.optimise_batch(WINDOW, xc[sel], yc[sel], shard=False)
+        finally:
+            del os.environ["CB_SPEC_SHARE_ROWS"]
         got = out.index_select(0, torch.from_numpy(sel).cuda()).cpu().numpy()
         check = {"windows": int(sel.size), "equal_to_single_gpu": bool(np.array_equal(solo, got)),
                  "max_rel_dev": float(np.max(np.abs(solo - got) / np.maximum(np.abs(solo), 1e-300)))}
