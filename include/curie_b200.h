@@ -178,6 +178,7 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
  * Gauss-Newton metric) on min_func.
  * ---------------------------------------------------------------------- */
 #define CB_FIT_FLAG_LINEAR_DZ 1   /* iterate in dz itself instead of u = exp(-2 k_min dz) */
+#define CB_FIT_FLAG_FORWARD_FIRST 2 /* dPhi/dbeta by forward differences far from the minimum, central near it (default: central throughout) */
 typedef struct cb_fit_options {
     double x0[4];            /* start (beta, zt, dz, C), used when x0_dev == NULL */
     double lb[4], ub[4];     /* bounds, +-INFINITY = unbounded (self.bounds, optimise.py:111-114) */

@@ -13,6 +13,7 @@
 // window, so it is computed once per model evaluation, not once per point.
 #pragma once
 #include "common.cuh"
+#include "fastlog.cuh"
 
 #define CB_PI 3.14159265358979323846264338327950288
 #define CB_KNU_EPS 1.0e-16
@@ -28,7 +29,10 @@
 #define CB_HD_NOINLINE CB_HD
 #endif
 CB_HD_NOINLINE double cb_exp(double x) { return exp(x); }
-CB_HD_NOINLINE double cb_log(double x) { return log(x); }
+// ln x through the spectrum kernels' short logarithm (fastlog.cuh: < 1 ulp, ~40 instructions instead of the
+// library's ~75; 0, subnormal, negative, inf and nan arguments take the library call): one call per forward-model
+// point plus the order-only coefficients -- it was 9 % of fit_kernel's instructions.
+CB_HD_NOINLINE double cb_log(double x) { return 2.0 * cb_half_log(x); }
 
 // 1/Gamma(1+m) = sum_k c_k m^k  (mpmath, 40 digits, rounded), split into even / odd parts:
 // E(m) = sum_{k even} c_k m^k, O(m) = sum_{k odd} c_k m^(k-1), so that

@@ -31,6 +31,8 @@ struct DevCtx {
     }
     __device__ __forceinline__ bool any(bool pred) const { return __any_sync(0xffffffffu, pred); }
     __device__ __forceinline__ bool all(bool pred) const { return __all_sync(0xffffffffu, pred); }
+    // fetch-and-increment of a global work counter
+    __device__ __forceinline__ unsigned atomic_inc_u32(unsigned *p) const { return atomicAdd(p, 1u); }
     template <class T> __device__ __forceinline__ static T ldg(const T *p) { return __ldg(p); }
     template <class T> __device__ __forceinline__ static T ldcg(const T *p) { return __ldcg(p); }
     template <class T> __device__ __forceinline__ static void stcg(T *p, T v) { __stcg(p, v); }
@@ -60,6 +62,7 @@ struct DevCtx {
 
 #ifdef CB_EMU
 #include <pthread.h>
+#include <string.h>
 #include <vector>
 struct EmuBlock {
     int nthreads, nblocks, bid;
@@ -120,6 +123,7 @@ struct HostCtx {
         return r;
     }
     bool all(bool pred) const { return !any(!pred); }
+    unsigned atomic_inc_u32(unsigned *p) const { return __atomic_fetch_add(p, 1u, __ATOMIC_SEQ_CST); }
     template <class T> static T ldg(const T *p) { return *p; }
     template <class T> static T ldcg(const T *p) { return *p; }
     template <class T> static const T *shared_view(const T *p) { return p; }      // plain memory under emulation
@@ -147,6 +151,7 @@ struct SerialCtx {
     double warp_sum(double v) const { return v; }
     bool any(bool pred) const { return pred; }
     bool all(bool pred) const { return pred; }
+    unsigned atomic_inc_u32(unsigned *p) const { return __atomic_fetch_add(p, 1u, __ATOMIC_SEQ_CST); }
     template <class T> static T ldg(const T *p) { return *p; }
     template <class T> static T ldcg(const T *p) { return *p; }
     template <class T> static const T *shared_view(const T *p) { return p; }      // plain memory under emulation

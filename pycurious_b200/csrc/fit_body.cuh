@@ -17,6 +17,22 @@
 //     creeping up to it through rejected steps
 //   * non-finite model values give 1e99 exactly like min_func (optimise.py:226-227)
 //
+// Execution structure (round 2).  A window advances in ROUNDS; every round is
+//     fit_eval_window : ONE fused evaluation of (trial, beta+h [, beta-h]) over (point, vector) pairs by a whole
+//                       warp, ending in the 15 sums of a Gauss-Newton step (model_eval.cuh) -- the derivative
+//                       evaluations of a trial are done speculatively WITH the trial (the first trial of a line
+//                       search is accepted ~90 % of the time);
+//     fit_step_window : the scalar part -- Armijo test, then [BFGS update, next direction and trial] or
+//                       [backtracked trial], and the order-only coefficients of the next evaluation -- by ONE
+//                       THREAD per window.
+// The two halves are separate kernels over the list of unfinished windows (fit_eval_kernel: one warp per window;
+// fit_step_kernel: one thread per window, 32 windows per warp), the solver state of a window living in global
+// memory between them (~1.5 KB per window and round: 1 % of the run time).  Round 1 ran both halves in one
+// persistent warp per window: the scalar half then executes on one lane of 32 and streams ~30 KB of straight-line
+// code through a 32 KB instruction cache that 24 independent warps share (ncu: 40 % of the stall samples were
+// instruction fetch, 18 of 32 lanes active).  Windows that need more rounds than the batched phase runs are
+// finished by fit_finish_kernel, which applies the same two functions in a per-warp loop.
+//
 // The reference's stopping point is set by its own noisy forward-difference gradient (factr 1e7,
 // pgtol 1e-5); this solver converges to the same bounded minimum more tightly, so on windows where
 // the reference is converged the parameters agree to ~1e-5 relative (tests/test_gpu_parity.py::_check_fit,
@@ -38,7 +54,15 @@ struct FitParams {
     int32_t *niter;         // [nwin] or NULL
     int32_t *status;        // [nwin] or NULL
     int32_t *nfev;          // [nwin] or NULL: model evaluations (one = nk forward-model points)
-    int32_t warps_per_block;
+    // scratch of the batched rounds (library-owned, see cb_fit_batch_rows): per window the solver state, the
+    // coefficients of its next evaluation and the sums of its last one; two lists of unfinished windows
+    double *state;          // [nwin, CB_FIT_STATE_STRIDE]
+    double *coef;           // [nwin, 3 FC_COUNT]
+    double *sums;           // [nwin, 16]
+    int32_t *list_in, *list_out;       // unfinished windows of this round / of the next one
+    unsigned int *count;               // [6]: list lengths of the rounds r, r+1, r+2 (rotating), then the
+                                       //      work counters of the evaluation kernels of those rounds
+    int32_t round;
 };
 
 enum { FIT_CONVERGED_PG = 0, FIT_CONVERGED_F = 1, FIT_LINESEARCH = 2, FIT_MAXITER = 3, FIT_BAD_START = 4 };
@@ -64,8 +88,12 @@ struct FitState {
     int32_t central;              // derivative evaluations use the central difference in beta from now on
     int32_t gcentral;             // the gradient of the current iterate was taken with the central difference
     int32_t use_pm;               // the evaluation being reduced staged Phi(beta - hb) (else forward difference)
-    int32_t buf_at_x;             // p0 / dPhi/ddz / Phi(beta + hb) in the slab belong to the current iterate
+    int32_t kind;                 // what the staged trial point is: first point, line-search trial, refinement
+    int32_t nv;                   // vectors of the round's fused evaluation: 2 (x, beta+hb) or 3 (+ beta-hb)
+    int32_t nls;                  // trials of the current line search so far
+    double alpha;                 // step length of the staged trial
 };
+enum { FIT_KIND_FIRST = 0, FIT_KIND_TRIAL = 1, FIT_KIND_REFINE = 2 };
 #define CB_FIT_STATE_DOUBLES ((int)((sizeof(FitState) + 7) / 8))
 enum { FIT_GO = 0, FIT_DONE = 1, FIT_REFINE = 2 };
 // dPhi/dbeta is a difference quotient in the order of K_nu (no closed form).  Far from the minimum the
@@ -74,7 +102,13 @@ enum { FIT_GO = 0, FIT_DONE = 1, FIT_REFINE = 2 };
 // gradient of the current iterate with the central difference and keeps using it, so every convergence
 // decision is made on central-difference gradients.
 #define CB_FIT_CENTRAL_BELOW 1.0e-3
-CB_HD int fit_slab_doubles(int nk) { return warp_slab_doubles(nk, true, CB_FIT_STATE_DOUBLES); }
+// one window's state in the scratch arrays
+#define CB_FIT_STATE_STRIDE (CB_FIT_STATE_DOUBLES | 1)
+CB_HD size_t fit_eval_smem_bytes(int warps) { return (size_t)warps * CB_FIT_TABLE_DOUBLES * sizeof(double); }
+// per-warp shared memory of the finish kernel: tables, state, sums (an even number of doubles: the tables hold double2)
+#define CB_FIT_FINISH_DOUBLES ((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_STRIDE + 16 + 1) & ~1)
+CB_HD size_t fit_finish_smem_bytes(int warps) { return (size_t)warps * CB_FIT_FINISH_DOUBLES * sizeof(double); }
+static_assert(CB_FIT_TABLE_DOUBLES % 2 == 0 && CB_FIT_CT_DOUBLES % 2 == 0, "double2 tables must stay 16-byte aligned");
 
 // Solve B d = -g on the free variables (frozen ones get d = 0) by Cholesky; returns false when the
 // reduced matrix is not positive definite.
@@ -201,14 +235,14 @@ CB_NOINLINE_BODY void fit_init(FitState *S, const cb_fit_options *o, const doubl
     }
     fit_set_trial(S);
     S->fresh = 1; S->stall = 0; S->status = FIT_MAXITER; S->action = FIT_GO; S->it = 0; S->nfev = 0; S->mask = 0;
-    S->central = 0; S->gcentral = 0; S->use_pm = 0; S->buf_at_x = 0;
+    S->central = (o->flags & CB_FIT_FLAG_FORWARD_FIRST) ? 0 : 1; S->gcentral = 0; S->use_pm = 0;
+    S->kind = FIT_KIND_FIRST; S->nv = S->central ? 3 : 2; S->nls = 0; S->alpha = 1.0;
 }
 
 // Make the evaluated trial point the current iterate (first evaluation: B = Gauss-Newton metric).
 CB_NOINLINE_BODY void fit_accept_first(FitState *S) {
     if (!S->okn) { S->status = FIT_BAD_START; S->action = FIT_DONE; }
     S->gcentral = S->use_pm;
-    S->buf_at_x = 1;
     S->f = S->fn;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { S->x[j] = S->xt[j]; S->g[j] = S->gn[j]; }
@@ -362,7 +396,6 @@ CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
         S->fresh = 1;
     }
     S->gcentral = S->use_pm;
-    S->buf_at_x = 1;
     const double fold = S->f;
     S->f = S->fn;
 #pragma unroll
@@ -376,110 +409,35 @@ CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
     else if (S->it >= max_iter) { S->status = FIT_MAXITER; S->action = FIT_DONE; }
 }
 
-// ---- all-lane phases ----------------------------------------------------------------------------
-// Objective, gradient and Gauss-Newton matrix at S->xt from the staged model values
-// (p0, dPhi/ddz at xt; pp, pm at beta +- hb).  The 15 sums are sum_i u_a[i] u_b[i] over the five
-// per-point vectors u = (r, dPhi/dbeta, k, dPhi/ddz, 1) (dPhi/dzt = -2k is applied as a scale).
-// Pass 1 stages r and the central difference in beta, lane-parallel over the points; in pass 2
-// lane q < 15 (and lane 16+q for the second half of the points) owns ONE of the 15 products and
-// walks the points with broadcast-free strided reads -- no 15-wide butterfly, ~100 instructions.
-// The arrays arrive as one pointer (obs: the arrays obs, p0, kb, pp, pm, dz, res follow each other nk apart) and
-// the k table, not as a WarpSlab reference: see model_eval_core.
-struct FitSlabView { const double *k; double *obs, *p0, *kb, *pp, *pm, *dz, *res; int nk; };
-
-template <class Ctx>
-CB_NOINLINE_BODY void fit_reduce_core(const Ctx &cx, const double *kh, double *obs0, int nk_, FitState *S, int lane) {
-    FitSlabView W;
-    W.k = kh; W.nk = nk_;
-    W.obs = obs0; W.p0 = obs0 + nk_; W.kb = obs0 + 2 * nk_; W.pp = obs0 + 3 * nk_; W.pm = obs0 + 4 * nk_;
-    W.dz = obs0 + 5 * nk_; W.res = W.pm;
-    const int L = cx.team_lanes(), nk = W.nk;
-    const double hb = S->hb;
-    const double rh = 1.0 / hb, rh2 = 0.5 * rh;
-    const bool use_pm = S->use_pm != 0;
-#pragma unroll 1
-    for (int i = lane; i < nk; i += L) {
-        const double p0 = W.p0[i], pp = W.pp[i], pm = use_pm ? W.pm[i] : 0.0;
-        const bool fp = isfinite(pp), fm = use_pm && isfinite(pm);
-        W.kb[i] = (fp && fm) ? (pp - pm) * rh2 : (fp ? (pp - p0) * rh : (fm ? (p0 - pm) * rh : 0.0));
-        W.res[i] = p0 - W.obs[i];             // Phi(beta - hb) is consumed: its slot holds the residuals for pass 2
-    }
-    if (lane == 0) S->one = 1.0;
-    cx.sync_warp();
-    const bool split = (L == 32);
-    const int half = split ? (lane >> 4) : 0;
-    const int lo = half ? (nk + 1) / 2 : 0, hi = split ? (half ? nk : (nk + 1) / 2) : nk;
-    const int qstep = split ? 16 : L;
-#pragma unroll 1
-    for (int q = split ? (lane & 15) : lane; q < 16; q += qstep) {
-        // q = 0: r.r;  1..4: r.J_a;  5..14: J_a.J_b packed upper triangle;  15: idle (keeps the shuffle convergent)
-        int va = 0, vb = 0;
-        if (q >= 1 && q < 5) vb = q;
-        else if (q >= 5) {
-            const int t = q - 5;
-            const int a = t < 4 ? 0 : (t < 7 ? 1 : (t < 9 ? 2 : 3));
-            va = a + 1;
-            vb = t - (a * 4 - (a * (a - 1)) / 2) + a + 1;
-        }
-        const double *A = va == 0 ? W.res : (va == 1 ? W.kb : (va == 2 ? W.k : (va == 3 ? W.dz : &S->one)));
-        const double *B = vb == 0 ? W.res : (vb == 1 ? W.kb : (vb == 2 ? W.k : (vb == 3 ? W.dz : &S->one)));
-        const int sa = va == 4 ? 0 : 1, sb = vb == 4 ? 0 : 1;
-        double acc = 0.0;
-        if (q < 15) {
-#pragma unroll 4
-            for (int i = lo; i < hi; ++i) acc = fma(A[i * sa], B[i * sb], acc);
-        }
-        if (split) acc += cx.shfl_xor(acc, 16);
-        acc *= (va == 2 ? -2.0 : 1.0) * (vb == 2 ? -2.0 : 1.0);
-        if (half == 0 && q < 15) {
-            if (q == 0) S->fn = 0.5 * acc;
-            else if (q < 5) S->gn[q - 1] = acc;
-            else S->Hn[q - 5] = acc;
-        }
-    }
-    cx.sync_warp();
-    if (lane == 0) {
-        bool ok = isfinite(S->fn);
-#pragma unroll 1
-        for (int a = 0; a < 4; ++a) ok = ok && isfinite(S->gn[a]);
-#pragma unroll 1
-        for (int q = 0; q < 10; ++q) ok = ok && isfinite(S->Hn[q]);
-        S->okn = ok ? 1 : 0;
-        if (!ok) {
-            S->fn = CB_BIG_MISFIT;
-#pragma unroll 1
-            for (int a = 0; a < 4; ++a) S->gn[a] = 0.0;
-#pragma unroll 1
-            for (int q = 0; q < 10; ++q) S->Hn[q] = 0.0;
-        } else {
-            S->fn += S->pen_t;
-            // chain rule for the solver coordinate of dz, then the priors (Gaussian in the physical parameters)
-            const double sd = S->sdz;
-            S->gn[2] *= sd;
-            S->Hn[tri(0, 2)] *= sd; S->Hn[tri(1, 2)] *= sd; S->Hn[tri(2, 3)] *= sd;
-            S->Hn[tri(2, 2)] *= sd * sd;
+// Objective, gradient and Gauss-Newton matrix at S->xt from the 15 sums of fit_eval_window (model_eval.cuh).
+CB_NOINLINE_BODY void fit_take_sums(FitState *S, const double *sums) {
+    S->fn = 0.5 * sums[0];
+    bool ok = isfinite(S->fn);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const double ja = a == 2 ? sd : 1.0;
-                S->gn[a] = fma((S->pt[a] - S->pmu[a]) * ja, S->pw[a], S->gn[a]);
-                S->Hn[tri(a, a)] = fma(ja * ja, S->pw[a], S->Hn[tri(a, a)]);
-            }
+    for (int a = 0; a < 4; ++a) { S->gn[a] = sums[1 + a]; ok = ok && isfinite(S->gn[a]); }
+#pragma unroll
+    for (int q = 0; q < 10; ++q) { S->Hn[q] = sums[5 + q]; ok = ok && isfinite(S->Hn[q]); }
+    S->okn = ok ? 1 : 0;
+    if (!ok) {
+        S->fn = CB_BIG_MISFIT;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) S->gn[a] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 10; ++q) S->Hn[q] = 0.0;
+    } else {
+        S->fn += S->pen_t;
+        // chain rule for the solver coordinate of dz, then the priors (Gaussian in the physical parameters)
+        const double sd = S->sdz;
+        S->gn[2] *= sd;
+        S->Hn[tri(0, 2)] *= sd; S->Hn[tri(1, 2)] *= sd; S->Hn[tri(2, 3)] *= sd;
+        S->Hn[tri(2, 2)] *= sd * sd;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const double ja = a == 2 ? sd : 1.0;
+            S->gn[a] = fma((S->pt[a] - S->pmu[a]) * ja, S->pw[a], S->gn[a]);
+            S->Hn[tri(a, a)] = fma(ja * ja, S->pw[a], S->Hn[tri(a, a)]);
         }
     }
-    cx.sync_warp();
-}
-
-template <class Ctx>
-CB_BODY void fit_reduce_full(const Ctx &cx, const WarpSlab &W, FitState *S, int lane) {
-    fit_reduce_core(cx, W.k, W.obs, W.nk, S, lane);
-}
-
-template <class Ctx>
-CB_BODY int fit_poll(const Ctx &cx, const FitState *S) {
-    cx.sync_warp();
-    const int a = S->action;
-    cx.sync_warp();
-    return a;
 }
 
 // Lane 0: the re-taken gradient replaces the iterate's (same point, same f up to rounding).
@@ -491,125 +449,218 @@ CB_NOINLINE_BODY void fit_refined(FitState *S) {
 #pragma unroll
     for (int q = 0; q < 10; ++q) S->H[q] = S->Hn[q];
     S->gcentral = 1;
-    S->buf_at_x = 1;
     S->action = FIT_GO;
 }
 
-// Lane 0: make the current iterate the trial point again (refinement after a failed line search).
+// Lane 0: make the current iterate the trial point again (refinement: its gradient is re-taken with the
+// central difference).
 CB_NOINLINE_BODY void fit_trial_at_x(FitState *S) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) S->xt[j] = S->x[j];
     fit_set_trial(S);
 }
 
-template <class Ctx>
-CB_BODY void fit_body(const Ctx &cx, const FitParams &P) {
-    const int tid = cx.tid();
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nk = P.nk;
-    const int64_t w = (int64_t)cx.bid() * P.warps_per_block + warp;
-    if (w >= P.nwin) return;     // whole warp leaves together
-
-    // per-warp slab in shared memory: wavenumber tables, model values, order tables, solver state
-    WarpSlab W = warp_slab_carve(reinterpret_cast<double *>(cx.smem()) +
-                                     (int64_t)warp * fit_slab_doubles(nk), nk, true, P.kh, P.ktab);
-    warp_slab_load(cx, W, P.phi + w * nk, lane);
-    FitState *S = reinterpret_cast<FitState *>(W.scratch);
-    const cb_fit_options *o = &P.opt;
-    const int max_iter = o->max_iter > 0 ? o->max_iter : 200;
-    const double gtol = o->gtol > 0.0 ? o->gtol : 1e-9;
-    const double ftol = o->ftol > 0.0 ? o->ftol : 1e-15;
-
-    if (lane == 0)
-        fit_init(S, o, P.x0_dev ? P.x0_dev + w * 4 : o->x0, P.prior_mu_dev ? P.prior_mu_dev + w * 4 : nullptr,
-                 W.sorted ? W.kmin : 0.0, W.sorted ? W.kmax : 0.0);
-    cx.sync_warp();
-    W.cu = S->cu;
-
-    // first evaluation: forward difference in beta (see CB_FIT_CENTRAL_BELOW)
-    model_coefs_warp(cx, W, S->pt, S->hb, 0, 2, lane);
-    model_eval_warp<false>(cx, W, 0, lane, W.p0, W.dz);
-    model_eval_warp<false>(cx, W, 1, lane, W.pp, nullptr);
-    fit_reduce_full(cx, W, S, lane);
-    if (lane == 0) { fit_accept_first(S); S->nfev = 2; }
-
-    // S->action is written by lane 0 only; every read is fenced by a barrier on both sides so that
-    // lane 0 cannot change it again before all lanes have seen the same value
-    while (fit_poll(cx, S) == FIT_GO) {
-        if (lane == 0) fit_direction(S, gtol);
-        const int act = fit_poll(cx, S);
-        if (act == FIT_DONE) break;
-        if (act == FIT_REFINE) {
-            int extra = 1;
-            if (S->buf_at_x) {            // Phi, dPhi/ddz and Phi(beta + hb) of this iterate are still staged
-                model_coefs_warp(cx, W, S->pt, S->hb, 2, 1, lane);
-            } else {
-                cx.sync_warp();
-                if (lane == 0) fit_trial_at_x(S);
-                cx.sync_warp();
-                model_coefs_warp(cx, W, S->pt, S->hb, 0, 3, lane);
-                model_eval_warp<false>(cx, W, 0, lane, W.p0, W.dz);
-                model_eval_warp<false>(cx, W, 1, lane, W.pp, nullptr);
-                extra = 3;
-            }
-            model_eval_warp<false>(cx, W, 2, lane, W.pm, nullptr);
-            if (lane == 0) S->use_pm = 1;
-            cx.sync_warp();
-            fit_reduce_full(cx, W, S, lane);
-            if (lane == 0) { S->nfev += extra; fit_refined(S); }
-            continue;
+// Lane 0, after an accepted point: next direction and its first trial (or the refinement point, or the end).
+CB_NOINLINE_BODY void fit_next_step(FitState *S, double gtol) {
+    for (int guard = 0; guard < 4 && S->action == FIT_GO; ++guard) {
+        fit_direction(S, gtol);
+        if (S->action == FIT_DONE) return;
+        if (S->action == FIT_REFINE) {
+            fit_trial_at_x(S);
+            S->kind = FIT_KIND_REFINE; S->nv = 3; S->action = FIT_GO;
+            return;
         }
-
-        // projected Armijo backtracking
-        const double f0 = S->f;
-        double alpha = 1.0;
-        bool accepted = false;
-        int nls = 0;
-        for (int ls = 0; ls < 40; ++ls) {
-            if (lane == 0) { fit_trial(S, alpha); S->buf_at_x = 0; }
-            cx.sync_warp();
-            const double dec = S->dec;
-            if (S->move == 0.0) break;
-            // coefficients of the trial point AND of its beta +- hb neighbours in one call (one lane each, same
-            // instruction count as the trial alone): the derivative evaluations of an accepted trial need no second pass
-            model_coefs_warp(cx, W, S->pt, S->hb, 0, S->central ? 3 : 2, lane);
-            model_eval_warp<false>(cx, W, 0, lane, W.p0, W.dz);
-            ++nls;
-            double ft = slab_half_ssq(cx, W, lane);
-            ft = isfinite(ft) ? ft + S->pen_t : CB_BIG_MISFIT;
-            if (ft <= f0 + 1e-4 * dec && ft < 1e98) { accepted = true; break; }
-            if (ft >= 1e98) alpha *= 0.25;
-            else {
-                // minimiser of the quadratic through f(0), f'(0), f(alpha)
-                const double den = 2.0 * (ft - f0 - dec);
-                const double an = den > 0.0 ? -dec * alpha / den : 0.5 * alpha;
-                alpha = clampd(an, 0.1 * alpha, 0.5 * alpha);
-            }
-            cx.sync_warp();
-        }
-        if (!accepted) {
-            cx.sync_warp();
-            if (lane == 0) { S->nfev += nls; fit_linesearch_failed(S); }
-            continue;
-        }
-        // derivatives at the accepted point: beta + hb (and beta - hb once the central difference is on);
-        // p0 and dPhi/ddz are already staged
-        const int central = S->central;
-        model_eval_warp<false>(cx, W, 1, lane, W.pp, nullptr);
-        if (central) model_eval_warp<false>(cx, W, 2, lane, W.pm, nullptr);
-        if (lane == 0) S->use_pm = central;
-        cx.sync_warp();
-        fit_reduce_full(cx, W, S, lane);
-        if (lane == 0) { S->nfev += nls + (central ? 2 : 1); fit_update(S, ftol, max_iter); }
+        S->alpha = 1.0; S->nls = 0;
+        fit_trial(S, 1.0);
+        S->kind = FIT_KIND_TRIAL; S->nv = S->central ? 3 : 2;
+        if (S->move != 0.0) return;
+        fit_linesearch_failed(S);        // no move possible: once more from the Gauss-Newton metric, else give up
     }
-    if (lane == 0) {
-        double pf[4];
-        fit_to_physical(S, S->x, pf);
+    if (S->action == FIT_GO) { S->status = FIT_LINESEARCH; S->action = FIT_DONE; }
+}
+
+// Lane 0, after a rejected trial (ft = its objective value): shorter step along the same direction.
+CB_NOINLINE_BODY void fit_backtrack(FitState *S, double ft, double gtol) {
+    const double f0 = S->f, dec = S->dec;
+    double alpha = S->alpha;
+    if (ft >= 1e98) alpha *= 0.25;
+    else {
+        // minimiser of the quadratic through f(0), f'(0), f(alpha)
+        const double den = 2.0 * (ft - f0 - dec);
+        const double an = den > 0.0 ? -dec * alpha / den : 0.5 * alpha;
+        alpha = clampd(an, 0.1 * alpha, 0.5 * alpha);
+    }
+    S->alpha = alpha;
+    S->nls += 1;
+    if (S->nls < 40) {
+        fit_trial(S, alpha);
+        if (S->move != 0.0) return;
+    }
+    fit_linesearch_failed(S);
+    if (S->action == FIT_GO) fit_next_step(S, gtol);
+}
+
+// Coefficients of the staged trial point for the next evaluation (nv vectors) -> c[3 FC_COUNT].
+CB_NOINLINE_BODY void fit_stage_coefs(const FitState *S, double *c) {
+    const int nv = S->nv;
+    for (int v = 0; v < nv; ++v) fit_coef_fill(c + v * FC_COUNT, S->pt, S->hb, v);
+    c[FC_AUX] = S->hb;
+    c[FC_COUNT + FC_AUX] = S->cu;
+    c[2 * FC_COUNT + FC_AUX] = (double)nv;
+}
+
+// One thread: the scalar half of a round.  `sums` = the 15 sums of the evaluation of the staged trial point.
+// Returns true when the window is finished; otherwise a new trial point and its coefficients are staged.
+CB_BODY bool fit_step_window(FitState *S, const double *sums, double gtol, double ftol, int max_iter, double *coef) {
+    const int kind = S->kind, nv = S->nv;
+    S->nfev += nv;
+    bool take = true;
+    double ft = 0.0;
+    if (kind == FIT_KIND_TRIAL) {                        // projected Armijo test
+        ft = 0.5 * sums[0];
+        ft = isfinite(ft) ? ft + S->pen_t : CB_BIG_MISFIT;
+        take = ft <= S->f + 1e-4 * S->dec && ft < 1e98;
+    }
+    if (take) {
+        S->use_pm = nv == 3;
+        fit_take_sums(S, sums);
+        if (kind == FIT_KIND_FIRST) fit_accept_first(S);
+        else if (kind == FIT_KIND_TRIAL) fit_update(S, ftol, max_iter);
+        else fit_refined(S);
+        if (S->action == FIT_GO) fit_next_step(S, gtol);
+    } else {
+        fit_backtrack(S, ft, gtol);
+    }
+    if (S->action != FIT_GO) return true;
+    fit_stage_coefs(S, coef);
+    return false;
+}
+
+CB_BODY void fit_write_result(const FitParams &P, FitState *S, int64_t w) {
+    double pf[4];
+    fit_to_physical(S, S->x, pf);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) P.x_out[w * 4 + j] = pf[j];
-        if (P.f_out) P.f_out[w] = S->f;
-        if (P.niter) P.niter[w] = S->it;
-        if (P.status) P.status[w] = S->status;
-        if (P.nfev) P.nfev[w] = S->nfev;
+    for (int j = 0; j < 4; ++j) P.x_out[w * 4 + j] = pf[j];
+    if (P.f_out) P.f_out[w] = S->f;
+    if (P.niter) P.niter[w] = S->it;
+    if (P.status) P.status[w] = S->status;
+    if (P.nfev) P.nfev[w] = S->nfev;
+}
+
+CB_BODY void fit_solver_constants(const FitParams &P, int &max_iter, double &gtol, double &ftol) {
+    const cb_fit_options *o = &P.opt;
+    max_iter = o->max_iter > 0 ? o->max_iter : 200;
+    gtol = o->gtol > 0.0 ? o->gtol : 1e-9;
+    ftol = o->ftol > 0.0 ? o->ftol : 1e-15;
+}
+
+// ---- kernels' bodies ----------------------------------------------------------------------------------------
+// begin: one thread per window -- initial state, coefficients of the first evaluation, the identity list.
+CB_BODY void fit_begin_window(const FitParams &P, int64_t w) {
+    const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
+    const bool sorted = meta[0] != 0.0;
+    FitState S;
+    memset(&S, 0, sizeof(S));
+    fit_init(&S, &P.opt, P.x0_dev ? P.x0_dev + w * 4 : P.opt.x0, P.prior_mu_dev ? P.prior_mu_dev + w * 4 : nullptr,
+             sorted ? meta[1] : 0.0, sorted ? meta[2] : 0.0);
+    fit_stage_coefs(&S, P.coef + w * (3 * FC_COUNT));
+    double *dst = P.state + w * CB_FIT_STATE_STRIDE;
+    const double *src = reinterpret_cast<const double *>(&S);
+    for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) dst[i] = src[i];
+    P.list_in[w] = (int32_t)w;
+}
+template <class Ctx>
+CB_BODY void fit_begin_body(const Ctx &cx, const FitParams &P) {
+    const int64_t w = (int64_t)cx.bid() * cx.nthreads() + cx.tid();
+    if (w == 0) {
+        P.count[0] = (unsigned)P.nwin;
+        for (int q = 1; q < 6; ++q) P.count[q] = 0u;
+    }
+    if (w < P.nwin) fit_begin_window(P, w);
+}
+
+// eval: one warp per unfinished window; the warps of a persistent grid claim list entries from a counter.
+template <class Ctx>
+CB_BODY void fit_eval_body(const Ctx &cx, const FitParams &P) {
+    const int tid = cx.tid(), warp = tid >> 5, lane = tid & 31, L = cx.team_lanes();
+    const unsigned n = P.count[P.round % 3];
+    unsigned int *next = P.count + 3 + P.round % 3;
+    if (cx.bid() == 0 && tid == 0) {       // what the round after next uses: nobody reads or writes these now
+        P.count[(P.round + 2) % 3] = 0u;
+        P.count[3 + (P.round + 2) % 3] = 0u;
+    }
+    double *tab = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * CB_FIT_TABLE_DOUBLES;
+    const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
+    const int sorted = meta[0] != 0.0 ? 1 : 0;
+    for (int j = lane; j < CB_TEMME_TAB; j += L) tab[CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + j] = P.ktab[3 * P.nk + j];
+#pragma unroll 1
+    for (;;) {
+        unsigned e = 0;
+        if (lane == 0) e = cx.atomic_inc_u32(next);
+        e = (unsigned)cx.shfl_i((int)e, 0);
+        if (e >= n) break;
+        const int64_t w = P.list_in[e];
+        cx.sync_warp();
+        const double *cg = P.coef + w * (3 * FC_COUNT);
+        for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = cg[j];
+        cx.sync_warp();
+        fit_eval_window(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, P.sums + w * 16);
+    }
+}
+
+// step: one thread per unfinished window, on a private copy of its state.
+template <class Ctx>
+CB_BODY void fit_step_entry(const Ctx &cx, const FitParams &P, int64_t e) {
+    int max_iter;
+    double gtol, ftol;
+    fit_solver_constants(P, max_iter, gtol, ftol);
+    const int64_t w = P.list_in[e];
+    FitState S;
+    double *d = reinterpret_cast<double *>(&S), *g = P.state + w * CB_FIT_STATE_STRIDE;
+    for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) d[i] = g[i];
+    const bool done = fit_step_window(&S, P.sums + w * 16, gtol, ftol, max_iter, P.coef + w * (3 * FC_COUNT));
+    if (done) fit_write_result(P, &S, w);
+    else {
+        for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) g[i] = d[i];
+        P.list_out[cx.atomic_inc_u32(P.count + (P.round + 1) % 3)] = (int32_t)w;
+    }
+}
+template <class Ctx>
+CB_BODY void fit_step_body(const Ctx &cx, const FitParams &P) {
+    const int tid = cx.tid(), nt = cx.nthreads();
+    const unsigned n = P.count[P.round % 3];
+#pragma unroll 1
+    for (int64_t e = (int64_t)cx.bid() * nt + tid; e < (int64_t)n; e += (int64_t)cx.nblocks() * nt) fit_step_entry(cx, P, e);
+}
+
+// finish: one warp per window still unfinished after the batched rounds, run to the end.
+template <class Ctx>
+CB_BODY void fit_finish_body(const Ctx &cx, const FitParams &P) {
+    const int tid = cx.tid(), warp = tid >> 5, lane = tid & 31, L = cx.team_lanes();
+    const int wpb = cx.nthreads() >> 5;
+    const unsigned n = P.count[P.round % 3];
+    int max_iter;
+    double gtol, ftol;
+    fit_solver_constants(P, max_iter, gtol, ftol);
+    double *tab = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * CB_FIT_FINISH_DOUBLES;
+    double *sd = tab + CB_FIT_TABLE_DOUBLES, *sums = sd + CB_FIT_STATE_STRIDE;
+    FitState *S = reinterpret_cast<FitState *>(sd);
+    const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
+    const int sorted = meta[0] != 0.0 ? 1 : 0;
+    for (int j = lane; j < CB_TEMME_TAB; j += L) tab[CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + j] = P.ktab[3 * P.nk + j];
+#pragma unroll 1
+    for (int64_t e = (int64_t)cx.bid() * wpb + warp; e < (int64_t)n; e += (int64_t)cx.nblocks() * wpb) {
+        const int64_t w = P.list_in[e];
+        cx.sync_warp();
+        const double *g = P.state + w * CB_FIT_STATE_STRIDE, *cg = P.coef + w * (3 * FC_COUNT);
+        for (int i = lane; i < CB_FIT_STATE_DOUBLES; i += L) sd[i] = g[i];
+        for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = cg[j];
+        cx.sync_warp();
+        for (;;) {
+            fit_eval_window(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, sums);
+            if (lane == 0 && fit_step_window(S, sums, gtol, ftol, max_iter, tab + CB_FIT_COEF_OFFSET)) fit_write_result(P, S, w);
+            cx.sync_warp();
+            if (S->action != FIT_GO) break;
+        }
     }
 }

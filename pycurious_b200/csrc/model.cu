@@ -1,16 +1,18 @@
 // Forward model hooks, batched MAP fit and Metropolis-Hastings: kernels + C-ABI entry points.
 // Bodies: besselk.cuh, bouligand.cuh, fit_body.cuh, mh_body.cuh.
 #include <cstring>
+#include <cstdlib>
+#include <cstdio>
 #include "fit_body.cuh"
 #include "mh_body.cuh"
 #include "tanaka_body.cuh"
 
 extern __shared__ double cb_dyn_smem_d[];
 
-// One warp (= one window / chain) per CTA: fit and chain lengths vary between windows, and with
-// single-warp CTAs the hardware block scheduler balances them.  The kernels are dependency-latency
-// bound (one long serial chain per window): throughput scales with resident warps, so the slab is kept
-// at ~9 KB (window-independent tables live in global memory) and registers at 80 for 24 CTAs per SM.
+// Misfit and Metropolis-Hastings: one warp (= one spectrum / chain) per CTA -- chain lengths vary between windows,
+// and with single-warp CTAs the hardware block scheduler balances them.  These kernels are dependency-latency
+// bound (one long serial chain per window): throughput scales with resident warps, so the slab is kept at ~9 KB
+// (window-independent tables live in global memory) and registers at 80 for 24 CTAs per SM.
 #define CB_FIT_WARPS 1
 #ifndef CB_FIT_CTAS_PER_SM
 #define CB_FIT_CTAS_PER_SM 24
@@ -72,9 +74,27 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) mi
     if (lane == 0) P.out[row] = f;
 }
 
-__global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) fit_kernel(const __grid_constant__ FitParams P) {
+// The MAP fit as rounds of two kernels over the list of unfinished windows (fit_body.cuh): the fused model
+// evaluation (one warp per window, persistent grid, entries claimed from a counter) and the scalar solver step (one
+// thread per window); fit_finish_kernel runs the stragglers to the end, one warp each.
+#define CB_FIT_EVAL_WARPS 8
+#define CB_FIT_EVAL_CTAS_PER_SM 3
+#define CB_FIT_FINISH_WARPS 4
+__global__ void __launch_bounds__(256) fit_begin_kernel(const __grid_constant__ FitParams P) {
+    DevCtx cx{nullptr};
+    fit_begin_body(cx, P);
+}
+__global__ void __launch_bounds__(CB_FIT_EVAL_WARPS * CB_WARP, CB_FIT_EVAL_CTAS_PER_SM) fit_eval_kernel(const __grid_constant__ FitParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
-    fit_body(cx, P);
+    fit_eval_body(cx, P);
+}
+__global__ void __launch_bounds__(128) fit_step_kernel(const __grid_constant__ FitParams P) {
+    DevCtx cx{nullptr};
+    fit_step_body(cx, P);
+}
+__global__ void __launch_bounds__(CB_FIT_FINISH_WARPS * CB_WARP) fit_finish_kernel(const __grid_constant__ FitParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
+    fit_finish_body(cx, P);
 }
 
 __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_MH_CTAS_PER_SM) mh_kernel(const __grid_constant__ MhParams P) {
@@ -146,6 +166,28 @@ static int ktable_make(const double *kh_dev, int nk, cudaStream_t st, double **o
     return CB_OK;
 }
 
+// Scratch of the batched fit, one buffer per (device, stream), grown on demand and kept (same ownership rule as the
+// k tables above: launches of one stream are ordered, different streams never share a buffer).
+#define CB_FIT_PASS_WINDOWS 262144
+static std::map<std::pair<int, cudaStream_t>, std::pair<char *, size_t>> g_fit_scratch;
+static int fit_scratch(cudaStream_t st, size_t bytes, char **out) {
+    int dev = 0;
+    CB_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ktab_mutex);
+    auto &slot = g_fit_scratch[std::make_pair(dev, st)];
+    if (slot.second < bytes) {
+        if (slot.first) {
+            CB_CUDA_TRY(cudaStreamSynchronize(st));      // a fit of this stream may still be using the old buffer
+            CB_CUDA_TRY(cudaFree(slot.first));
+            slot.first = nullptr; slot.second = 0;
+        }
+        CB_CUDA_TRY(cudaMalloc((void **)&slot.first, bytes));
+        slot.second = bytes;
+    }
+    *out = slot.first;
+    return CB_OK;
+}
+
 static int elementwise_grid(int64_t n) {
     int64_t g = (n + 255) / 256;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -190,7 +232,8 @@ int cb_bouligand_points(const double *kh_dev, const double *params_dev, int64_t 
 enum { SLAB_MISFIT = 0, SLAB_FIT = 1, SLAB_MH = 2 };
 static int per_warp_launch_shape(int nk, int64_t nwin, int kind, int *grid, size_t *smem) {
     CB_REQUIRE(nk > 0 && nk <= 512, "nk must be in [1, 512]");
-    const int slab = kind == SLAB_FIT ? fit_slab_doubles(nk) : (kind == SLAB_MH ? mh_slab_doubles(nk) : warp_slab_doubles(nk, false));
+    CB_REQUIRE(kind != SLAB_FIT, "the fit has its own launch shape");
+    const int slab = kind == SLAB_MH ? mh_slab_doubles(nk) : warp_slab_doubles(nk, false);
     *smem = (size_t)CB_FIT_WARPS * (size_t)slab * sizeof(double);
     int64_t g = (nwin + CB_FIT_WARPS - 1) / CB_FIT_WARPS;
     CB_REQUIRE(g <= 2147483647LL, "too many windows for one launch");
@@ -237,20 +280,58 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     }
     int rc = cb_check_device();
     if (rc) return rc;
-    int grid;
-    size_t smem;
-    if ((rc = per_warp_launch_shape(nk, nwin, SLAB_FIT, &grid, &smem)) != CB_OK) return rc;
-    FitParams P;
-    memset(&P, 0, sizeof(P));
-    P.kh = kh_dev; P.nk = nk; P.phi = phi_dev; P.nwin = nwin; P.opt = *opt_host; P.x0_dev = x0_dev;
-    P.prior_mu_dev = prior_mu_dev;
-    P.x_out = x_out_dev; P.f_out = f_out_dev; P.niter = niter_dev; P.status = status_dev; P.nfev = nfev_dev;
-    P.warps_per_block = CB_FIT_WARPS;
-    if (smem > 48 * 1024) CB_CUDA_TRY(cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_REQUIRE(nk > 0 && nk <= CB_KTABLE_MAX_NK, "nk out of range");
+    static int env_rounds = -1, sm_count = 0;
+    if (env_rounds < 0) {
+        const char *e = getenv("CB_FIT_ROUNDS");          // batched rounds before the per-warp finish (tuning)
+        env_rounds = e ? atoi(e) : 20;
+        int dev = 0;
+        CB_CUDA_TRY(cudaGetDevice(&dev));
+        CB_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
     double *ktab = nullptr;
-    if ((rc = ktable_make(kh_dev, nk, (cudaStream_t)stream, &ktab)) != CB_OK) return rc;
-    P.ktab = ktab;
-    fit_kernel<<<grid, CB_FIT_WARPS * CB_WARP, smem, (cudaStream_t)stream>>>(P);
+    if ((rc = ktable_make(kh_dev, nk, st, &ktab)) != CB_OK) return rc;
+    // library-owned scratch per (device, stream): state, coefficients, sums, two lists, counters; inputs larger
+    // than CB_FIT_PASS_WINDOWS go through it in passes
+    const int64_t pass = nwin < CB_FIT_PASS_WINDOWS ? nwin : CB_FIT_PASS_WINDOWS;
+    const size_t per_win = (size_t)(CB_FIT_STATE_STRIDE + 3 * FC_COUNT + 16) * sizeof(double) + 2 * sizeof(int32_t);
+    char *scratch = nullptr;
+    if ((rc = fit_scratch(st, (size_t)pass * per_win + 64, &scratch)) != CB_OK) return rc;
+    for (int64_t off = 0; off < nwin; off += pass) {
+        const int64_t n = nwin - off < pass ? nwin - off : pass;
+        FitParams P;
+        memset(&P, 0, sizeof(P));
+        P.kh = kh_dev; P.ktab = ktab; P.nk = nk; P.phi = phi_dev + off * nk; P.nwin = n; P.opt = *opt_host;
+        P.x0_dev = x0_dev ? x0_dev + off * 4 : nullptr;
+        P.prior_mu_dev = prior_mu_dev ? prior_mu_dev + off * 4 : nullptr;
+        P.x_out = x_out_dev + off * 4;
+        P.f_out = f_out_dev ? f_out_dev + off : nullptr;
+        P.niter = niter_dev ? niter_dev + off : nullptr;
+        P.status = status_dev ? status_dev + off : nullptr;
+        P.nfev = nfev_dev ? nfev_dev + off : nullptr;
+        P.count = reinterpret_cast<unsigned int *>(scratch);
+        P.state = reinterpret_cast<double *>(scratch + 64);
+        P.coef = P.state + (size_t)pass * CB_FIT_STATE_STRIDE;
+        P.sums = P.coef + (size_t)pass * 3 * FC_COUNT;
+        int32_t *la = reinterpret_cast<int32_t *>(P.sums + (size_t)pass * 16), *lb = la + pass;
+        P.list_in = la; P.list_out = lb;
+        fit_begin_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(P);
+        int64_t g = (n + CB_FIT_EVAL_WARPS - 1) / CB_FIT_EVAL_WARPS;
+        const int eval_grid = (int)(g < (int64_t)sm_count * CB_FIT_EVAL_CTAS_PER_SM ? g : (int64_t)sm_count * CB_FIT_EVAL_CTAS_PER_SM);
+        g = (n + 127) / 128;
+        const int step_grid = (int)(g < (int64_t)sm_count * 16 ? g : (int64_t)sm_count * 16);
+        for (int r = 0; r < env_rounds; ++r) {
+            P.round = r;
+            fit_eval_kernel<<<eval_grid, CB_FIT_EVAL_WARPS * CB_WARP, fit_eval_smem_bytes(CB_FIT_EVAL_WARPS), st>>>(P);
+            fit_step_kernel<<<step_grid, 128, 0, st>>>(P);
+            int32_t *t = P.list_in; P.list_in = P.list_out; P.list_out = t;
+        }
+        P.round = env_rounds;
+        g = (n + CB_FIT_FINISH_WARPS - 1) / CB_FIT_FINISH_WARPS;
+        const int fin_grid = (int)(g < (int64_t)sm_count * 8 ? g : (int64_t)sm_count * 8);
+        fit_finish_kernel<<<fin_grid, CB_FIT_FINISH_WARPS * CB_WARP, fit_finish_smem_bytes(CB_FIT_FINISH_WARPS), st>>>(P);
+    }
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }

@@ -481,6 +481,324 @@ CB_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int la
                                 idx, lane, out_phi, out_ddz, obs, bound);
 }
 
+// ---- fused evaluation of the fit: (trial, beta+h [, beta-h]) -> the 15 sums of one Gauss-Newton step ---------------
+// The MAP fit needs Phi at a trial point and at its beta +- h neighbours (dPhi/dbeta has no closed form).  The
+// vectors share zt, dz and C, hence x = k dz and the class split; evaluating them one after the other runs every
+// class pass once per vector, each with few live lanes (the Bessel classes of a 99-bin window hold ~40 points: one
+// full chunk with the longest Miller recurrence plus a quarter-full one).  Here the work items are (point, vector)
+// PAIRS: lane = (point within the chunk) * nv + vector, so the chunks are full, the pairs of one chunk have
+// neighbouring x (the Miller trip count follows the chunk's smallest x) and the number of passes drops from 2 nv to
+// ~nv + 1.  The model values never reach memory: the lanes of a point exchange them by shuffles and the lane of
+// vector 0 accumulates the point's contribution to
+//     sums[0] = r.r;  sums[1..4] = r.J_a;  sums[5..14] = J_a.J_b (packed upper triangle)
+// with r = Phi - obs and J = (dPhi/dbeta, dPhi/dzt = -2k, dPhi/ddz, dPhi/dC = 1); the lanes are summed by a
+// transposing butterfly (16 double shuffles).  Per-warp tables in shared memory (doubles): CT [3][CB_MILLER_NMAX+1]
+// weights C_n of the normalising sum per vector (a_{n+1} is updated inside the recurrence), RPQ [3][CB_TEMME_TAB]
+// double2, RNJ [CB_TEMME_TAB] 1/j, COEF [3][FC_COUNT].
+enum {
+    FC_MU, FC_A1, FC_RMU, FC_HP, FC_HQ, FC_SINC, FC_GAM1, FC_GAM2, FC_QG, FC_NU, FC_BM1, FC_LGC, FC_LEAD, FC_LGNU,
+    FC_NL, FC_FAST, FC_BETA, FC_ZT, FC_C, FC_DZ, FC_RDZ, FC_RSDZ, FC_LHDZ,
+    FC_AUX,            // vector 0: the beta step hb; vector 1: the solver coordinate's cu; vector 2: number of vectors
+    FC_COUNT
+};
+#define CB_FIT_CT_DOUBLES (3 * (CB_MILLER_NMAX + 1))
+#define CB_FIT_RPQ_DOUBLES (2 * 3 * CB_TEMME_TAB)
+#define CB_FIT_TABLE_DOUBLES (CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + CB_TEMME_TAB + 3 * FC_COUNT)
+#define CB_FIT_COEF_OFFSET (CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + CB_TEMME_TAB)
+
+// Coefficients of vector v of the trial point x (beta offset by 0, +hb, -hb) -> c[FC_COUNT].
+CB_HD void fit_coef_fill(double *c, const double *x, double hb, int v) {
+    const double beta = x[0] + (v == 1 ? hb : (v == 2 ? -hb : 0.0));
+    const EvalCoef e = eval_coef_make(beta, x[1], x[2], x[3]);
+    c[FC_MU] = e.m.ord.mu; c[FC_A1] = e.a1; c[FC_RMU] = e.rmu; c[FC_HP] = e.hp; c[FC_HQ] = e.hq;
+    c[FC_SINC] = e.m.ord.sinc; c[FC_GAM1] = e.m.ord.gam1; c[FC_GAM2] = e.m.ord.gam2; c[FC_QG] = 0.25 * e.m.gnu;
+    c[FC_NU] = e.m.nu; c[FC_BM1] = e.m.beta - 1.0; c[FC_LGC] = e.lgc; c[FC_LEAD] = e.m.lead; c[FC_LGNU] = e.lgnu;
+    c[FC_NL] = (double)e.m.ord.nl; c[FC_FAST] = e.fast ? 1.0 : 0.0; c[FC_BETA] = e.m.beta; c[FC_ZT] = e.m.zt;
+    c[FC_C] = e.m.C; c[FC_DZ] = e.m.dz; c[FC_RDZ] = e.rdz; c[FC_RSDZ] = e.rsdz; c[FC_LHDZ] = e.m.lhalfdz;
+    c[FC_AUX] = 0.0;
+}
+
+// One point's contribution to the 15 sums (p0, pp, pm = Phi at beta, beta + hb, beta - hb; jd = dPhi/ddz).
+CB_HD void fit_sums_add(double *v, double p0, double pp, double pm, bool use_pm, double rh, double jd, double k,
+                        double obs) {
+    const bool fp = isfinite(pp), fm = use_pm && isfinite(pm);
+    const double jb = (fp && fm) ? (pp - pm) * (0.5 * rh) : (fp ? (pp - p0) * rh : (fm ? (p0 - pm) * rh : 0.0));
+    const double r = p0 - obs, jk = -2.0 * k;
+    v[0] = fma(r, r, v[0]); v[1] = fma(r, jb, v[1]); v[2] = fma(r, jk, v[2]); v[3] = fma(r, jd, v[3]); v[4] += r;
+    v[5] = fma(jb, jb, v[5]); v[6] = fma(jb, jk, v[6]); v[7] = fma(jb, jd, v[7]); v[8] += jb;
+    v[9] = fma(jk, jk, v[9]); v[10] = fma(jk, jd, v[10]); v[11] += jk;
+    v[12] = fma(jd, jd, v[12]); v[13] += jd;
+    v[14] += 1.0;
+}
+
+// tab: the warp's tables with COEF filled for nv vectors (FC_AUX: hb, cu, nv); obs: the window's spectrum (global);
+// sums_out[16] receives the sums (any address space; written by 15 lanes after the butterfly).
+template <class Ctx>
+CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const double *ktab, int nk, int sorted,
+                             int lane, const double *obs, double *sums_out) {
+    const int L = cx.team_lanes();
+    double *CTg = tab;
+    double2 *RPQg = reinterpret_cast<double2 *>(tab + CB_FIT_CT_DOUBLES);
+    const double *RNJg = tab + CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES;
+    double *COEF = tab + CB_FIT_COEF_OFFSET;
+    const double *logk = ktab, *rk = ktab + nk, *sq = ktab + 2 * nk, *rn = ktab + 3 * nk;
+    const auto C0 = Ctx::shared_view((const double *)COEF);
+    const double hb = C0[FC_AUX], cu = C0[FC_COUNT + FC_AUX];
+    const int nv = (int)C0[2 * FC_COUNT + FC_AUX];
+    const bool use_pm = nv == 3;
+    const double rh = 1.0 / hb;
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = 0.0;
+
+    bool fast = sorted != 0;
+    for (int u = 0; u < nv; ++u) fast = fast && C0[u * FC_COUNT + FC_FAST] != 0.0;
+    if (!fast) {                                          // generic per-point path, reference nan/inf semantics
+        ModelCoef m[3];
+        for (int u = 0; u < nv; ++u) {
+            const double *c = COEF + u * FC_COUNT;
+            m[u] = model_coef(c[FC_BETA], c[FC_ZT], c[FC_DZ], c[FC_C]);
+        }
+#pragma unroll 1
+        for (int i = lane; i < nk; i += L) {
+            const double k = Ctx::ldg(kh + i), lk = Ctx::ldg(logk + i);
+            double jd = 0.0;
+            const double p0 = generic_point(&m[0], k, lk, &jd);
+            const double pp = generic_point(&m[1], k, lk, nullptr);
+            const double pm = use_pm ? generic_point(&m[2], k, lk, nullptr) : 0.0;
+            fit_sums_add(v, p0, pp, pm, use_pm, rh, jd, k, Ctx::ldg(obs + i));
+        }
+    } else {
+        const double dz = C0[FC_DZ], zt = C0[FC_ZT], Cc = C0[FC_C], lhdz = C0[FC_LHDZ], rdz = C0[FC_RDZ];
+        // ---- classes from vector 0 (one split for all vectors: the difference quotient in beta must not straddle
+        //      two evaluation methods): [0,nT) Temme, [nT,nS) Miller, [nS,nk) K negligible ------------------------
+        int lastT = -1, lastC = -1;
+        {
+            const double nu0 = C0[FC_NU], lgnu0 = C0[FC_LGNU], cudz = cu * dz;
+#pragma unroll 1
+            for (int i = lane; i < nk; i += L) {
+                const double k = Ctx::ldg(kh + i), lk = Ctx::ldg(logk + i);
+                const double xi = k * dz;
+                if (xi <= 2.0) lastT = i;
+                const bool skip = xi > 2.0 && (2.0 * xi - cudz - nu0 * (lk + lhdz) + lgnu0 > CB_SKIP_LOG);
+                if (!skip) lastC = i;
+            }
+        }
+        const int nT = cx.warp_max_i(lastT) + 1;
+        int nS = cx.warp_max_i(lastC) + 1;
+        if (nS < nT) nS = nT;
+
+        // ---- closed-form class: every vector from the k and ln k the lane holds; dPhi/ddz = 0 -------------------
+        {
+            const double b0 = C0[FC_BM1], g0 = C0[FC_LGC], b1 = C0[FC_COUNT + FC_BM1], g1 = C0[FC_COUNT + FC_LGC];
+            const double b2 = use_pm ? C0[2 * FC_COUNT + FC_BM1] : 0.0, g2 = use_pm ? C0[2 * FC_COUNT + FC_LGC] : 0.0;
+#pragma unroll 1
+            for (int i = nS + lane; i < nk; i += L) {
+                const double k = Ctx::ldg(kh + i), lk = Ctx::ldg(logk + i);
+                const bool over = k * dz > CB_COSH_OVERFLOW;
+                const double lin = fma(-2.0 * k, zt, Cc);
+                const double p0 = over ? INFINITY : lin - b0 * lk + g0, pp = over ? INFINITY : lin - b1 * lk + g1;
+                const double pm = over ? INFINITY : lin - b2 * lk + g2;
+                fit_sums_add(v, p0, pp, pm, use_pm, rh, over ? NAN : 0.0, k, Ctx::ldg(obs + i));
+            }
+        }
+
+        // ---- order-only tables of the nv vectors, built side by side (the product scans overlap) -----------------
+        if (nS > nT) {
+            if (L == 1) {
+                for (int u = 0; u < nv; ++u) {
+                    const double a1 = COEF[u * FC_COUNT + FC_A1];
+                    double *CT = CTg + u * (CB_MILLER_NMAX + 1);
+                    double c = a1;
+                    CT[0] = 1.0; CT[1] = a1;
+                    for (int n = 2; n <= CB_MILLER_NMAX; ++n) { c *= fma(a1, Ctx::ldg(rn + n), (double)(n - 1)); CT[n] = c; }
+                }
+            } else {
+                double a1v[3], q[3][3], incl[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    a1v[u] = C0[(u < nv ? u : 0) * FC_COUNT + FC_A1];
+                    double run = 1.0;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int n = 3 * lane + 2 + j;
+                        const double g = n <= CB_MILLER_NMAX ? fma(a1v[u], Ctx::ldg(rn + n), (double)(n - 1)) : 1.0;
+                        run *= g;
+                        q[u][j] = run;
+                    }
+                    incl[u] = run;
+                }
+#pragma unroll 1
+                for (int d = 1; d < L; d <<= 1) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const double t = cx.shfl_up(incl[u], d);
+                        if (lane >= d) incl[u] *= t;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    double excl = cx.shfl_up(incl[u], 1);
+                    if (lane == 0) excl = 1.0;
+                    const double base = a1v[u] * excl;
+                    if (u < nv) {
+                        double *CT = CTg + u * (CB_MILLER_NMAX + 1);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const int n = 3 * lane + 2 + j;
+                            if (n <= CB_MILLER_NMAX) CT[n] = base * q[u][j];
+                        }
+                        if (lane == 0) { CT[0] = 1.0; CT[1] = a1v[u]; }
+                    }
+                }
+            }
+        }
+        if (nT > 0) {
+#pragma unroll 1
+            for (int j = 1 + lane; j < CB_TEMME_TAB; j += L) {
+#pragma unroll 1
+                for (int u = 0; u < nv; ++u) {
+                    const double mu = C0[u * FC_COUNT + FC_MU];
+                    RPQg[u * CB_TEMME_TAB + j] = make_double2(1.0 / ((double)j - mu), 1.0 / ((double)j + mu));
+                }
+            }
+        }
+        cx.sync_warp();
+
+        // ---- chunks of P = L / nv consecutive points x nv vectors: lane = point * nv + vector ---------------------
+        const int VL = L >= nv ? nv : 1;              // vectors side by side in the lanes (1 under serial emulation)
+        const int P = L / VL;
+        const int il = lane / VL, vl = lane - il * VL;
+        const auto RNJ = Ctx::shared_view(RNJg);
+#pragma unroll 1
+        for (int c0 = 0; c0 < nS; c0 += P) {
+            const int c1 = c0 + P < nS ? c0 + P : nS;
+            const int i = c0 + il;
+            const bool act = il < P && i < c1;
+            const bool temme = i < nT;
+            double ph0 = 0.0, phs1 = 0.0, phs2 = 0.0, jd = 0.0;      // this lane's Phi (serial emulation: of all vectors)
+#pragma unroll 1
+            for (int u = vl; u < nv; u += VL) {
+                const auto CV = Ctx::shared_view((const double *)(COEF + u * FC_COUNT));
+                const double mu = CV[FC_MU], a1 = CV[FC_A1];
+                double a = 0.0, b = 0.0;              // K_mu, K_mu+1 (Temme: unscaled; Miller: times e^x)
+                if (temme) {
+                    if (act) {
+                        const double d = -(Ctx::ldg(logk + i) + lhdz);      // ln(2/x)
+                        const double sg = mu * d;
+                        const double ee = cb_exp(sg), ei = 1.0 / ee;
+                        const double shd = fabs(sg) < 1e-4 ? d * (1.0 + sg * sg * (1.0 / 6.0)) : 0.5 * (ee - ei) * CV[FC_RMU];
+                        double ff = CV[FC_SINC] * (CV[FC_GAM1] * 0.5 * (ee + ei) + CV[FC_GAM2] * shd);
+                        double p = CV[FC_HP] * ee, q = CV[FC_HQ] * ei, c = 1.0;
+                        const double x2 = 0.5 * Ctx::ldg(kh + i) * dz, dd = x2 * x2;
+                        double sum = ff, sum1 = p;
+                        const auto RPQ = Ctx::shared_view((const double2 *)(RPQg + u * CB_TEMME_TAB));
+#pragma unroll 1
+                        for (int j = 1; j < CB_TEMME_TAB; ++j) {
+                            const double fj = (double)j;
+                            const double2 r = RPQ[j];
+                            ff = (fj * ff + p + q) * (r.x * r.y);
+                            c *= dd * RNJ[j];
+                            p *= r.x;
+                            q *= r.y;
+                            const double del = c * ff;
+                            sum += del;
+                            sum1 = fma(c, p - fj * ff, sum1);
+                            if (fabs(del) < fabs(sum) * CB_KNU_EPS) break;
+                        }
+                        a = sum;
+                        b = sum1 * (2.0 * Ctx::ldg(rk + i) * rdz);
+                    }
+                } else if (c1 > nT) {
+                    // Miller backward recurrence, trip count uniform over the chunk (from its smallest Miller x)
+                    const int ii = act ? i : c1 - 1;
+                    const double xi = Ctx::ldg(kh + ii) * dz;
+                    int N = (int)(12.0 + 140.0 * (Ctx::ldg(rk + (c0 > nT ? c0 : nT)) * rdz)) + 1;
+                    if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
+                    const auto CT = Ctx::shared_view((const double *)(CTg + u * (CB_MILLER_NMAX + 1)));
+                    double yp = 0.0, y = 1.0, S = CT[N];
+                    double tn = 2.0 * (double)N;                              // 2n
+                    double an1 = -(a1 + (double)N * (double)(N + 1));         // a_{n+1}
+                    const double twox = 2.0 * xi;
+                    double bn = tn + twox;                                    // b_n = 2(n + x)
+#pragma unroll 2
+                    for (int n = N; n >= 1; --n) {
+                        const double cm = CT[n - 1];
+                        const double ym = fma(bn, y, an1 * yp);
+                        yp = y;
+                        y = ym;
+                        S = fma(cm, y, S);
+                        an1 += tn;                                            // a_n = a_{n+1} + 2n
+                        tn -= 2.0;
+                        bn = tn + twox;
+                    }
+                    if (act) {
+                        const double invx = Ctx::ldg(rk + ii) * rdz;
+                        const double sc = cb_pow2_inverse_of(S);
+                        const double cS = Ctx::ldg(sq + ii) * CV[FC_RSDZ] / (S * sc);
+                        const double ys = y * sc, yps = yp * sc;
+                        a = cS * ys;
+                        b = cS * fma(mu + xi + 0.5, ys, -a1 * yps) * invx;
+                    }
+                }
+                // ---- F: scale to K e^-x, raise the order, bracket e^-x = Gamma(nu)/4 (1 + e^-2x) - hx (K_nu e^-x), log
+                if (act) {
+                    const double k = Ctx::ldg(kh + i), lk = Ctx::ldg(logk + i), xi = k * dz;
+                    const double ex = cb_exp(temme ? -xi : -2.0 * xi);
+                    const double e2 = temme ? ex * ex : ex;
+                    a *= ex;
+                    b *= ex;
+                    const double tox = 2.0 * Ctx::ldg(rk + i) * rdz;
+                    const int nl = (int)CV[FC_NL];
+#pragma unroll 1
+                    for (int j = 1; j < nl; ++j) {
+                        const double c = fma((mu + (double)j) * tox, b, a);
+                        a = b;
+                        b = c;
+                    }
+                    const double hx = cb_exp(CV[FC_NU] * (lk + lhdz));
+                    const double qg = CV[FC_QG];
+                    const double br = fma(qg, 1.0 + e2, -b * hx);
+                    const double ph = fma(-2.0 * k, zt, Cc) - CV[FC_BM1] * lk + cb_log(CV[FC_LEAD] * br);
+                    if (u == 0) jd = k * fma(hx, a + b, -2.0 * qg * e2) / br;
+                    if (L == 1) { if (u == 0) ph0 = ph; else if (u == 1) phs1 = ph; else phs2 = ph; }
+                    else ph0 = ph;
+                }
+            }
+            // the lanes of one point hand their Phi to the lane of vector 0, which accumulates the point
+            double pp = phs1, pm = phs2;
+            if (L != 1) {
+                const int base = lane - vl;
+                pp = cx.shfl(ph0, (base + 1) & (L - 1));
+                pm = cx.shfl(ph0, (base + 2) & (L - 1));
+            }
+            if (act && vl == 0) fit_sums_add(v, ph0, pp, use_pm ? pm : 0.0, use_pm, rh, jd, Ctx::ldg(kh + i), Ctx::ldg(obs + i));
+        }
+    }
+
+    // 16 sums over the lanes by a transposing butterfly: every level halves the sums a lane carries; lane l ends
+    // with sum number (bits 4..1 of l, most significant first)
+    if (L == 32) {
+        int mine = 0;
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {
+            const int m = 16 >> lv, n = 8 >> lv;
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const double send = up ? v[j] : v[j + n], keep = up ? v[j + n] : v[j];
+                v[j] = keep + cx.shfl_xor(send, m);
+            }
+            mine = 2 * mine + (up ? 1 : 0);
+        }
+        v[0] += cx.shfl_xor(v[0], 1);
+        if ((lane & 1) == 0 && mine < 15) sums_out[mine] = v[0];
+    } else {
+        for (int q = 0; q < 15; ++q) sums_out[q] = v[q];
+    }
+    cx.sync_warp();
+}
+
 // 0.5 sum (p0 - obs)^2 over the slab (every lane returns the total).
 template <class Ctx>
 CB_BODY double slab_half_ssq(const Ctx &cx, const WarpSlab &W, int lane) {

@@ -246,7 +246,41 @@ void emu_misfit(const double *kh, int nk, const double *phi, int64_t phi_stride,
     }
 }
 
-// mode 0: SerialCtx (one lane per warp, fast); mode 1: HostCtx (32 pthreads per warp, checks the shuffles)
+// The batched fit under emulation: begin, `rounds` rounds of (evaluation, step) over the list of unfinished
+// windows, then the per-warp finish -- the device's sequence (model.cu:cb_fit_batch_rows).
+// mode 0: SerialCtx (one lane per warp, fast); mode 1: HostCtx (32 pthreads per warp, checks the shuffles).
+static int emu_fit_run(FitParams &P, int mode, int rounds) {
+    const int64_t n = P.nwin;
+    std::vector<double> state(n * CB_FIT_STATE_STRIDE), coef(n * 3 * FC_COUNT), sums(n * 16);
+    std::vector<int32_t> la(n + 1), lb(n + 1);
+    unsigned count[6] = {(unsigned)n, 0, 0, 0, 0, 0};
+    P.state = state.data(); P.coef = coef.data(); P.sums = sums.data(); P.list_in = la.data(); P.list_out = lb.data();
+    P.count = count;
+    for (int64_t w = 0; w < n; ++w) fit_begin_window(P, w);
+    std::vector<double> sm(fit_finish_smem_bytes(2) / sizeof(double) + 8);
+    for (int r = 0; r < rounds; ++r) {
+        P.round = r;
+        if (mode == 0) {
+            SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
+            fit_eval_body(cx, P);
+        } else {
+            emu_launch(2, 64, fit_eval_smem_bytes(2), [&](const HostCtx &cx) { fit_eval_body(cx, P); });
+        }
+        SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
+        const unsigned cnt = count[r % 3];
+        for (unsigned e = 0; e < cnt; ++e) fit_step_entry(cx, P, (int64_t)e);
+        std::swap(P.list_in, P.list_out);
+    }
+    P.round = rounds;
+    if (mode == 0) {
+        SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
+        fit_finish_body(cx, P);
+    } else {
+        emu_launch(2, 64, fit_finish_smem_bytes(2), [&](const HostCtx &cx) { fit_finish_body(cx, P); });
+    }
+    return 0;
+}
+
 int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_fit_options *opt, const double *x0,
             double *x_out, double *f_out, int32_t *niter, int32_t *status, int32_t *nfev, int mode) {
     FitParams P;
@@ -254,18 +288,7 @@ int emu_fit(const double *kh, int nk, const double *phi, int64_t nwin, const cb_
     const std::vector<double> ktab = emu_ktable(kh, nk);
     P.kh = kh; P.ktab = ktab.data(); P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.x0_dev = x0;
     P.x_out = x_out; P.f_out = f_out; P.niter = niter; P.status = status; P.nfev = nfev;
-    if (mode == 0) {
-        P.warps_per_block = 1;
-        std::vector<double> sm(fit_slab_doubles(nk));
-        for (int64_t w = 0; w < nwin; ++w) {
-            SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
-            fit_body(cx, P);
-        }
-    } else {
-        P.warps_per_block = 2;
-        emu_launch((int)((nwin + 1) / 2), 64, 2 * fit_slab_doubles(nk) * sizeof(double), [&](const HostCtx &cx) { fit_body(cx, P); });
-    }
-    return 0;
+    return emu_fit_run(P, mode, mode == 0 ? 6 : 3);
 }
 
 void emu_tanaka(const double *k, int nk, const double *lnphi, const double *sigma, int64_t nwin, double a0, double a1,
@@ -367,13 +390,7 @@ int emu_fit_rows(const double *kh, int nk, const double *phi, int64_t nwin, cons
     const std::vector<double> ktab = emu_ktable(kh, nk);
     P.kh = kh; P.ktab = ktab.data(); P.nk = nk; P.phi = phi; P.nwin = nwin; P.opt = *opt; P.prior_mu_dev = prior_mu_rows;
     P.x_out = x_out; P.f_out = f_out;
-    P.warps_per_block = 1;
-    std::vector<double> sm(fit_slab_doubles(nk));
-    for (int64_t w = 0; w < nwin; ++w) {
-        SerialCtx cx{0, 1, (int)w, (int)nwin, reinterpret_cast<char *>(sm.data())};
-        fit_body(cx, P);
-    }
-    return 0;
+    return emu_fit_run(P, 0, 4);
 }
 
 int emu_mh(const double *kh, int nk, const double *phi, int64_t nwin, const cb_mh_options *opt, const double *x0,

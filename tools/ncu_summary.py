@@ -122,7 +122,7 @@ for kn in dict.fromkeys(names):
     print("stall reasons: " + ", ".join("%s %.1f%%" % (k.replace("stall_", ""), 100.0 * v / st)
                                           for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:8]) + "\n")
     print("| file:line | samples % | warp-inst % | lanes |\n|---|---|---|---|")
-    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:18]:
+    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][int(os.environ.get("NCU_SORT", "0"))])[:int(os.environ.get("NCU_TOP", "18"))]:
         print("| %s:%d | %.2f | %.2f | %.1f |" % (key[0], key[1], 100.0 * a[0] / max(1, tot[0]), 100.0 * a[1] / max(1, tot[1]),
                                                  a[2] / max(1, a[1])))
     print()
