@@ -38,6 +38,7 @@
 // the reference is converged the parameters agree to ~1e-5 relative (tests/test_gpu_parity.py::_check_fit,
 // tests/test_gpu_config3.py; reference self-sensitivity on the rest: tests/golden/make_golden_cfg3.py).
 #pragma once
+#include <stddef.h>
 #include "model_eval.cuh"
 
 struct FitParams {
@@ -56,7 +57,12 @@ struct FitParams {
     int32_t *nfev;          // [nwin] or NULL: model evaluations (one = nk forward-model points)
     // scratch of the batched rounds (library-owned, see cb_fit_batch_rows): per window the solver state, the
     // coefficients of its next evaluation and the sums of its last one; two lists of unfinished windows
-    double *state;          // [nwin, CB_FIT_STATE_STRIDE]
+    double *state;          // [CB_FIT_PERSIST_DOUBLES, stride]: field-major, so that the threads of the step kernel
+                            //      (one window each) read and write whole lines
+    int64_t stride;         // windows the scratch arrays are laid out for (>= nwin)
+    double *tmpl;           // [CB_FIT_STATE_DOUBLES]: the initial state for opt.x0 and opt.prior_mu, built once per
+                            //      launch (fit_template_body); carries the launch's constants (bounds in the solver
+                            //      coordinate, cosh wall, prior weights)
     double *coef;           // [nwin, 3 FC_COUNT]
     double *sums;           // [nwin, 16]
     int32_t *list_in, *list_out;       // unfinished windows of this round / of the next one
@@ -74,25 +80,32 @@ CB_HD int tri(int i, int j) {   // i <= j
 // Solver state of one window, in the warp's shared-memory slab.  The 4x4 algebra is done by lane 0
 // (the other lanes wait at the next warp barrier); the model evaluations are done by all lanes.
 struct FitState {
-    double x[4], lb[4], ub[4];
+    // ---- what a window carries from round to round (saved in the scratch arrays, CB_FIT_PERSIST_DOUBLES doubles) ----
+    double x[4];
     double f, g[4], H[10];        // current iterate: objective, gradient, Gauss-Newton matrix (+ prior precision)
     double B[10];                 // quasi-Newton metric (packed upper triangle)
     double d[4], gd;              // search direction and g.d
     double xt[4], dec, move, pen_t, hb;   // trial point, g.(xt-x), max |xt-x|, prior penalty at xt, beta step
-    double fn, gn[4], Hn[10];     // full evaluation at the accepted trial point
-    double pmu[4], pw[4];         // prior mean and inverse variance (0 = no prior)
-    double one;                   // 1.0 (the dPhi/dC column of the Jacobian, read with stride 0)
     double pt[4];                 // physical parameters (beta, zt, dz, C) of the trial point
-    double cu, sdz;               // solver coordinate u = exp(-cu dz) (cu = 0: u = dz); sdz = d dz / d u at the trial point
-    int32_t okn, fresh, stall, status, action, it, nfev, mask;
+    double sdz;                   // d dz / d u at the trial point (solver coordinate u = exp(-cu dz); cu = 0: u = dz)
+    double alpha;                 // step length of the staged trial
+    int32_t fresh, stall, status, action, it, nfev, mask;
     int32_t central;              // derivative evaluations use the central difference in beta from now on
     int32_t gcentral;             // the gradient of the current iterate was taken with the central difference
     int32_t use_pm;               // the evaluation being reduced staged Phi(beta - hb) (else forward difference)
     int32_t kind;                 // what the staged trial point is: first point, line-search trial, refinement
     int32_t nv;                   // vectors of the round's fused evaluation: 2 (x, beta+hb) or 3 (+ beta-hb)
     int32_t nls;                  // trials of the current line search so far
-    double alpha;                 // step length of the staged trial
+    int32_t pad_;
+    // ---- constants of the launch (pmu: of the window when per-row prior means are given) ----
+    double lb[4], ub[4];
+    double pmu[4], pw[4];         // prior mean and inverse variance (0 = no prior)
+    double cu;
+    // ---- transients of one solver step ----
+    double fn, gn[4], Hn[10];     // full evaluation at the accepted trial point
+    int32_t okn, pad2_;
 };
+#define CB_FIT_PERSIST_DOUBLES ((int)(offsetof(FitState, lb) / 8))
 enum { FIT_KIND_FIRST = 0, FIT_KIND_TRIAL = 1, FIT_KIND_REFINE = 2 };
 #define CB_FIT_STATE_DOUBLES ((int)((sizeof(FitState) + 7) / 8))
 enum { FIT_GO = 0, FIT_DONE = 1, FIT_REFINE = 2 };
@@ -102,11 +115,9 @@ enum { FIT_GO = 0, FIT_DONE = 1, FIT_REFINE = 2 };
 // gradient of the current iterate with the central difference and keeps using it, so every convergence
 // decision is made on central-difference gradients.
 #define CB_FIT_CENTRAL_BELOW 1.0e-3
-// one window's state in the scratch arrays
-#define CB_FIT_STATE_STRIDE (CB_FIT_STATE_DOUBLES | 1)
 CB_HD size_t fit_eval_smem_bytes(int warps) { return (size_t)warps * CB_FIT_TABLE_DOUBLES * sizeof(double); }
 // per-warp shared memory of the finish kernel: tables, state, sums (an even number of doubles: the tables hold double2)
-#define CB_FIT_FINISH_DOUBLES ((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_STRIDE + 16 + 1) & ~1)
+#define CB_FIT_FINISH_DOUBLES ((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 16 + 1) & ~1)
 CB_HD size_t fit_finish_smem_bytes(int warps) { return (size_t)warps * CB_FIT_FINISH_DOUBLES * sizeof(double); }
 static_assert(CB_FIT_TABLE_DOUBLES % 2 == 0 && CB_FIT_CT_DOUBLES % 2 == 0, "double2 tables must stay 16-byte aligned");
 
@@ -555,27 +566,64 @@ CB_BODY void fit_solver_constants(const FitParams &P, int &max_iter, double &gto
 }
 
 // ---- kernels' bodies ----------------------------------------------------------------------------------------
-// begin: one thread per window -- initial state, coefficients of the first evaluation, the identity list.
-CB_BODY void fit_begin_window(const FitParams &P, int64_t w) {
+// The per-window state in the scratch arrays is field-major; a thread (or the lanes of a warp) moves one window's
+// persistent part between it and a FitState.
+CB_BODY void fit_state_load(const FitParams &P, int64_t w, FitState *S, int first, int step) {
+    double *d = reinterpret_cast<double *>(S);
+    for (int i = first; i < CB_FIT_PERSIST_DOUBLES; i += step) d[i] = P.state[(int64_t)i * P.stride + w];
+}
+CB_BODY void fit_state_store(const FitParams &P, int64_t w, const FitState *S) {
+    const double *d = reinterpret_cast<const double *>(S);
+    for (int i = 0; i < CB_FIT_PERSIST_DOUBLES; ++i) P.state[(int64_t)i * P.stride + w] = d[i];
+}
+// constants of the launch from the template; the window's own prior means where the caller gave per-row ones
+CB_BODY void fit_state_constants(const FitParams &P, int64_t w, FitState *S) {
+    const FitState *T = reinterpret_cast<const FitState *>(P.tmpl);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { S->lb[j] = T->lb[j]; S->ub[j] = T->ub[j]; S->pmu[j] = T->pmu[j]; S->pw[j] = T->pw[j]; }
+    S->cu = T->cu;
+    if (P.prior_mu_dev) {
+        const double *row = P.prior_mu_dev + w * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (!isnan(P.opt.prior_mu[j]) && !isnan(row[j])) S->pmu[j] = row[j];
+    }
+}
+
+// template: one thread -- the initial state for the launch's common start point and priors.
+CB_BODY void fit_template_body(const FitParams &P) {
     const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
     const bool sorted = meta[0] != 0.0;
     FitState S;
     memset(&S, 0, sizeof(S));
-    fit_init(&S, &P.opt, P.x0_dev ? P.x0_dev + w * 4 : P.opt.x0, P.prior_mu_dev ? P.prior_mu_dev + w * 4 : nullptr,
-             sorted ? meta[1] : 0.0, sorted ? meta[2] : 0.0);
-    fit_stage_coefs(&S, P.coef + w * (3 * FC_COUNT));
-    double *dst = P.state + w * CB_FIT_STATE_STRIDE;
+    fit_init(&S, &P.opt, P.opt.x0, nullptr, sorted ? meta[1] : 0.0, sorted ? meta[2] : 0.0);
     const double *src = reinterpret_cast<const double *>(&S);
-    for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) dst[i] = src[i];
+    for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) P.tmpl[i] = src[i];
+    P.count[0] = (unsigned)P.nwin;
+    for (int q = 1; q < 6; ++q) P.count[q] = 0u;
+}
+
+// begin: one thread per window -- initial state (the template, or its own start point / prior means), coefficients
+// of the first evaluation, the identity list.
+CB_BODY void fit_begin_window(const FitParams &P, int64_t w) {
+    FitState S;
+    if (P.x0_dev || P.prior_mu_dev) {
+        const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
+        const bool sorted = meta[0] != 0.0;
+        memset(&S, 0, sizeof(S));
+        fit_init(&S, &P.opt, P.x0_dev ? P.x0_dev + w * 4 : P.opt.x0, P.prior_mu_dev ? P.prior_mu_dev + w * 4 : nullptr,
+                 sorted ? meta[1] : 0.0, sorted ? meta[2] : 0.0);
+    } else {
+        double *d = reinterpret_cast<double *>(&S);
+        for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) d[i] = P.tmpl[i];
+    }
+    fit_stage_coefs(&S, P.coef + w * (3 * FC_COUNT));
+    fit_state_store(P, w, &S);
     P.list_in[w] = (int32_t)w;
 }
 template <class Ctx>
 CB_BODY void fit_begin_body(const Ctx &cx, const FitParams &P) {
     const int64_t w = (int64_t)cx.bid() * cx.nthreads() + cx.tid();
-    if (w == 0) {
-        P.count[0] = (unsigned)P.nwin;
-        for (int q = 1; q < 6; ++q) P.count[q] = 0u;
-    }
     if (w < P.nwin) fit_begin_window(P, w);
 }
 
@@ -604,8 +652,32 @@ CB_BODY void fit_eval_body(const Ctx &cx, const FitParams &P) {
         const double *cg = P.coef + w * (3 * FC_COUNT);
         for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = cg[j];
         cx.sync_warp();
-        fit_eval_window(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, P.sums + w * 16);
+        fit_eval_window<false>(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, P.sums + w * 16);
     }
+}
+
+// first round of a launch whose windows share the start point (no x0_dev): the model values are the same for every
+// window, so each CTA evaluates them once (warp 0, into shared memory) and every window only forms its sums.
+CB_HD size_t fit_first_smem_bytes(int nk) { return (size_t)(CB_FIT_TABLE_DOUBLES + 4 * nk) * sizeof(double); }
+template <class Ctx>
+CB_BODY void fit_first_body(const Ctx &cx, const FitParams &P) {
+    const int tid = cx.tid(), warp = tid >> 5, lane = tid & 31, L = cx.team_lanes();
+    const int wpb = cx.nthreads() >> 5, nk = P.nk;
+    double *tab = reinterpret_cast<double *>(cx.smem()), *vals = tab + CB_FIT_TABLE_DOUBLES;
+    const double *meta = P.ktab + 3 * nk + (CB_MILLER_NMAX + 1);
+    const int sorted = meta[0] != 0.0 ? 1 : 0;
+    if (warp == 0) {
+        for (int j = lane; j < CB_TEMME_TAB; j += L) tab[CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + j] = P.ktab[3 * nk + j];
+        for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = P.coef[j];      // window 0's = everybody's
+        cx.sync_warp();
+        fit_eval_window<true>(cx, tab, P.kh, P.ktab, nk, sorted, lane, nullptr, nullptr, vals);
+    }
+    cx.sync_block();
+    const double hb = tab[CB_FIT_COEF_OFFSET + FC_AUX];
+    const bool use_pm = tab[CB_FIT_COEF_OFFSET + 2 * FC_COUNT + FC_AUX] == 3.0;
+#pragma unroll 1
+    for (int64_t w = (int64_t)cx.bid() * wpb + warp; w < P.nwin; w += (int64_t)cx.nblocks() * wpb)
+        fit_sums_from_values(cx, vals, P.kh, nk, use_pm, hb, lane, P.phi + w * nk, P.sums + w * 16);
 }
 
 // step: one thread per unfinished window, on a private copy of its state.
@@ -616,12 +688,12 @@ CB_BODY void fit_step_entry(const Ctx &cx, const FitParams &P, int64_t e) {
     fit_solver_constants(P, max_iter, gtol, ftol);
     const int64_t w = P.list_in[e];
     FitState S;
-    double *d = reinterpret_cast<double *>(&S), *g = P.state + w * CB_FIT_STATE_STRIDE;
-    for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) d[i] = g[i];
+    fit_state_load(P, w, &S, 0, 1);
+    fit_state_constants(P, w, &S);
     const bool done = fit_step_window(&S, P.sums + w * 16, gtol, ftol, max_iter, P.coef + w * (3 * FC_COUNT));
     if (done) fit_write_result(P, &S, w);
     else {
-        for (int i = 0; i < CB_FIT_STATE_DOUBLES; ++i) g[i] = d[i];
+        fit_state_store(P, w, &S);
         P.list_out[cx.atomic_inc_u32(P.count + (P.round + 1) % 3)] = (int32_t)w;
     }
 }
@@ -643,7 +715,7 @@ CB_BODY void fit_finish_body(const Ctx &cx, const FitParams &P) {
     double gtol, ftol;
     fit_solver_constants(P, max_iter, gtol, ftol);
     double *tab = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * CB_FIT_FINISH_DOUBLES;
-    double *sd = tab + CB_FIT_TABLE_DOUBLES, *sums = sd + CB_FIT_STATE_STRIDE;
+    double *sd = tab + CB_FIT_TABLE_DOUBLES, *sums = sd + CB_FIT_STATE_DOUBLES;
     FitState *S = reinterpret_cast<FitState *>(sd);
     const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
     const int sorted = meta[0] != 0.0 ? 1 : 0;
@@ -652,12 +724,13 @@ CB_BODY void fit_finish_body(const Ctx &cx, const FitParams &P) {
     for (int64_t e = (int64_t)cx.bid() * wpb + warp; e < (int64_t)n; e += (int64_t)cx.nblocks() * wpb) {
         const int64_t w = P.list_in[e];
         cx.sync_warp();
-        const double *g = P.state + w * CB_FIT_STATE_STRIDE, *cg = P.coef + w * (3 * FC_COUNT);
-        for (int i = lane; i < CB_FIT_STATE_DOUBLES; i += L) sd[i] = g[i];
+        const double *cg = P.coef + w * (3 * FC_COUNT);
+        fit_state_load(P, w, S, lane, L);
+        if (lane == 0) fit_state_constants(P, w, S);
         for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = cg[j];
         cx.sync_warp();
         for (;;) {
-            fit_eval_window(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, sums);
+            fit_eval_window<false>(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, sums);
             if (lane == 0 && fit_step_window(S, sums, gtol, ftol, max_iter, tab + CB_FIT_COEF_OFFSET)) fit_write_result(P, S, w);
             cx.sync_warp();
             if (S->action != FIT_GO) break;

@@ -77,10 +77,15 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) mi
 // The MAP fit as rounds of two kernels over the list of unfinished windows (fit_body.cuh): the fused model
 // evaluation (one warp per window, persistent grid, entries claimed from a counter) and the scalar solver step (one
 // thread per window); fit_finish_kernel runs the stragglers to the end, one warp each.
+#ifndef CB_FIT_EVAL_WARPS
 #define CB_FIT_EVAL_WARPS 8
+#endif
+#ifndef CB_FIT_EVAL_CTAS_PER_SM
 #define CB_FIT_EVAL_CTAS_PER_SM 3
+#endif
 #define CB_FIT_FINISH_WARPS 4
-__global__ void __launch_bounds__(256) fit_begin_kernel(const __grid_constant__ FitParams P) {
+__global__ void fit_template_kernel(const __grid_constant__ FitParams P) { fit_template_body(P); }
+__global__ void __launch_bounds__(256, 2) fit_begin_kernel(const __grid_constant__ FitParams P) {
     DevCtx cx{nullptr};
     fit_begin_body(cx, P);
 }
@@ -88,7 +93,11 @@ __global__ void __launch_bounds__(CB_FIT_EVAL_WARPS * CB_WARP, CB_FIT_EVAL_CTAS_
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
     fit_eval_body(cx, P);
 }
-__global__ void __launch_bounds__(128) fit_step_kernel(const __grid_constant__ FitParams P) {
+__global__ void __launch_bounds__(256) fit_first_kernel(const __grid_constant__ FitParams P) {
+    DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
+    fit_first_body(cx, P);
+}
+__global__ void __launch_bounds__(128, 4) fit_step_kernel(const __grid_constant__ FitParams P) {
     DevCtx cx{nullptr};
     fit_step_body(cx, P);
 }
@@ -280,7 +289,7 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     }
     int rc = cb_check_device();
     if (rc) return rc;
-    CB_REQUIRE(nk > 0 && nk <= CB_KTABLE_MAX_NK, "nk out of range");
+    CB_REQUIRE(nk > 0 && nk <= 512, "nk must be in [1, 512]");
     static int env_rounds = -1, sm_count = 0;
     if (env_rounds < 0) {
         const char *e = getenv("CB_FIT_ROUNDS");          // batched rounds before the per-warp finish (tuning)
@@ -292,12 +301,14 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     cudaStream_t st = (cudaStream_t)stream;
     double *ktab = nullptr;
     if ((rc = ktable_make(kh_dev, nk, st, &ktab)) != CB_OK) return rc;
+    CB_CUDA_TRY(cudaFuncSetAttribute(fit_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_eval_smem_bytes(CB_FIT_EVAL_WARPS)));
     // library-owned scratch per (device, stream): state, coefficients, sums, two lists, counters; inputs larger
     // than CB_FIT_PASS_WINDOWS go through it in passes
     const int64_t pass = nwin < CB_FIT_PASS_WINDOWS ? nwin : CB_FIT_PASS_WINDOWS;
-    const size_t per_win = (size_t)(CB_FIT_STATE_STRIDE + 3 * FC_COUNT + 16) * sizeof(double) + 2 * sizeof(int32_t);
+    const size_t per_win = (size_t)(CB_FIT_PERSIST_DOUBLES + 3 * FC_COUNT + 16) * sizeof(double) + 2 * sizeof(int32_t);
+    const size_t head = 64 + (size_t)((CB_FIT_STATE_DOUBLES + 7) & ~7) * sizeof(double);
     char *scratch = nullptr;
-    if ((rc = fit_scratch(st, (size_t)pass * per_win + 64, &scratch)) != CB_OK) return rc;
+    if ((rc = fit_scratch(st, (size_t)pass * per_win + head, &scratch)) != CB_OK) return rc;
     for (int64_t off = 0; off < nwin; off += pass) {
         const int64_t n = nwin - off < pass ? nwin - off : pass;
         FitParams P;
@@ -311,11 +322,14 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
         P.status = status_dev ? status_dev + off : nullptr;
         P.nfev = nfev_dev ? nfev_dev + off : nullptr;
         P.count = reinterpret_cast<unsigned int *>(scratch);
-        P.state = reinterpret_cast<double *>(scratch + 64);
-        P.coef = P.state + (size_t)pass * CB_FIT_STATE_STRIDE;
+        P.tmpl = reinterpret_cast<double *>(scratch + 64);
+        P.state = reinterpret_cast<double *>(scratch + head);
+        P.stride = pass;
+        P.coef = P.state + (size_t)pass * CB_FIT_PERSIST_DOUBLES;
         P.sums = P.coef + (size_t)pass * 3 * FC_COUNT;
         int32_t *la = reinterpret_cast<int32_t *>(P.sums + (size_t)pass * 16), *lb = la + pass;
         P.list_in = la; P.list_out = lb;
+        fit_template_kernel<<<1, 1, 0, st>>>(P);
         fit_begin_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(P);
         int64_t g = (n + CB_FIT_EVAL_WARPS - 1) / CB_FIT_EVAL_WARPS;
         const int eval_grid = (int)(g < (int64_t)sm_count * CB_FIT_EVAL_CTAS_PER_SM ? g : (int64_t)sm_count * CB_FIT_EVAL_CTAS_PER_SM);
@@ -323,7 +337,8 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
         const int step_grid = (int)(g < (int64_t)sm_count * 16 ? g : (int64_t)sm_count * 16);
         for (int r = 0; r < env_rounds; ++r) {
             P.round = r;
-            fit_eval_kernel<<<eval_grid, CB_FIT_EVAL_WARPS * CB_WARP, fit_eval_smem_bytes(CB_FIT_EVAL_WARPS), st>>>(P);
+            if (r == 0 && !P.x0_dev) fit_first_kernel<<<eval_grid, 256, fit_first_smem_bytes(nk), st>>>(P);
+            else fit_eval_kernel<<<eval_grid, CB_FIT_EVAL_WARPS * CB_WARP, fit_eval_smem_bytes(CB_FIT_EVAL_WARPS), st>>>(P);
             fit_step_kernel<<<step_grid, 128, 0, st>>>(P);
             int32_t *t = P.list_in; P.list_in = P.list_out; P.list_out = t;
         }

@@ -531,11 +531,69 @@ CB_HD void fit_sums_add(double *v, double p0, double pp, double pm, bool use_pm,
     v[14] += 1.0;
 }
 
+// exp / log inside the fused evaluation are inlined (three exp and one log site): a call in the chunk loop makes the
+// 16 running sums and the loop state live across it, and at 80 registers they spill around every call.
+CB_HD double cb_log_inline(double x) { return 2.0 * cb_half_log(x); }
+
+// Cold path of the fused evaluation: one point, all vectors, through the reference-order arithmetic (unsorted k,
+// dz <= 0, beta < 0, non-finite parameters ...).  out = (Phi, Phi(beta + hb), Phi(beta - hb), dPhi/ddz).
+CB_NOINLINE_BODY void fit_generic_point(const double *coef, int nv, double k, double lk, double *out) {
+    out[2] = 0.0; out[3] = 0.0;
+    for (int u = 0; u < nv; ++u) {
+        const double *c = coef + u * FC_COUNT;
+        const ModelCoef m = model_coef(c[FC_BETA], c[FC_ZT], c[FC_DZ], c[FC_C]);
+        out[u] = generic_point(&m, k, lk, u == 0 ? out + 3 : nullptr);
+    }
+}
+
+// 16 per-lane sums over the lanes by a transposing butterfly: every level halves the sums a lane carries (16 double
+// shuffles instead of 15 x 5); lane l ends with sum number (bits 4..1 of l, most significant first) and writes it.
+template <class Ctx>
+CB_BODY void fit_sums_reduce(const Ctx &cx, double *v, int lane, double *sums_out) {
+    if (cx.team_lanes() == 32) {
+        int mine = 0;
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {
+            const int m = 16 >> lv, n = 8 >> lv;
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+                const double send = up ? v[j] : v[j + n], keep = up ? v[j + n] : v[j];
+                v[j] = keep + cx.shfl_xor(send, m);
+            }
+            mine = 2 * mine + (up ? 1 : 0);
+        }
+        v[0] += cx.shfl_xor(v[0], 1);
+        if ((lane & 1) == 0 && mine < 15) sums_out[mine] = v[0];
+    } else {
+        for (int q = 0; q < 15; ++q) sums_out[q] = v[q];
+    }
+}
+
+// The 15 sums of one window from stored model values (fit_eval_window<true>) and its spectrum.
+template <class Ctx>
+CB_BODY void fit_sums_from_values(const Ctx &cx, const double *store, const double *kh, int nk, bool use_pm, double hb,
+                                  int lane, const double *obs, double *sums_out) {
+    const int L = cx.team_lanes();
+    const double rh = 1.0 / hb;
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = 0.0;
+#pragma unroll 1
+    for (int i = lane; i < nk; i += L)
+        fit_sums_add(v, store[i], store[nk + i], store[2 * nk + i], use_pm, rh, store[3 * nk + i], Ctx::ldg(kh + i), Ctx::ldg(obs + i));
+    fit_sums_reduce(cx, v, lane, sums_out);
+    cx.sync_warp();
+}
+
 // tab: the warp's tables with COEF filled for nv vectors (FC_AUX: hb, cu, nv); obs: the window's spectrum (global);
 // sums_out[16] receives the sums (any address space; written by 15 lanes after the butterfly).
-template <class Ctx>
+// STORE = true: the model values go to store[0..4 nk) (Phi, Phi(beta + hb), Phi(beta - hb), dPhi/ddz, nk apart) instead
+// of into the sums (obs, sums_out unused): the first evaluation of a launch whose windows share the start point
+// is done once per CTA and every window only forms its own sums from it (fit_sums_from_values).
+template <bool STORE, class Ctx>
 CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const double *ktab, int nk, int sorted,
-                             int lane, const double *obs, double *sums_out) {
+                             int lane, const double *obs, double *sums_out, double *store = nullptr) {
     const int L = cx.team_lanes();
     double *CTg = tab;
     double2 *RPQg = reinterpret_cast<double2 *>(tab + CB_FIT_CT_DOUBLES);
@@ -554,19 +612,12 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
     bool fast = sorted != 0;
     for (int u = 0; u < nv; ++u) fast = fast && C0[u * FC_COUNT + FC_FAST] != 0.0;
     if (!fast) {                                          // generic per-point path, reference nan/inf semantics
-        ModelCoef m[3];
-        for (int u = 0; u < nv; ++u) {
-            const double *c = COEF + u * FC_COUNT;
-            m[u] = model_coef(c[FC_BETA], c[FC_ZT], c[FC_DZ], c[FC_C]);
-        }
 #pragma unroll 1
         for (int i = lane; i < nk; i += L) {
-            const double k = Ctx::ldg(kh + i), lk = Ctx::ldg(logk + i);
-            double jd = 0.0;
-            const double p0 = generic_point(&m[0], k, lk, &jd);
-            const double pp = generic_point(&m[1], k, lk, nullptr);
-            const double pm = use_pm ? generic_point(&m[2], k, lk, nullptr) : 0.0;
-            fit_sums_add(v, p0, pp, pm, use_pm, rh, jd, k, Ctx::ldg(obs + i));
+            double vals[4];
+            fit_generic_point(COEF, nv, Ctx::ldg(kh + i), Ctx::ldg(logk + i), vals);
+            if (STORE) { store[i] = vals[0]; store[nk + i] = vals[1]; store[2 * nk + i] = vals[2]; store[3 * nk + i] = vals[3]; }
+            else fit_sums_add(v, vals[0], vals[1], vals[2], use_pm, rh, vals[3], Ctx::ldg(kh + i), Ctx::ldg(obs + i));
         }
     } else {
         const double dz = C0[FC_DZ], zt = C0[FC_ZT], Cc = C0[FC_C], lhdz = C0[FC_LHDZ], rdz = C0[FC_RDZ];
@@ -599,7 +650,8 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                 const double lin = fma(-2.0 * k, zt, Cc);
                 const double p0 = over ? INFINITY : lin - b0 * lk + g0, pp = over ? INFINITY : lin - b1 * lk + g1;
                 const double pm = over ? INFINITY : lin - b2 * lk + g2;
-                fit_sums_add(v, p0, pp, pm, use_pm, rh, over ? NAN : 0.0, k, Ctx::ldg(obs + i));
+                if (STORE) { store[i] = p0; store[nk + i] = pp; store[2 * nk + i] = pm; store[3 * nk + i] = over ? NAN : 0.0; }
+                else fit_sums_add(v, p0, pp, pm, use_pm, rh, over ? NAN : 0.0, k, Ctx::ldg(obs + i));
             }
         }
 
@@ -686,7 +738,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                     if (act) {
                         const double d = -(Ctx::ldg(logk + i) + lhdz);      // ln(2/x)
                         const double sg = mu * d;
-                        const double ee = cb_exp(sg), ei = 1.0 / ee;
+                        const double ee = exp(sg), ei = 1.0 / ee;
                         const double shd = fabs(sg) < 1e-4 ? d * (1.0 + sg * sg * (1.0 / 6.0)) : 0.5 * (ee - ei) * CV[FC_RMU];
                         double ff = CV[FC_SINC] * (CV[FC_GAM1] * 0.5 * (ee + ei) + CV[FC_GAM2] * shd);
                         double p = CV[FC_HP] * ee, q = CV[FC_HQ] * ei, c = 1.0;
@@ -715,6 +767,9 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                     const double xi = Ctx::ldg(kh + ii) * dz;
                     int N = (int)(12.0 + 140.0 * (Ctx::ldg(rk + (c0 > nT ? c0 : nT)) * rdz)) + 1;
                     if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
+                    // one 8-byte shared load per step (the weight C_n); a_{n+1} = -(a1 + n(n+1)) and b_n = 2(n + x) are
+                    // updated in registers: tabulating a_{n+1} beside C_n saves two additions per step but costs 2.3 KB
+                    // per warp and, at 80 registers, spills (measured 11-16 % slower)
                     const auto CT = Ctx::shared_view((const double *)(CTg + u * (CB_MILLER_NMAX + 1)));
                     double yp = 0.0, y = 1.0, S = CT[N];
                     double tn = 2.0 * (double)N;                              // 2n
@@ -744,7 +799,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                 // ---- F: scale to K e^-x, raise the order, bracket e^-x = Gamma(nu)/4 (1 + e^-2x) - hx (K_nu e^-x), log
                 if (act) {
                     const double k = Ctx::ldg(kh + i), lk = Ctx::ldg(logk + i), xi = k * dz;
-                    const double ex = cb_exp(temme ? -xi : -2.0 * xi);
+                    const double ex = exp(temme ? -xi : -2.0 * xi);
                     const double e2 = temme ? ex * ex : ex;
                     a *= ex;
                     b *= ex;
@@ -756,10 +811,10 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                         a = b;
                         b = c;
                     }
-                    const double hx = cb_exp(CV[FC_NU] * (lk + lhdz));
+                    const double hx = exp(CV[FC_NU] * (lk + lhdz));
                     const double qg = CV[FC_QG];
                     const double br = fma(qg, 1.0 + e2, -b * hx);
-                    const double ph = fma(-2.0 * k, zt, Cc) - CV[FC_BM1] * lk + cb_log(CV[FC_LEAD] * br);
+                    const double ph = fma(-2.0 * k, zt, Cc) - CV[FC_BM1] * lk + cb_log_inline(CV[FC_LEAD] * br);
                     if (u == 0) jd = k * fma(hx, a + b, -2.0 * qg * e2) / br;
                     if (L == 1) { if (u == 0) ph0 = ph; else if (u == 1) phs1 = ph; else phs2 = ph; }
                     else ph0 = ph;
@@ -772,30 +827,14 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                 pp = cx.shfl(ph0, (base + 1) & (L - 1));
                 pm = cx.shfl(ph0, (base + 2) & (L - 1));
             }
-            if (act && vl == 0) fit_sums_add(v, ph0, pp, use_pm ? pm : 0.0, use_pm, rh, jd, Ctx::ldg(kh + i), Ctx::ldg(obs + i));
+            if (act && vl == 0) {
+                if (STORE) { store[i] = ph0; store[nk + i] = pp; store[2 * nk + i] = use_pm ? pm : 0.0; store[3 * nk + i] = jd; }
+                else fit_sums_add(v, ph0, pp, use_pm ? pm : 0.0, use_pm, rh, jd, Ctx::ldg(kh + i), Ctx::ldg(obs + i));
+            }
         }
     }
 
-    // 16 sums over the lanes by a transposing butterfly: every level halves the sums a lane carries; lane l ends
-    // with sum number (bits 4..1 of l, most significant first)
-    if (L == 32) {
-        int mine = 0;
-#pragma unroll
-        for (int lv = 0; lv < 4; ++lv) {
-            const int m = 16 >> lv, n = 8 >> lv;
-            const bool up = (lane & m) != 0;
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-                const double send = up ? v[j] : v[j + n], keep = up ? v[j + n] : v[j];
-                v[j] = keep + cx.shfl_xor(send, m);
-            }
-            mine = 2 * mine + (up ? 1 : 0);
-        }
-        v[0] += cx.shfl_xor(v[0], 1);
-        if ((lane & 1) == 0 && mine < 15) sums_out[mine] = v[0];
-    } else {
-        for (int q = 0; q < 15; ++q) sums_out[q] = v[q];
-    }
+    if (!STORE) fit_sums_reduce(cx, v, lane, sums_out);
     cx.sync_warp();
 }
 

@@ -251,16 +251,25 @@ void emu_misfit(const double *kh, int nk, const double *phi, int64_t phi_stride,
 // mode 0: SerialCtx (one lane per warp, fast); mode 1: HostCtx (32 pthreads per warp, checks the shuffles).
 static int emu_fit_run(FitParams &P, int mode, int rounds) {
     const int64_t n = P.nwin;
-    std::vector<double> state(n * CB_FIT_STATE_STRIDE), coef(n * 3 * FC_COUNT), sums(n * 16);
+    std::vector<double> state(n * CB_FIT_PERSIST_DOUBLES), coef(n * 3 * FC_COUNT), sums(n * 16), tmpl(CB_FIT_STATE_DOUBLES);
     std::vector<int32_t> la(n + 1), lb(n + 1);
     unsigned count[6] = {(unsigned)n, 0, 0, 0, 0, 0};
     P.state = state.data(); P.coef = coef.data(); P.sums = sums.data(); P.list_in = la.data(); P.list_out = lb.data();
-    P.count = count;
+    P.count = count; P.stride = n; P.tmpl = tmpl.data();
+    fit_template_body(P);
     for (int64_t w = 0; w < n; ++w) fit_begin_window(P, w);
     std::vector<double> sm(fit_finish_smem_bytes(2) / sizeof(double) + 8);
     for (int r = 0; r < rounds; ++r) {
         P.round = r;
-        if (mode == 0) {
+        if (r == 0 && !P.x0_dev) {          // common start point: model values once per CTA, sums per window
+            if (mode == 0) {
+                std::vector<double> sf(fit_first_smem_bytes(P.nk) / sizeof(double) + 8);
+                SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sf.data())};
+                fit_first_body(cx, P);
+            } else {
+                emu_launch(2, 64, fit_first_smem_bytes(P.nk), [&](const HostCtx &cx) { fit_first_body(cx, P); });
+            }
+        } else if (mode == 0) {
             SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
             fit_eval_body(cx, P);
         } else {
