@@ -81,6 +81,31 @@ def window_origins(g, window, xc, yc):
     return (iy - half).astype(np.int32), (ix - half).astype(np.int32), 2 * half + 1
 
 
+def share_rows_for_list(g, window, xc, yc, sample=4096):
+    """The spectrum path (shared row spectra or window by window) for a centroid list that is about to be split
+    into blocks -- over ranks, devices or scratch slices.  SpectrumPlan.run decides per call from the row reuse
+    of the windows it is given, and the two paths agree to ~1e-14 but not bit for bit; a split list must therefore
+    take ONE decision, from the same data on every rank: the row reuse of its first `sample` windows."""
+    xc, yc = np.asarray(xc, dtype=np.float64), np.asarray(yc, dtype=np.float64)
+    m = int(min(xc.size, sample))
+    if m <= 1:
+        return False
+    iy0, ix0, nw = window_origins(g, window, xc[:m], yc[:m])
+    groups = np.unique(ix0).size
+    span = int(iy0.max()) - int(iy0.min()) + nw
+    return float(m) * nw / (float(groups) * span) >= SpectrumPlan.SHARE_MIN_REUSE
+
+
+def share_rows_for_lattice(g, window, xs, ys):
+    """share_rows_for_list for the lattice xs x ys (x fastest)."""
+    if len(xs) * len(ys) <= 1:
+        return False
+    half = window_nodes(window, g.dx)[1]
+    iy = nearest_node(g.ycoords, np.asarray(ys, dtype=np.float64))
+    span = int(iy.max()) - int(iy.min()) + 2 * half + 1
+    return float(len(ys)) * (2 * half + 1) / span >= SpectrumPlan.SHARE_MIN_REUSE
+
+
 class Lattice:
     """The centroid lattice xs x ys (x fastest) standing in for create_centroid_list's two raveled lists:
     the batch entry points accept it in place of (xc_list, yc_list) and never expand it on the host."""

@@ -69,6 +69,8 @@ struct FitParams {
     unsigned int *count;               // [6]: list lengths of the rounds r, r+1, r+2 (rotating), then the
                                        //      work counters of the evaluation kernels of those rounds
     int32_t round;
+    int32_t handover;       // the batched rounds stop once fewer windows than this are unfinished: fit_finish_body
+                            // takes them, a CTA per window (few windows make a round latency bound)
 };
 
 enum { FIT_CONVERGED_PG = 0, FIT_CONVERGED_F = 1, FIT_LINESEARCH = 2, FIT_MAXITER = 3, FIT_BAD_START = 4 };
@@ -116,9 +118,6 @@ enum { FIT_GO = 0, FIT_DONE = 1, FIT_REFINE = 2 };
 // decision is made on central-difference gradients.
 #define CB_FIT_CENTRAL_BELOW 1.0e-3
 CB_HD size_t fit_eval_smem_bytes(int warps) { return (size_t)warps * CB_FIT_TABLE_DOUBLES * sizeof(double); }
-// per-warp shared memory of the finish kernel: tables, state, sums (an even number of doubles: the tables hold double2)
-#define CB_FIT_FINISH_DOUBLES ((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 16 + 1) & ~1)
-CB_HD size_t fit_finish_smem_bytes(int warps) { return (size_t)warps * CB_FIT_FINISH_DOUBLES * sizeof(double); }
 static_assert(CB_FIT_TABLE_DOUBLES % 2 == 0 && CB_FIT_CT_DOUBLES % 2 == 0, "double2 tables must stay 16-byte aligned");
 
 // Solve B d = -g on the free variables (frozen ones get d = 0) by Cholesky; returns false when the
@@ -543,7 +542,7 @@ CB_BODY bool fit_step_window(FitState *S, const double *sums, double gtol, doubl
         fit_backtrack(S, ft, gtol);
     }
     if (S->action != FIT_GO) return true;
-    fit_stage_coefs(S, coef);
+    if (coef) fit_stage_coefs(S, coef);
     return false;
 }
 
@@ -637,6 +636,7 @@ CB_BODY void fit_eval_body(const Ctx &cx, const FitParams &P) {
         P.count[(P.round + 2) % 3] = 0u;
         P.count[3 + (P.round + 2) % 3] = 0u;
     }
+    if ((int64_t)n < (int64_t)P.handover) return;       // left to the finish kernel (the step kernel passes the list on)
     double *tab = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * CB_FIT_TABLE_DOUBLES;
     const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
     const int sorted = meta[0] != 0.0 ? 1 : 0;
@@ -680,7 +680,8 @@ CB_BODY void fit_first_body(const Ctx &cx, const FitParams &P) {
         fit_sums_from_values(cx, vals, P.kh, nk, use_pm, hb, lane, P.phi + w * nk, P.sums + w * 16);
 }
 
-// step: one thread per unfinished window, on a private copy of its state.
+// step: one thread per unfinished window, on a private copy of its state.  (Four lanes per window with the three
+// coefficient sets side by side was measured slower: 3.4 vs 2.3 ms over the rounds of config 3.)
 template <class Ctx>
 CB_BODY void fit_step_entry(const Ctx &cx, const FitParams &P, int64_t e) {
     int max_iter;
@@ -701,38 +702,72 @@ template <class Ctx>
 CB_BODY void fit_step_body(const Ctx &cx, const FitParams &P) {
     const int tid = cx.tid(), nt = cx.nthreads();
     const unsigned n = P.count[P.round % 3];
+    if ((int64_t)n < (int64_t)P.handover) {              // handed over: the list travels on unchanged
+        for (int64_t e = (int64_t)cx.bid() * nt + tid; e < (int64_t)n; e += (int64_t)cx.nblocks() * nt) P.list_out[e] = P.list_in[e];
+        if (cx.bid() == 0 && tid == 0) P.count[(P.round + 1) % 3] = n;
+        return;
+    }
 #pragma unroll 1
     for (int64_t e = (int64_t)cx.bid() * nt + tid; e < (int64_t)n; e += (int64_t)cx.nblocks() * nt) fit_step_entry(cx, P, e);
 }
 
-// finish: one warp per window still unfinished after the batched rounds, run to the end.
+// finish: the windows still unfinished after the batched rounds, run to the end -- one CTA per window: its warps
+// share the chunks of every evaluation (fit_eval_window's part / nparts), warp 0 sums the partial sums, takes the
+// solver step on lane 0 and fills the coefficients of the next evaluation on lanes 0..nv-1.  With few windows left
+// a round is latency bound (one warp needs ~50 us for an evaluation and ~20 us for the scalar step).
+// Shared memory (doubles): tables, state, sums[16], partial sums [warps][16].
+CB_HD size_t fit_finish_smem_bytes(int warps) {
+    return (size_t)(((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 1) & ~1) + 16 + 16 * warps) * sizeof(double);
+}
 template <class Ctx>
 CB_BODY void fit_finish_body(const Ctx &cx, const FitParams &P) {
-    const int tid = cx.tid(), warp = tid >> 5, lane = tid & 31, L = cx.team_lanes();
-    const int wpb = cx.nthreads() >> 5;
+    const int tid = cx.tid(), nthr = cx.nthreads(), warp = tid >> 5, lane = tid & 31, L = cx.team_lanes();
+    const int nwarps = nthr >> 5;
     const unsigned n = P.count[P.round % 3];
     int max_iter;
     double gtol, ftol;
     fit_solver_constants(P, max_iter, gtol, ftol);
-    double *tab = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * CB_FIT_FINISH_DOUBLES;
-    double *sd = tab + CB_FIT_TABLE_DOUBLES, *sums = sd + CB_FIT_STATE_DOUBLES;
+    double *tab = reinterpret_cast<double *>(cx.smem());
+    double *sd = tab + CB_FIT_TABLE_DOUBLES;
+    double *sums = tab + ((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 1) & ~1), *wsums = sums + 16;
     FitState *S = reinterpret_cast<FitState *>(sd);
     const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
     const int sorted = meta[0] != 0.0 ? 1 : 0;
-    for (int j = lane; j < CB_TEMME_TAB; j += L) tab[CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + j] = P.ktab[3 * P.nk + j];
+    if (warp == 0)
+        for (int j = lane; j < CB_TEMME_TAB; j += L) tab[CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + j] = P.ktab[3 * P.nk + j];
 #pragma unroll 1
-    for (int64_t e = (int64_t)cx.bid() * wpb + warp; e < (int64_t)n; e += (int64_t)cx.nblocks() * wpb) {
+    for (int64_t e = cx.bid(); e < (int64_t)n; e += cx.nblocks()) {
         const int64_t w = P.list_in[e];
-        cx.sync_warp();
-        const double *cg = P.coef + w * (3 * FC_COUNT);
-        fit_state_load(P, w, S, lane, L);
-        if (lane == 0) fit_state_constants(P, w, S);
-        for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = cg[j];
-        cx.sync_warp();
+        cx.sync_block();
+        if (warp == 0) {
+            const double *cg = P.coef + w * (3 * FC_COUNT);
+            fit_state_load(P, w, S, lane, L);
+            if (lane == 0) fit_state_constants(P, w, S);
+            for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = cg[j];
+        }
+        cx.sync_block();
         for (;;) {
-            fit_eval_window<false>(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, sums);
-            if (lane == 0 && fit_step_window(S, sums, gtol, ftol, max_iter, tab + CB_FIT_COEF_OFFSET)) fit_write_result(P, S, w);
-            cx.sync_warp();
+            fit_eval_window<false>(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, wsums + 16 * warp, nullptr,
+                                   warp, nwarps);
+            cx.sync_block();
+            if (warp == 0) {
+                for (int q = lane; q < 15; q += L) {
+                    double t = 0.0;
+                    for (int ww = 0; ww < nwarps; ++ww) t += wsums[16 * ww + q];
+                    sums[q] = t;
+                }
+                cx.sync_warp();
+                if (lane == 0 && fit_step_window(S, sums, gtol, ftol, max_iter, nullptr)) fit_write_result(P, S, w);
+                cx.sync_warp();
+                if (S->action == FIT_GO) {
+                    const int nv = S->nv;
+                    double *c = tab + CB_FIT_COEF_OFFSET;
+                    for (int v = lane; v < nv; v += L) fit_coef_fill(c + v * FC_COUNT, S->pt, S->hb, v);
+                    cx.sync_warp();
+                    if (lane == 0) { c[FC_AUX] = S->hb; c[FC_COUNT + FC_AUX] = S->cu; c[2 * FC_COUNT + FC_AUX] = (double)nv; }
+                }
+            }
+            cx.sync_block();
             if (S->action != FIT_GO) break;
         }
     }

@@ -290,9 +290,11 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     int rc = cb_check_device();
     if (rc) return rc;
     CB_REQUIRE(nk > 0 && nk <= 512, "nk must be in [1, 512]");
-    static int env_rounds = -1, sm_count = 0;
+    static int env_rounds = -1, env_handover = 0, sm_count = 0;
     if (env_rounds < 0) {
-        const char *e = getenv("CB_FIT_ROUNDS");          // batched rounds before the per-warp finish (tuning)
+        const char *e = getenv("CB_FIT_HANDOVER");        // unfinished windows below which the finish kernel takes over
+        env_handover = e ? atoi(e) : 2048;
+        e = getenv("CB_FIT_ROUNDS");                      // batched rounds at most (tuning)
         env_rounds = e ? atoi(e) : 20;
         int dev = 0;
         CB_CUDA_TRY(cudaGetDevice(&dev));
@@ -329,6 +331,7 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
         P.sums = P.coef + (size_t)pass * 3 * FC_COUNT;
         int32_t *la = reinterpret_cast<int32_t *>(P.sums + (size_t)pass * 16), *lb = la + pass;
         P.list_in = la; P.list_out = lb;
+        P.handover = env_handover;
         fit_template_kernel<<<1, 1, 0, st>>>(P);
         fit_begin_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(P);
         int64_t g = (n + CB_FIT_EVAL_WARPS - 1) / CB_FIT_EVAL_WARPS;
@@ -343,8 +346,7 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
             int32_t *t = P.list_in; P.list_in = P.list_out; P.list_out = t;
         }
         P.round = env_rounds;
-        g = (n + CB_FIT_FINISH_WARPS - 1) / CB_FIT_FINISH_WARPS;
-        const int fin_grid = (int)(g < (int64_t)sm_count * 8 ? g : (int64_t)sm_count * 8);
+        const int fin_grid = (int)(n < (int64_t)sm_count * 8 ? n : (int64_t)sm_count * 8);
         fit_finish_kernel<<<fin_grid, CB_FIT_FINISH_WARPS * CB_WARP, fit_finish_smem_bytes(CB_FIT_FINISH_WARPS), st>>>(P);
     }
     CB_CUDA_TRY(cudaGetLastError());

@@ -591,9 +591,13 @@ CB_BODY void fit_sums_from_values(const Ctx &cx, const double *store, const doub
 // STORE = true: the model values go to store[0..4 nk) (Phi, Phi(beta + hb), Phi(beta - hb), dPhi/ddz, nk apart) instead
 // of into the sums (obs, sums_out unused): the first evaluation of a launch whose windows share the start point
 // is done once per CTA and every window only forms its own sums from it (fit_sums_from_values).
+// part / nparts: the warps of a CTA that work on ONE window together (the stragglers' finish kernel) take the
+// chunks and the closed-form points round robin, warp `part` of `nparts`; the tables are built by part 0 behind a
+// block barrier and every warp delivers partial sums.
 template <bool STORE, class Ctx>
 CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const double *ktab, int nk, int sorted,
-                             int lane, const double *obs, double *sums_out, double *store = nullptr) {
+                             int lane, const double *obs, double *sums_out, double *store = nullptr, int part = 0,
+                             int nparts = 1) {
     const int L = cx.team_lanes();
     double *CTg = tab;
     double2 *RPQg = reinterpret_cast<double2 *>(tab + CB_FIT_CT_DOUBLES);
@@ -613,7 +617,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
     for (int u = 0; u < nv; ++u) fast = fast && C0[u * FC_COUNT + FC_FAST] != 0.0;
     if (!fast) {                                          // generic per-point path, reference nan/inf semantics
 #pragma unroll 1
-        for (int i = lane; i < nk; i += L) {
+        for (int i = lane + L * part; i < nk; i += L * nparts) {
             double vals[4];
             fit_generic_point(COEF, nv, Ctx::ldg(kh + i), Ctx::ldg(logk + i), vals);
             if (STORE) { store[i] = vals[0]; store[nk + i] = vals[1]; store[2 * nk + i] = vals[2]; store[3 * nk + i] = vals[3]; }
@@ -644,7 +648,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
             const double b0 = C0[FC_BM1], g0 = C0[FC_LGC], b1 = C0[FC_COUNT + FC_BM1], g1 = C0[FC_COUNT + FC_LGC];
             const double b2 = use_pm ? C0[2 * FC_COUNT + FC_BM1] : 0.0, g2 = use_pm ? C0[2 * FC_COUNT + FC_LGC] : 0.0;
 #pragma unroll 1
-            for (int i = nS + lane; i < nk; i += L) {
+            for (int i = nS + lane + L * part; i < nk; i += L * nparts) {
                 const double k = Ctx::ldg(kh + i), lk = Ctx::ldg(logk + i);
                 const bool over = k * dz > CB_COSH_OVERFLOW;
                 const double lin = fma(-2.0 * k, zt, Cc);
@@ -656,7 +660,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
         }
 
         // ---- order-only tables of the nv vectors, built side by side (the product scans overlap) -----------------
-        if (nS > nT) {
+        if (nS > nT && part == 0) {
             if (L == 1) {
                 for (int u = 0; u < nv; ++u) {
                     const double a1 = COEF[u * FC_COUNT + FC_A1];
@@ -705,7 +709,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                 }
             }
         }
-        if (nT > 0) {
+        if (nT > 0 && part == 0) {
 #pragma unroll 1
             for (int j = 1 + lane; j < CB_TEMME_TAB; j += L) {
 #pragma unroll 1
@@ -715,7 +719,8 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                 }
             }
         }
-        cx.sync_warp();
+        if (nparts > 1) cx.sync_block();
+        else cx.sync_warp();
 
         // ---- chunks of P = L / nv consecutive points x nv vectors: lane = point * nv + vector ---------------------
         const int VL = L >= nv ? nv : 1;              // vectors side by side in the lanes (1 under serial emulation)
@@ -723,7 +728,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
         const int il = lane / VL, vl = lane - il * VL;
         const auto RNJ = Ctx::shared_view(RNJg);
 #pragma unroll 1
-        for (int c0 = 0; c0 < nS; c0 += P) {
+        for (int c0 = part * P; c0 < nS; c0 += nparts * P) {
             const int c1 = c0 + P < nS ? c0 + P : nS;
             const int i = c0 + il;
             const bool act = il < P && i < c1;

@@ -140,7 +140,7 @@ class CurieOptimise(CurieGrid):
         torch.cuda.current_stream().synchronize()
         return host.numpy()
 
-    def _run_blocks(self, n, block, shard=None, as_numpy=True, min_per_worker=None, transpose=False):
+    def _run_blocks(self, n, block, shard=None, as_numpy=True, min_per_worker=None, transpose=False, decide=None):
         """Evaluate `block(obj, lo, hi)` -> device tensor (hi-lo, ...) over range(n) in contiguous blocks and
         return the concatenation in reference order ((C, n) instead of (n, C) with `transpose`).
 
@@ -148,7 +148,10 @@ class CurieOptimise(CurieGrid):
             the full result (the reference's fan-out, optimise.py:386-444, across processes)
           * else over min(max_processors, visible GPUs) devices of this process, one host thread each, every
             device writing its block of one page-locked result array
-          * else on the current device."""
+          * else on the current device.
+
+        `decide()` -> the spectrum path of the WHOLE problem (_plans.share_rows_for_list); when the work is split it
+        is taken once and imposed on every block, so that the result does not depend on how many workers there are."""
         import torch
         if shard is None:
             shard = self.shard
@@ -156,7 +159,10 @@ class CurieOptimise(CurieGrid):
         if shard and _pdist.is_distributed():
             import torch.distributed as dist
             lo, hi = _pdist.shard_range(n, dist.get_rank(), dist.get_world_size())
-            full = tr(_pdist.gather_blocks(block(self, lo, hi), n, dst=None))
+            sh = self._shadow()
+            sh._share_rows = decide() if decide is not None else None
+            full = tr(_pdist.gather_blocks(block(sh, lo, hi), n, dst=None))
+            sh._settle()
             out = self._to_host(full) if as_numpy else full
             self._settle()
             return out
@@ -165,9 +171,11 @@ class CurieOptimise(CurieGrid):
         if ndev > 1:
             box = {}
             lock = threading.Lock()
+            path = decide() if decide is not None else None
 
             def work(lo, hi, dev):
                 sh = self._shadow()
+                sh._share_rows = path
                 t = block(sh, lo, hi)
                 with lock:                     # the first block to finish fixes the result's trailing shape
                     if "host" not in box:
@@ -179,7 +187,12 @@ class CurieOptimise(CurieGrid):
 
             _pdist.fan_out_devices(ndev, n, work)
             return box["host"].numpy() if as_numpy else box["host"].cuda()
-        t = tr(block(self, 0, n))
+        prev = getattr(self, "_share_rows", None)
+        self._share_rows = decide() if decide is not None else None      # the same decision a split run takes
+        try:
+            t = tr(block(self, 0, n))
+        finally:
+            self._share_rows = prev
         out = self._to_host(t) if as_numpy else t
         self._settle()
         return out
@@ -215,7 +228,8 @@ class CurieOptimise(CurieGrid):
             else:
                 g, iy0, ix0, n = self._windows_device(window, xc_list, yc_list)
             plan = _plans.spectrum_plan(n, self.dx, _plans.taper_vector(taper, n, **kwargs))
-            phi, sig = plan.run(g, iy0, ix0, process_subgrid is not None, power)
+            phi, sig = plan.run(g, iy0, ix0, process_subgrid is not None, power,
+                                share_rows=getattr(self, "_share_rows", None))
             return plan.k, phi, sig
         n_probe = _plans.window_nodes(window, self.dx)[1] * 2 + 1
         filt = self._window_filter(process_subgrid, n_probe)
@@ -322,7 +336,8 @@ class CurieOptimise(CurieGrid):
         xc_a, yc_a = np.asarray(xc_list), np.asarray(yc_list)
         return self._run_blocks(len(xc_a), lambda o, lo, hi: o._fit_block(window, xc_a[lo:hi], yc_a[lo:hi], x0, taper,
                                                                           process_subgrid, kwargs),
-                                shard=shard, as_numpy=as_numpy, transpose=_rows_out)
+                                shard=shard, as_numpy=as_numpy, transpose=_rows_out,
+                                decide=lambda: _plans.share_rows_for_list(self, window, xc_a, yc_a))
 
     # ------------------------------------------------------------------ map assembly
     def curie_depth_maps(self, window, spacingX=None, spacingY=None, *, beta=3.0, zt=1.0, dz=10.0, C=5.0,
@@ -372,7 +387,8 @@ class CurieOptimise(CurieGrid):
 
         # the per-device floor is in windows: rows * cols
         allc = self._run_blocks(rows, block, shard=shard, as_numpy=as_numpy,
-                                min_per_worker=max(1, -(-self.MIN_WINDOWS_PER_DEVICE // max(cols, 1))))
+                                min_per_worker=max(1, -(-self.MIN_WINDOWS_PER_DEVICE // max(cols, 1))),
+                                decide=lambda: _plans.share_rows_for_lattice(self, window, xs, ys))
         names = ("beta", "zt", "dz", "C", "curie_depth")
         maps = {nm: allc[:, :, j] for j, nm in enumerate(names)}
         if uncertainty == "sensitivity":
@@ -522,7 +538,8 @@ class CurieOptimise(CurieGrid):
             # the acceptance counts ride along as one more column
             return torch.cat([out.reshape(hi - lo, -1), acc.to(torch.float64).unsqueeze(1)], dim=1)
 
-        res = self._run_blocks(n, block, shard=shard, as_numpy=as_numpy)
+        res = self._run_blocks(n, block, shard=shard, as_numpy=as_numpy,
+                               decide=lambda: _plans.share_rows_for_list(self, window, xc_a, yc_a))
         acc = res[:, -1]
         self.last_accepted = acc.astype(np.int64) if as_numpy else acc.to(torch.int64)
         res = res[:, :-1]
@@ -601,4 +618,5 @@ class CurieOptimise(CurieGrid):
 
         # one device holds n * nsim fits: the per-device floor is in fits
         return self._run_blocks(len(xc_a), block, shard=shard, as_numpy=as_numpy,
-                                min_per_worker=max(1, self.MIN_WINDOWS_PER_DEVICE // max(int(nsim), 1)))
+                                min_per_worker=max(1, self.MIN_WINDOWS_PER_DEVICE // max(int(nsim), 1)),
+                                decide=lambda: _plans.share_rows_for_list(self, window, xc_a, yc_a))

@@ -251,6 +251,7 @@ void emu_misfit(const double *kh, int nk, const double *phi, int64_t phi_stride,
 // mode 0: SerialCtx (one lane per warp, fast); mode 1: HostCtx (32 pthreads per warp, checks the shuffles).
 static int emu_fit_run(FitParams &P, int mode, int rounds) {
     const int64_t n = P.nwin;
+    P.handover = n > 4 ? 3 : 0;                      // small enough to exercise both the rounds and the hand-over
     std::vector<double> state(n * CB_FIT_PERSIST_DOUBLES), coef(n * 3 * FC_COUNT), sums(n * 16), tmpl(CB_FIT_STATE_DOUBLES);
     std::vector<int32_t> la(n + 1), lb(n + 1);
     unsigned count[6] = {(unsigned)n, 0, 0, 0, 0, 0};

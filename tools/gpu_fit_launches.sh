@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-launch durations of the fit kernels of one config-3 step (ncu, gpu__time_duration only).  Usage: <tag>
 TAG=${1:-fit}; OUT=gpurun_out; mkdir -p $OUT
-ARGS="--steps 1 --warmup 0 --no-cpu-baseline --no-extra-configs --mcmc-nsim 0"
+ARGS="--grid ${GRID:-4096} --steps 1 --warmup 0 --no-cpu-baseline --no-extra-configs --mcmc-nsim 0"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^fit_' -c 44 --csv --log-file $OUT/fit_launches_$TAG.csv python bench.py $ARGS > $OUT/ncu_l_$TAG.log 2>&1
 echo "rc=$?"
 python - <<'P'
