@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(256) fit_first_kernel(const __grid_constant__ 
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem_d)};
     fit_first_body(cx, P);
 }
-__global__ void __launch_bounds__(128, 4) fit_step_kernel(const __grid_constant__ FitParams P) {
+#ifndef CB_FIT_STEP_BLOCKS
+#define CB_FIT_STEP_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, CB_FIT_STEP_BLOCKS) fit_step_kernel(const __grid_constant__ FitParams P) {
     DevCtx cx{nullptr};
     fit_step_body(cx, P);
 }

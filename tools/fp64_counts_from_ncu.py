@@ -30,9 +30,17 @@ out = {"source": "ncu thread-level FP64 instruction counts, one launch per kerne
 f_row, c_row = flop("rowspec_kernel"), flop("colspec_kernel")
 out["spectrum_flop_per_window_201"] = (f_row[0] + c_row[0]) / units["windows"]
 out["spectrum_instr"] = {"rowspec_kernel": f_row[1], "colspec_kernel": c_row[1]}
-f_fit = flop("fit_kernel")
-out["fit_flop_per_point"] = f_fit[0] / units["fit_points"]
-out["fit_instr"] = f_fit[1]
+# the fit is a sequence of launches (template, begin, first, evaluation / step rounds, finish): all of them, summed;
+# a point = one wavenumber of one evaluated parameter vector (nfev counts the vectors, speculative ones included)
+fit_kernels = sorted(k for k in per if k.startswith("fit_"))
+tot, parts = 0.0, {}
+for k in fit_kernels:
+    n_launch = len(per[k]["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"])
+    fl = sum(flop(k, i)[0] for i in range(n_launch))
+    parts[k] = {"launches": n_launch, "flop": fl}
+    tot += fl
+out["fit_flop_per_point"] = tot / units["fit_points"]
+out["fit_kernels"] = parts
 f_mh = flop("mh_kernel")
 out["mh_flop_per_step_99"] = f_mh[0] / units["mh_steps"]
 out["mh_instr"] = f_mh[1]
