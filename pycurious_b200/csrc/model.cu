@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(CB_FIT_WARPS * CB_WARP, CB_FIT_CTAS_PER_SM) mi
 #ifndef CB_FIT_EVAL_CTAS_PER_SM
 #define CB_FIT_EVAL_CTAS_PER_SM 3
 #endif
+#ifndef CB_FIT_FINISH_WARPS
 #define CB_FIT_FINISH_WARPS 4
+#endif
 __global__ void fit_template_kernel(const __grid_constant__ FitParams P) { fit_template_body(P); }
 __global__ void __launch_bounds__(256, 2) fit_begin_kernel(const __grid_constant__ FitParams P) {
     DevCtx cx{nullptr};

@@ -4,7 +4,7 @@
 OUT=gpurun_out; mkdir -p $OUT
 for v in "$@"; do
   if [ "$v" = main ]; then unset CB_LIB_PATH; else export CB_LIB_PATH=$PWD/tools/variants/libcurie_$v.so; fi
-  python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-extra-configs --mcmc-nsim 0 2>/dev/null | python -c "
+  python bench.py --grid ${GRID:-4096} --steps 3 --warmup 2 --no-cpu-baseline --no-extra-configs --mcmc-nsim 0 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
