@@ -18,7 +18,7 @@
 //   * non-finite model values give 1e99 exactly like min_func (optimise.py:226-227)
 //
 // Execution structure (round 2).  A window advances in ROUNDS; every round is
-//     fit_eval_window : ONE fused evaluation of (trial, beta+h [, beta-h]) over (point, vector) pairs by a whole
+//     fit_eval_values : ONE fused evaluation of (trial, beta+h [, beta-h]) over (point, vector) pairs by a whole
 //                       warp, ending in the 15 sums of a Gauss-Newton step (model_eval.cuh) -- the derivative
 //                       evaluations of a trial are done speculatively WITH the trial (the first trial of a line
 //                       search is accepted ~90 % of the time);
@@ -117,7 +117,9 @@ enum { FIT_GO = 0, FIT_DONE = 1, FIT_REFINE = 2 };
 // gradient of the current iterate with the central difference and keeps using it, so every convergence
 // decision is made on central-difference gradients.
 #define CB_FIT_CENTRAL_BELOW 1.0e-3
-CB_HD size_t fit_eval_smem_bytes(int warps) { return (size_t)warps * CB_FIT_TABLE_DOUBLES * sizeof(double); }
+// per warp: the order tables and the model values of one evaluation (4 nk doubles)
+CB_HD int fit_eval_warp_doubles(int nk) { return (CB_FIT_TABLE_DOUBLES + 4 * nk + 1) & ~1; }
+CB_HD size_t fit_eval_smem_bytes(int warps, int nk) { return (size_t)warps * fit_eval_warp_doubles(nk) * sizeof(double); }
 static_assert(CB_FIT_TABLE_DOUBLES % 2 == 0 && CB_FIT_CT_DOUBLES % 2 == 0, "double2 tables must stay 16-byte aligned");
 
 // Solve B d = -g on the free variables (frozen ones get d = 0) by Cholesky; returns false when the
@@ -419,7 +421,7 @@ CB_NOINLINE_BODY void fit_update(FitState *S, double ftol, int max_iter) {
     else if (S->it >= max_iter) { S->status = FIT_MAXITER; S->action = FIT_DONE; }
 }
 
-// Objective, gradient and Gauss-Newton matrix at S->xt from the 15 sums of fit_eval_window (model_eval.cuh).
+// Objective, gradient and Gauss-Newton matrix at S->xt from the 15 sums of fit_sums_from_values (model_eval.cuh).
 CB_NOINLINE_BODY void fit_take_sums(FitState *S, const double *sums) {
     S->fn = 0.5 * sums[0];
     bool ok = isfinite(S->fn);
@@ -637,7 +639,8 @@ CB_BODY void fit_eval_body(const Ctx &cx, const FitParams &P) {
         P.count[3 + (P.round + 2) % 3] = 0u;
     }
     if ((int64_t)n < (int64_t)P.handover) return;       // left to the finish kernel (the step kernel passes the list on)
-    double *tab = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * CB_FIT_TABLE_DOUBLES;
+    double *tab = reinterpret_cast<double *>(cx.smem()) + (int64_t)warp * fit_eval_warp_doubles(P.nk);
+    double *vals = tab + CB_FIT_TABLE_DOUBLES;
     const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
     const int sorted = meta[0] != 0.0 ? 1 : 0;
     for (int j = lane; j < CB_TEMME_TAB; j += L) tab[CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + j] = P.ktab[3 * P.nk + j];
@@ -652,7 +655,10 @@ CB_BODY void fit_eval_body(const Ctx &cx, const FitParams &P) {
         const double *cg = P.coef + w * (3 * FC_COUNT);
         for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = cg[j];
         cx.sync_warp();
-        fit_eval_window<false>(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, P.sums + w * 16);
+        fit_eval_values(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, vals);
+        cx.sync_warp();
+        fit_sums_from_values(cx, vals, P.kh, P.nk, tab[CB_FIT_COEF_OFFSET + 2 * FC_COUNT + FC_AUX] == 3.0,
+                             tab[CB_FIT_COEF_OFFSET + FC_AUX], lane, P.phi + w * P.nk, P.sums + w * 16);
     }
 }
 
@@ -670,7 +676,7 @@ CB_BODY void fit_first_body(const Ctx &cx, const FitParams &P) {
         for (int j = lane; j < CB_TEMME_TAB; j += L) tab[CB_FIT_CT_DOUBLES + CB_FIT_RPQ_DOUBLES + j] = P.ktab[3 * nk + j];
         for (int j = lane; j < 3 * FC_COUNT; j += L) tab[CB_FIT_COEF_OFFSET + j] = P.coef[j];      // window 0's = everybody's
         cx.sync_warp();
-        fit_eval_window<true>(cx, tab, P.kh, P.ktab, nk, sorted, lane, nullptr, nullptr, vals);
+        fit_eval_values(cx, tab, P.kh, P.ktab, nk, sorted, lane, vals);
     }
     cx.sync_block();
     const double hb = tab[CB_FIT_COEF_OFFSET + FC_AUX];
@@ -712,12 +718,12 @@ CB_BODY void fit_step_body(const Ctx &cx, const FitParams &P) {
 }
 
 // finish: the windows still unfinished after the batched rounds, run to the end -- one CTA per window: its warps
-// share the chunks of every evaluation (fit_eval_window's part / nparts), warp 0 sums the partial sums, takes the
+// share the chunks of every evaluation (fit_eval_values part / nparts), warp 0 forms the sums, takes the
 // solver step on lane 0 and fills the coefficients of the next evaluation on lanes 0..nv-1.  With few windows left
 // a round is latency bound (one warp needs ~50 us for an evaluation and ~20 us for the scalar step).
-// Shared memory (doubles): tables, state, sums[16], partial sums [warps][16].
-CB_HD size_t fit_finish_smem_bytes(int warps) {
-    return (size_t)(((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 1) & ~1) + 16 + 16 * warps) * sizeof(double);
+// Shared memory (doubles): tables, state, sums[16], model values [4 nk].
+CB_HD size_t fit_finish_smem_bytes(int nk) {
+    return (size_t)(((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 1) & ~1) + 16 + 4 * nk) * sizeof(double);
 }
 template <class Ctx>
 CB_BODY void fit_finish_body(const Ctx &cx, const FitParams &P) {
@@ -729,7 +735,7 @@ CB_BODY void fit_finish_body(const Ctx &cx, const FitParams &P) {
     fit_solver_constants(P, max_iter, gtol, ftol);
     double *tab = reinterpret_cast<double *>(cx.smem());
     double *sd = tab + CB_FIT_TABLE_DOUBLES;
-    double *sums = tab + ((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 1) & ~1), *wsums = sums + 16;
+    double *sums = tab + ((CB_FIT_TABLE_DOUBLES + CB_FIT_STATE_DOUBLES + 1) & ~1), *vals = sums + 16;
     FitState *S = reinterpret_cast<FitState *>(sd);
     const double *meta = P.ktab + 3 * P.nk + (CB_MILLER_NMAX + 1);
     const int sorted = meta[0] != 0.0 ? 1 : 0;
@@ -747,16 +753,11 @@ CB_BODY void fit_finish_body(const Ctx &cx, const FitParams &P) {
         }
         cx.sync_block();
         for (;;) {
-            fit_eval_window<false>(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, P.phi + w * P.nk, wsums + 16 * warp, nullptr,
-                                   warp, nwarps);
+            fit_eval_values(cx, tab, P.kh, P.ktab, P.nk, sorted, lane, vals, warp, nwarps);
             cx.sync_block();
             if (warp == 0) {
-                for (int q = lane; q < 15; q += L) {
-                    double t = 0.0;
-                    for (int ww = 0; ww < nwarps; ++ww) t += wsums[16 * ww + q];
-                    sums[q] = t;
-                }
-                cx.sync_warp();
+                fit_sums_from_values(cx, vals, P.kh, P.nk, tab[CB_FIT_COEF_OFFSET + 2 * FC_COUNT + FC_AUX] == 3.0,
+                                     tab[CB_FIT_COEF_OFFSET + FC_AUX], lane, P.phi + w * P.nk, sums);
                 if (lane == 0 && fit_step_window(S, sums, gtol, ftol, max_iter, nullptr)) fit_write_result(P, S, w);
                 cx.sync_warp();
                 if (S->action == FIT_GO) {

@@ -295,23 +295,28 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     int rc = cb_check_device();
     if (rc) return rc;
     CB_REQUIRE(nk > 0 && nk <= 512, "nk must be in [1, 512]");
-    static int env_rounds = -1, env_handover = 0, sm_count = 0;
-    if (env_rounds < 0) {
-        const char *e = getenv("CB_FIT_HANDOVER");        // unfinished windows below which the finish kernel takes over
-        env_handover = e ? atoi(e) : 2048;
-        e = getenv("CB_FIT_ROUNDS");                      // batched rounds at most (tuning)
-        env_rounds = e ? atoi(e) : 20;
-        int dev = 0;
-        CB_CUDA_TRY(cudaGetDevice(&dev));
-        CB_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    // tuning / test knobs, read per call: CB_FIT_HANDOVER = unfinished windows below which the finish kernel takes
+    // over (0: never before the last round), CB_FIT_ROUNDS = batched rounds at most, CB_FIT_PASS = windows per pass
+    // of the scratch; every setting gives the same results (tests/test_gpu_parity.py::test_fit_paths_agree)
+    int env_handover = 2048, env_rounds = 20;
+    int64_t env_pass = CB_FIT_PASS_WINDOWS;
+    if (const char *e = getenv("CB_FIT_HANDOVER")) env_handover = atoi(e);
+    if (const char *e = getenv("CB_FIT_ROUNDS")) env_rounds = atoi(e);
+    if (const char *e = getenv("CB_FIT_PASS")) env_pass = atoll(e);
+    if (env_rounds < 1) env_rounds = 1;
+    if (env_pass < 1 || env_pass > CB_FIT_PASS_WINDOWS) env_pass = CB_FIT_PASS_WINDOWS;
+    int dev_id = 0, sm_count = 0;
+    CB_CUDA_TRY(cudaGetDevice(&dev_id));
+    CB_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_id));
     cudaStream_t st = (cudaStream_t)stream;
     double *ktab = nullptr;
     if ((rc = ktable_make(kh_dev, nk, st, &ktab)) != CB_OK) return rc;
-    CB_CUDA_TRY(cudaFuncSetAttribute(fit_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_eval_smem_bytes(CB_FIT_EVAL_WARPS)));
+    CB_CUDA_TRY(cudaFuncSetAttribute(fit_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_eval_smem_bytes(CB_FIT_EVAL_WARPS, nk)));
+    if (fit_finish_smem_bytes(nk) > 48 * 1024)
+        CB_CUDA_TRY(cudaFuncSetAttribute(fit_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_finish_smem_bytes(nk)));
     // library-owned scratch per (device, stream): state, coefficients, sums, two lists, counters; inputs larger
     // than CB_FIT_PASS_WINDOWS go through it in passes
-    const int64_t pass = nwin < CB_FIT_PASS_WINDOWS ? nwin : CB_FIT_PASS_WINDOWS;
+    const int64_t pass = nwin < env_pass ? nwin : env_pass;
     const size_t per_win = (size_t)(CB_FIT_PERSIST_DOUBLES + 3 * FC_COUNT + 16) * sizeof(double) + 2 * sizeof(int32_t);
     const size_t head = 64 + (size_t)((CB_FIT_STATE_DOUBLES + 7) & ~7) * sizeof(double);
     char *scratch = nullptr;
@@ -346,13 +351,13 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
         for (int r = 0; r < env_rounds; ++r) {
             P.round = r;
             if (r == 0 && !P.x0_dev) fit_first_kernel<<<eval_grid, 256, fit_first_smem_bytes(nk), st>>>(P);
-            else fit_eval_kernel<<<eval_grid, CB_FIT_EVAL_WARPS * CB_WARP, fit_eval_smem_bytes(CB_FIT_EVAL_WARPS), st>>>(P);
+            else fit_eval_kernel<<<eval_grid, CB_FIT_EVAL_WARPS * CB_WARP, fit_eval_smem_bytes(CB_FIT_EVAL_WARPS, nk), st>>>(P);
             fit_step_kernel<<<step_grid, 128, 0, st>>>(P);
             int32_t *t = P.list_in; P.list_in = P.list_out; P.list_out = t;
         }
         P.round = env_rounds;
         const int fin_grid = (int)(n < (int64_t)sm_count * 8 ? n : (int64_t)sm_count * 8);
-        fit_finish_kernel<<<fin_grid, CB_FIT_FINISH_WARPS * CB_WARP, fit_finish_smem_bytes(CB_FIT_FINISH_WARPS), st>>>(P);
+        fit_finish_kernel<<<fin_grid, CB_FIT_FINISH_WARPS * CB_WARP, fit_finish_smem_bytes(nk), st>>>(P);
     }
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;

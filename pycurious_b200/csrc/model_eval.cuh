@@ -488,10 +488,10 @@ CB_BODY double model_eval_warp(const Ctx &cx, const WarpSlab &W, int idx, int la
 // full chunk with the longest Miller recurrence plus a quarter-full one).  Here the work items are (point, vector)
 // PAIRS: lane = (point within the chunk) * nv + vector, so the chunks are full, the pairs of one chunk have
 // neighbouring x (the Miller trip count follows the chunk's smallest x) and the number of passes drops from 2 nv to
-// ~nv + 1.  The model values never reach memory: the lanes of a point exchange them by shuffles and the lane of
-// vector 0 accumulates the point's contribution to
+// ~nv + 1.  The model values stay in shared memory (4 nk doubles per window); from them every lane accumulates its
+// points' contributions to
 //     sums[0] = r.r;  sums[1..4] = r.J_a;  sums[5..14] = J_a.J_b (packed upper triangle)
-// with r = Phi - obs and J = (dPhi/dbeta, dPhi/dzt = -2k, dPhi/ddz, dPhi/dC = 1); the lanes are summed by a
+// with r = Phi - obs and J = (dPhi/dbeta, dPhi/dzt = -2k, dPhi/ddz, dPhi/dC = 1), and the lanes are summed by a
 // transposing butterfly (16 double shuffles).  Per-warp tables in shared memory (doubles): CT [3][CB_MILLER_NMAX+1]
 // weights C_n of the normalising sum per vector (a_{n+1} is updated inside the recurrence), RPQ [3][CB_TEMME_TAB]
 // double2, RNJ [CB_TEMME_TAB] 1/j, COEF [3][FC_COUNT].
@@ -570,7 +570,7 @@ CB_BODY void fit_sums_reduce(const Ctx &cx, double *v, int lane, double *sums_ou
     }
 }
 
-// The 15 sums of one window from stored model values (fit_eval_window<true>) and its spectrum.
+// The 15 sums of one window from stored model values (fit_eval_values) and its spectrum.
 template <class Ctx>
 CB_BODY void fit_sums_from_values(const Ctx &cx, const double *store, const double *kh, int nk, bool use_pm, double hb,
                                   int lane, const double *obs, double *sums_out) {
@@ -588,16 +588,17 @@ CB_BODY void fit_sums_from_values(const Ctx &cx, const double *store, const doub
 
 // tab: the warp's tables with COEF filled for nv vectors (FC_AUX: hb, cu, nv); obs: the window's spectrum (global);
 // sums_out[16] receives the sums (any address space; written by 15 lanes after the butterfly).
-// STORE = true: the model values go to store[0..4 nk) (Phi, Phi(beta + hb), Phi(beta - hb), dPhi/ddz, nk apart) instead
-// of into the sums (obs, sums_out unused): the first evaluation of a launch whose windows share the start point
-// is done once per CTA and every window only forms its own sums from it (fit_sums_from_values).
+// The model values go to store[0..4 nk) in shared memory (Phi, Phi(beta + hb), Phi(beta - hb), dPhi/ddz, nk apart),
+// every lane writing the value of its own (point, vector) pair; the 15 sums are then formed from them by
+// fit_sums_from_values -- ONE summation order for every way a window can be evaluated (a warp of the batched
+// evaluation kernel, the four warps of a straggler's CTA, the shared first evaluation), so that a window's result
+// does not depend on how many other windows are unfinished, i.e. on how a survey is split over GPUs.
 // part / nparts: the warps of a CTA that work on ONE window together (the stragglers' finish kernel) take the
 // chunks and the closed-form points round robin, warp `part` of `nparts`; the tables are built by part 0 behind a
-// block barrier and every warp delivers partial sums.
-template <bool STORE, class Ctx>
-CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const double *ktab, int nk, int sorted,
-                             int lane, const double *obs, double *sums_out, double *store = nullptr, int part = 0,
-                             int nparts = 1) {
+// block barrier.  The caller synchronises (warp or block) before the values are read.
+template <class Ctx>
+CB_BODY void fit_eval_values(const Ctx &cx, double *tab, const double *kh, const double *ktab, int nk, int sorted,
+                             int lane, double *store, int part = 0, int nparts = 1) {
     const int L = cx.team_lanes();
     double *CTg = tab;
     double2 *RPQg = reinterpret_cast<double2 *>(tab + CB_FIT_CT_DOUBLES);
@@ -608,10 +609,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
     const double hb = C0[FC_AUX], cu = C0[FC_COUNT + FC_AUX];
     const int nv = (int)C0[2 * FC_COUNT + FC_AUX];
     const bool use_pm = nv == 3;
-    const double rh = 1.0 / hb;
-    double v[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = 0.0;
+    (void)hb;
 
     bool fast = sorted != 0;
     for (int u = 0; u < nv; ++u) fast = fast && C0[u * FC_COUNT + FC_FAST] != 0.0;
@@ -620,8 +618,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
         for (int i = lane + L * part; i < nk; i += L * nparts) {
             double vals[4];
             fit_generic_point(COEF, nv, Ctx::ldg(kh + i), Ctx::ldg(logk + i), vals);
-            if (STORE) { store[i] = vals[0]; store[nk + i] = vals[1]; store[2 * nk + i] = vals[2]; store[3 * nk + i] = vals[3]; }
-            else fit_sums_add(v, vals[0], vals[1], vals[2], use_pm, rh, vals[3], Ctx::ldg(kh + i), Ctx::ldg(obs + i));
+            store[i] = vals[0]; store[nk + i] = vals[1]; store[2 * nk + i] = vals[2]; store[3 * nk + i] = vals[3];
         }
     } else {
         const double dz = C0[FC_DZ], zt = C0[FC_ZT], Cc = C0[FC_C], lhdz = C0[FC_LHDZ], rdz = C0[FC_RDZ];
@@ -654,8 +651,7 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                 const double lin = fma(-2.0 * k, zt, Cc);
                 const double p0 = over ? INFINITY : lin - b0 * lk + g0, pp = over ? INFINITY : lin - b1 * lk + g1;
                 const double pm = over ? INFINITY : lin - b2 * lk + g2;
-                if (STORE) { store[i] = p0; store[nk + i] = pp; store[2 * nk + i] = pm; store[3 * nk + i] = over ? NAN : 0.0; }
-                else fit_sums_add(v, p0, pp, pm, use_pm, rh, over ? NAN : 0.0, k, Ctx::ldg(obs + i));
+                store[i] = p0; store[nk + i] = pp; store[2 * nk + i] = pm; store[3 * nk + i] = over ? NAN : 0.0;
             }
         }
 
@@ -733,7 +729,6 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
             const int i = c0 + il;
             const bool act = il < P && i < c1;
             const bool temme = i < nT;
-            double ph0 = 0.0, phs1 = 0.0, phs2 = 0.0, jd = 0.0;      // this lane's Phi (serial emulation: of all vectors)
 #pragma unroll 1
             for (int u = vl; u < nv; u += VL) {
                 const auto CV = Ctx::shared_view((const double *)(COEF + u * FC_COUNT));
@@ -819,28 +814,14 @@ CB_BODY void fit_eval_window(const Ctx &cx, double *tab, const double *kh, const
                     const double hx = exp(CV[FC_NU] * (lk + lhdz));
                     const double qg = CV[FC_QG];
                     const double br = fma(qg, 1.0 + e2, -b * hx);
-                    const double ph = fma(-2.0 * k, zt, Cc) - CV[FC_BM1] * lk + cb_log_inline(CV[FC_LEAD] * br);
-                    if (u == 0) jd = k * fma(hx, a + b, -2.0 * qg * e2) / br;
-                    if (L == 1) { if (u == 0) ph0 = ph; else if (u == 1) phs1 = ph; else phs2 = ph; }
-                    else ph0 = ph;
+                    store[u * nk + i] = fma(-2.0 * k, zt, Cc) - CV[FC_BM1] * lk + cb_log_inline(CV[FC_LEAD] * br);
+                    if (u == 0) store[3 * nk + i] = k * fma(hx, a + b, -2.0 * qg * e2) / br;
                 }
-            }
-            // the lanes of one point hand their Phi to the lane of vector 0, which accumulates the point
-            double pp = phs1, pm = phs2;
-            if (L != 1) {
-                const int base = lane - vl;
-                pp = cx.shfl(ph0, (base + 1) & (L - 1));
-                pm = cx.shfl(ph0, (base + 2) & (L - 1));
-            }
-            if (act && vl == 0) {
-                if (STORE) { store[i] = ph0; store[nk + i] = pp; store[2 * nk + i] = use_pm ? pm : 0.0; store[3 * nk + i] = jd; }
-                else fit_sums_add(v, ph0, pp, use_pm ? pm : 0.0, use_pm, rh, jd, Ctx::ldg(kh + i), Ctx::ldg(obs + i));
             }
         }
     }
 
-    if (!STORE) fit_sums_reduce(cx, v, lane, sums_out);
-    cx.sync_warp();
+    (void)use_pm;
 }
 
 // 0.5 sum (p0 - obs)^2 over the slab (every lane returns the total).

@@ -259,7 +259,7 @@ static int emu_fit_run(FitParams &P, int mode, int rounds) {
     P.count = count; P.stride = n; P.tmpl = tmpl.data();
     fit_template_body(P);
     for (int64_t w = 0; w < n; ++w) fit_begin_window(P, w);
-    std::vector<double> sm(fit_finish_smem_bytes(2) / sizeof(double) + 8);
+    std::vector<double> sm((fit_finish_smem_bytes(P.nk) + fit_eval_smem_bytes(1, P.nk)) / sizeof(double) + 8);
     for (int r = 0; r < rounds; ++r) {
         P.round = r;
         if (r == 0 && !P.x0_dev) {          // common start point: model values once per CTA, sums per window
@@ -274,7 +274,7 @@ static int emu_fit_run(FitParams &P, int mode, int rounds) {
             SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
             fit_eval_body(cx, P);
         } else {
-            emu_launch(2, 64, fit_eval_smem_bytes(2), [&](const HostCtx &cx) { fit_eval_body(cx, P); });
+            emu_launch(2, 64, fit_eval_smem_bytes(2, P.nk), [&](const HostCtx &cx) { fit_eval_body(cx, P); });
         }
         SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
         const unsigned cnt = count[r % 3];
@@ -286,7 +286,7 @@ static int emu_fit_run(FitParams &P, int mode, int rounds) {
         SerialCtx cx{0, 1, 0, 1, reinterpret_cast<char *>(sm.data())};
         fit_finish_body(cx, P);
     } else {
-        emu_launch(2, 64, fit_finish_smem_bytes(2), [&](const HostCtx &cx) { fit_finish_body(cx, P); });
+        emu_launch(2, 64, fit_finish_smem_bytes(P.nk), [&](const HostCtx &cx) { fit_finish_body(cx, P); });
     }
     return 0;
 }

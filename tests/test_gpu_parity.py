@@ -391,6 +391,41 @@ def test_fit_custom_process_subgrid_and_single(grid, oracle, mag):
     np.testing.assert_allclose(x_dev, xp, rtol=2e-5)
 
 
+def test_fit_paths_agree(grid, monkeypatch):
+    """The batched fit (csrc/fit_body.cuh) reaches a window's result by different launches depending on how many
+    windows are unfinished: batched evaluation / step rounds, the CTA-per-window finish kernel after the hand-over,
+    several passes over the scratch for large inputs, the shared first evaluation for a common start point or one
+    evaluation per window for per-window start points.  Every route must give the same bits."""
+    import torch
+    g = load_golden("fit.npz")
+    k, phi = g["w200_k"], np.ascontiguousarray(np.tile(g["w200_phi"], (40, 1)))          # 1,440 spectra
+    phi *= 1.0 + 1e-3 * np.random.default_rng(5).standard_normal(phi.shape)
+    phi_t = torch.from_numpy(phi).cuda()
+    x0 = (3.0, 1.0, 10.0, 5.0)
+
+    def run(**env):
+        for name in ("CB_FIT_HANDOVER", "CB_FIT_ROUNDS", "CB_FIT_PASS"):
+            monkeypatch.delenv(name, raising=False)
+        for name, v in env.items():
+            monkeypatch.setenv(name, str(v))
+        x, d = grid._fit_device(k, phi_t, x0, diagnostics=True)
+        return x.cpu().numpy(), {kk: v.cpu().numpy() for kk, v in d.items()}
+
+    base, dbase = run()                                       # 1,440 < 2,048: everything in the finish kernel
+    assert np.all(np.isfinite(base)) and np.all(dbase["status"] <= 1)
+    for env in (dict(CB_FIT_HANDOVER=0), dict(CB_FIT_HANDOVER=0, CB_FIT_ROUNDS=3), dict(CB_FIT_HANDOVER=200),
+                dict(CB_FIT_HANDOVER=0, CB_FIT_PASS=500), dict(CB_FIT_PASS=97, CB_FIT_HANDOVER=50)):
+        x, d = run(**env)
+        assert np.array_equal(x, base), env
+        assert np.array_equal(d["nfev"], dbase["nfev"]) and np.array_equal(d["f"], dbase["f"]), env
+    # per-window start points (no shared first evaluation): the same start for all must reproduce the common-start run
+    monkeypatch.delenv("CB_FIT_PASS", raising=False)
+    monkeypatch.setenv("CB_FIT_HANDOVER", "0")
+    x0_dev = torch.tensor(x0, dtype=torch.float64, device="cuda").repeat(phi.shape[0], 1).contiguous()
+    x, _ = grid._fit_device(k, phi_t, x0, x0_dev=x0_dev, diagnostics=True)
+    assert np.array_equal(x.cpu().numpy(), base)
+
+
 def test_fft_domain_filters_match_reference(grid, oracle, mag):
     """CurieGrid.upward_continuation / reduce_to_pole (grid.py:405-546): FFTs on the device, golden outputs of
     the reference itself; also as a `process_subgrid` callback of optimise (optimise.py:282-294)."""
