@@ -768,8 +768,8 @@ CB_BODY void fit_eval_values(const Ctx &cx, double *tab, const double *kh, const
                     int N = (int)(12.0 + 140.0 * (Ctx::ldg(rk + (c0 > nT ? c0 : nT)) * rdz)) + 1;
                     if (N > CB_MILLER_NMAX - 1) N = CB_MILLER_NMAX - 1;
                     // one 8-byte shared load per step (the weight C_n); a_{n+1} = -(a1 + n(n+1)) and b_n = 2(n + x) are
-                    // updated in registers: tabulating a_{n+1} beside C_n saves two additions per step but costs 2.3 KB
-                    // per warp and, at 80 registers, spills (measured 11-16 % slower)
+                    // updated in registers: tabulating a_{n+1} beside C_n (one 16-byte load, two additions less per step)
+                    // was measured 11-13 % slower with and without spills -- the loop is bound by shared-memory loads
                     const auto CT = Ctx::shared_view((const double *)(CTg + u * (CB_MILLER_NMAX + 1)));
                     double yp = 0.0, y = 1.0, S = CT[N];
                     double tn = 2.0 * (double)N;                              // 2n
