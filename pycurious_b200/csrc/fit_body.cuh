@@ -686,8 +686,9 @@ CB_BODY void fit_first_body(const Ctx &cx, const FitParams &P) {
         fit_sums_from_values(cx, vals, P.kh, nk, use_pm, hb, lane, P.phi + w * nk, P.sums + w * 16);
 }
 
-// step: one thread per unfinished window, on a private copy of its state.  (Four lanes per window with the three
-// coefficient sets side by side was measured slower: 3.4 vs 2.3 ms over the rounds of config 3.)
+// step: one thread per unfinished window, on a private copy of its state.  (Measured slower: four lanes per window
+// with the three coefficient sets side by side, 3.4 vs 2.3 ms over the rounds of config 3; the private copy in
+// shared memory at an odd stride instead of local memory, 2.8 vs 2.3 ms.)
 template <class Ctx>
 CB_BODY void fit_step_entry(const Ctx &cx, const FitParams &P, int64_t e) {
     int max_iter;
