@@ -59,6 +59,9 @@ int cb_fp64_fma_peak(double *tflops_out);
  * pinned-memory limit) is reported and the caller falls back to a pageable copy. */
 int cb_host_register(void *host, int64_t bytes);
 int cb_host_unregister(void *host);
+/* Frees the scratch the library owns per (device, stream): the window-independent k tables of the model kernels
+ * and the solver state of cb_fit_batch.  The caller guarantees that no launch of this library is in flight. */
+int cb_release_scratch(void);
 
 /* ------------------------------------------------------------------------
  * Spectrum stage:  CurieGrid.subgrid -> [remove_trend_linear] -> radial_spectrum
@@ -174,8 +177,15 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
 
 /* ------------------------------------------------------------------------
  * MAP fit:  CurieOptimise.optimise / optimise_routine (optimise.py:232-301, :446-509)
- * One window per warp; bounded quasi-Newton (projected BFGS seeded with the
- * Gauss-Newton metric) on min_func.
+ * Bounded quasi-Newton (projected BFGS seeded with the Gauss-Newton metric) on
+ * min_func, in place of scipy's L-BFGS-B.  One call issues a sequence of
+ * asynchronous launches on `stream` (model evaluation: one window per warp;
+ * solver step: one window per thread; a straggler kernel) and returns without
+ * synchronising.  The solver state between the launches lives in scratch the
+ * library owns per (device, stream) -- about 1.5 KB per window, at most 262,144
+ * windows at a time (larger inputs go through it in passes); cb_release_scratch
+ * frees it.  A window's result does not depend on the batch it arrives in.
+ * nk <= 512.
  * ---------------------------------------------------------------------- */
 #define CB_FIT_FLAG_LINEAR_DZ 1   /* iterate in dz itself instead of u = exp(-2 k_min dz) */
 #define CB_FIT_FLAG_FORWARD_FIRST 2 /* dPhi/dbeta by forward differences far from the minimum, central near it (default: central throughout) */

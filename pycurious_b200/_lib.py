@@ -53,6 +53,7 @@ SIGNATURES = {
     "cb_fp64_fma_peak": (_I, [C.POINTER(_D)]),
     "cb_host_register": (_I, [_VP, _I64]),
     "cb_host_unregister": (_I, [_VP]),
+    "cb_release_scratch": (_I, []),
     "cb_spectrum_plan_create": (_I, [_I, _I, _VP, _VP, _VP, _VP, C.POINTER(_VP)]),
     "cb_spectrum_plan_destroy": (_I, [_VP]),
     "cb_spectrum_plan_get_info": (_I, [_VP, C.POINTER(SpectrumPlanInfo)]),

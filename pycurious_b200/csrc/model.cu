@@ -209,6 +209,24 @@ static int elementwise_grid(int64_t n) {
 
 extern "C" {
 
+int cb_release_scratch(void) {
+    std::lock_guard<std::mutex> lock(g_ktab_mutex);
+    int dev = 0;
+    CB_CUDA_TRY(cudaGetDevice(&dev));
+    for (auto &kv : g_ktab) {
+        CB_CUDA_TRY(cudaSetDevice(kv.first.first));
+        cudaFree(kv.second);
+    }
+    g_ktab.clear();
+    for (auto &kv : g_fit_scratch) {
+        CB_CUDA_TRY(cudaSetDevice(kv.first.first));
+        cudaFree(kv.second.first);
+    }
+    g_fit_scratch.clear();
+    CB_CUDA_TRY(cudaSetDevice(dev));
+    return CB_OK;
+}
+
 int cb_besselk(const double *nu_dev, const double *x_dev, int64_t n, double *out_dev, void *stream) {
     CB_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return CB_OK;
