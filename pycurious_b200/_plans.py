@@ -86,6 +86,8 @@ def share_rows_for_list(g, window, xc, yc, sample=4096):
     into blocks -- over ranks, devices or scratch slices.  SpectrumPlan.run decides per call from the row reuse
     of the windows it is given, and the two paths agree to ~1e-14 but not bit for bit; a split list must therefore
     take ONE decision, from the same data on every rank: the row reuse of its first `sample` windows."""
+    if os.environ.get("CB_SPEC_SHARE_ROWS", "auto") != "auto":
+        return None                        # forced for every call by the environment (SpectrumPlan.run reads it)
     xc, yc = np.asarray(xc, dtype=np.float64), np.asarray(yc, dtype=np.float64)
     m = int(min(xc.size, sample))
     if m <= 1:
@@ -98,6 +100,8 @@ def share_rows_for_list(g, window, xc, yc, sample=4096):
 
 def share_rows_for_lattice(g, window, xs, ys):
     """share_rows_for_list for the lattice xs x ys (x fastest)."""
+    if os.environ.get("CB_SPEC_SHARE_ROWS", "auto") != "auto":
+        return None
     if len(xs) * len(ys) <= 1:
         return False
     half = window_nodes(window, g.dx)[1]

@@ -24,6 +24,11 @@ __global__ void __launch_bounds__(512, 1) line_fft_kernel(const __grid_constant_
     line_fft_body(cx, P);
 }
 
+__global__ void __launch_bounds__(256) op_half_kernel(const double2 *op, int n, double2 *op_half) {
+    DevCtx cx{nullptr};
+    op_half_body(cx, op, n, op_half);
+}
+
 template <class T>
 static int upload_vec(T **dst, const std::vector<T> &src) {
     *dst = nullptr;
@@ -145,7 +150,8 @@ int cb_fft2_filter(const cb_fft_plan *plan_x, const cb_fft_plan *plan_y, const d
 
 int64_t cb_fft2_filter_windows_workspace_bytes(int n, int64_t nwin) {
     if (n <= 0 || nwin <= 0) return 0;
-    return 2 * nwin * (int64_t)n * n * 16 + 512;
+    const int64_t half = n / 2 + 1;
+    return (2 * nwin + 1) * (int64_t)n * half * 16 + 512;        // A, B [nwin][n][half] + the operator's Hermitian half
 }
 
 int cb_fft2_filter_windows(const cb_fft_plan *plan, const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
@@ -161,31 +167,23 @@ int cb_fft2_filter_windows(const cb_fft_plan *plan, const double *grid_dev, int6
     CB_REQUIRE(workspace_bytes >= cb_fft2_filter_windows_workspace_bytes((int)n, nwin),
                "workspace too small (see cb_fft2_filter_windows_workspace_bytes)");
     cudaStream_t st = (cudaStream_t)stream;
-    double2 *A = reinterpret_cast<double2 *>(((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255);
-    double2 *B = A + nwin * n * n;
-    int rc;
-    LineFftParams P;
-    // 1. rows forward, gathered from the grid: window i -> A[i]
-    memset(&P, 0, sizeof(P));
-    P.in_real = grid_dev; P.in_es = 1; P.in_ls = ld; P.in_ld = ld; P.iy0 = iy0_dev; P.ix0 = ix0_dev;
-    P.out_cplx = A; P.out_es = 1; P.out_ls = n; P.out_bs = n * n; P.lines_per_img = n; P.nlines = nwin * n; P.scale = 1.0;
-    if ((rc = launch_lines(plan, P, st))) return rc;
-    // 2. columns forward, times the filter: A -> B
-    memset(&P, 0, sizeof(P));
-    P.in_cplx = A; P.in_es = n; P.in_ls = 1; P.in_bs = n * n; P.out_cplx = B; P.out_es = n; P.out_ls = 1; P.out_bs = n * n;
-    P.lines_per_img = n; P.nlines = nwin * n; P.scale = 1.0;
-    P.mul = reinterpret_cast<const double2 *>(filter_dev);
-    if ((rc = launch_lines(plan, P, st))) return rc;
-    // 3. columns inverse: B -> A
-    memset(&P, 0, sizeof(P));
-    P.in_cplx = B; P.in_es = n; P.in_ls = 1; P.in_bs = n * n; P.out_cplx = A; P.out_es = n; P.out_ls = 1; P.out_bs = n * n;
-    P.lines_per_img = n; P.nlines = nwin * n; P.inverse = 1; P.scale = 1.0 / (double)n;
-    if ((rc = launch_lines(plan, P, st))) return rc;
-    // 4. rows inverse, real part: A -> out stack
-    memset(&P, 0, sizeof(P));
-    P.in_cplx = A; P.in_es = 1; P.in_ls = n; P.in_bs = n * n; P.out_real = out_dev; P.out_es = 1; P.out_ls = n; P.out_bs = n * n;
-    P.lines_per_img = n; P.nlines = nwin * n; P.inverse = 1; P.scale = 1.0 / (double)n;
-    return launch_lines(plan, P, st);
+    // Real windows have Hermitian spectra and real(ifft2(op * .)) acts through the Hermitian part of op: row PAIRS
+    // in one complex transform on the way in and out, the column passes over the half plane v <= n/2 only -- 4 x
+    // ceil(n/2) line transforms per window instead of 4 n.  Layout: op_half [n][half], A, B [nwin][n][half].
+    const int64_t half = n / 2 + 1;
+    double2 *op_half = reinterpret_cast<double2 *>(((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255);
+    double2 *A = op_half + n * half;
+    double2 *B = A + nwin * n * half;
+    op_half_kernel<<<(int)std::min<int64_t>((n * half + 255) / 256, 1024), 256, 0, st>>>(
+        reinterpret_cast<const double2 *>(filter_dev), (int)n, op_half);
+    CB_CUDA_TRY(cudaGetLastError());
+    for (int pass = 0; pass < 4; ++pass) {
+        LineFftParams P;
+        fft2_windows_pass(pass, (int)n, nwin, grid_dev, ld, iy0_dev, ix0_dev, A, B, op_half, out_dev, P);
+        const int rc = launch_lines(plan, P, st);
+        if (rc) return rc;
+    }
+    return CB_OK;
 }
 
 }  // extern "C"

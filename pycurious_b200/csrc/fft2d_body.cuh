@@ -17,6 +17,7 @@
 #pragma once
 #include "exec_ctx.cuh"
 #include "fft_engine.cuh"
+#include <string.h>
 
 struct LineFftParams {
     const double *in_real;     // real input (first pass) or NULL
@@ -32,6 +33,14 @@ struct LineFftParams {
     const int32_t *iy0, *ix0;  // first pass of a window batch: image i starts at in_real + iy0[i]*in_ld + ix0[i]
     int64_t in_ld;
     int32_t n;                 // line length
+    // Real data have Hermitian spectra, and a filter applied as real(ifft2(op * fft2(x))) acts through its
+    // Hermitian part only; the window batch uses both (cb_fft2_filter_windows):
+    //   pair = 1  forward pass over PAIRS of real lines (lines 2p, 2p+1 of an image in one complex transform,
+    //             untangled); only elements k < half of each spectrum are written
+    //   pair = 2  inverse pass from two Hermitian half lines (elements k < half given, the rest by conjugate
+    //             symmetry) to two real lines
+    //   pair = 0  plain complex lines (the column passes then run over the half columns only)
+    int32_t pair, half;
     int32_t inverse;           // 1: conj in, conj out, scale
     double scale;
     int32_t bluestein;
@@ -51,12 +60,24 @@ CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
         cx.sync_warp();
         int64_t img = 0, l = line;
         if (P.lines_per_img) { img = line / P.lines_per_img; l = line - img * P.lines_per_img; }
-        int64_t in0 = img * P.in_bs + l * P.in_ls;
+        const int64_t l0 = P.pair ? 2 * l : l;                       // first (or only) line of this transform
+        const bool has1 = P.pair && l0 + 1 < P.n;                     // (pair modes: square images, n lines of n elements)
+        int64_t in0 = img * P.in_bs + l0 * P.in_ls;
         if (P.iy0) in0 += (int64_t)Ctx::ldg(P.iy0 + img) * P.in_ld + Ctx::ldg(P.ix0 + img);
         for (int x = lane; x < M; x += CB_WARP) {
             double2 z = cplx(0.0, 0.0);
             if (x < n) {
-                if (P.in_real) z = cplx(P.in_real[in0 + (int64_t)x * P.in_es], 0.0);
+                if (P.pair == 1) {
+                    z = cplx(P.in_real[in0 + (int64_t)x * P.in_es], has1 ? P.in_real[in0 + P.in_ls + (int64_t)x * P.in_es] : 0.0);
+                } else if (P.pair == 2) {
+                    // Z[x] = A0[x] + i A1[x], the half lines extended by A[n - x] = conj A[x]
+                    const bool up = x >= P.half;
+                    const int64_t xi = up ? n - x : x;
+                    double2 a = P.in_cplx[in0 + xi * P.in_es];
+                    double2 b = has1 ? P.in_cplx[in0 + P.in_ls + xi * P.in_es] : cplx(0.0, 0.0);
+                    if (up) { a = cconj(a); b = cconj(b); }
+                    z = cplx(a.x - b.y, a.y + b.x);
+                } else if (P.in_real) z = cplx(P.in_real[in0 + (int64_t)x * P.in_es], 0.0);
                 else z = P.in_cplx[in0 + (int64_t)x * P.in_es];
                 if (P.inverse) z = cconj(z);
                 if (P.bluestein) z = cmul(z, Ctx::ldg(P.chirp + x));
@@ -65,15 +86,68 @@ CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
         }
         if (P.bluestein) GenericFft::convolve(cx, buf, P.tw, P.filt, P.fft, lane);
         else GenericFft::forward(cx, buf, P.tw, P.fft, lane);
+        auto X = [&](int k) -> double2 {
+            return P.bluestein ? cmul(Ctx::ldg(P.chirp + k), cconj(buf[CB_PAD(k)])) : buf[CB_PAD(Ctx::ldg(P.slot + k))];
+        };
+        if (P.pair == 1) {
+            // untangle: line l0 has A[k] = (Z[k] + conj Z[-k]) / 2, line l0 + 1 has B[k] = (Z[k] - conj Z[-k]) / (2i)
+            for (int k = lane; k < P.half; k += CB_WARP) {
+                const double2 zv = X(k), zm = X(k ? n - k : 0);
+                const int64_t o = img * P.out_bs + l0 * P.out_ls + (int64_t)k * P.out_es;
+                P.out_cplx[o] = cplx(0.5 * (zv.x + zm.x), 0.5 * (zv.y - zm.y));
+                if (has1) P.out_cplx[o + P.out_ls] = cplx(0.5 * (zv.y + zm.y), -0.5 * (zv.x - zm.x));
+            }
+            continue;
+        }
         for (int k = lane; k < n; k += CB_WARP) {
-            double2 z = P.bluestein ? cmul(Ctx::ldg(P.chirp + k), cconj(buf[CB_PAD(k)]))
-                                    : buf[CB_PAD(Ctx::ldg(P.slot + k))];
+            double2 z = X(k);
             if (P.inverse) z = cscale(cconj(z), P.scale);
-            const int64_t oi = l * P.out_ls + (int64_t)k * P.out_es;     // offset within the image
+            const int64_t oi = l0 * P.out_ls + (int64_t)k * P.out_es;     // offset within the image
             const int64_t o = img * P.out_bs + oi;
             if (P.mul) z = cmul(z, Ctx::ldg(P.mul + oi));
-            if (P.out_real) P.out_real[o] = z.x;
+            if (P.pair == 2) {
+                P.out_real[o] = z.x;
+                if (has1) P.out_real[o + P.out_ls] = z.y;
+            } else if (P.out_real) P.out_real[o] = z.x;
             else P.out_cplx[o] = z;
         }
     }
+}
+
+// The four passes of the window batch (cb_fft2_filter_windows and its emulation): windows gathered from the grid
+// -> A[img][y][v] (v < half) -> B[img][u][v] = op_sym * column transform -> A (column inverse) -> real stack.
+// op_half = the Hermitian part of the operator on the half plane, [n][half].
+static inline void fft2_windows_pass(int pass, int n, int64_t nwin, const double *grid, int64_t ld, const int32_t *iy0,
+                                     const int32_t *ix0, double2 *A, double2 *B, const double2 *op_half, double *out,
+                                     LineFftParams &P) {
+    const int64_t half = n / 2 + 1, npairs = (n + 1) / 2, img = (int64_t)n * half;
+    memset(&P, 0, sizeof(P));
+    P.n = n; P.half = (int32_t)half; P.scale = 1.0;
+    if (pass == 0) {            // row pairs forward, gathered from the grid
+        P.pair = 1; P.in_real = grid; P.in_es = 1; P.in_ls = ld; P.in_ld = ld; P.iy0 = iy0; P.ix0 = ix0;
+        P.out_cplx = A; P.out_es = 1; P.out_ls = half; P.out_bs = img; P.lines_per_img = npairs; P.nlines = nwin * npairs;
+    } else if (pass == 1) {     // half columns forward, times the operator
+        P.in_cplx = A; P.in_es = half; P.in_ls = 1; P.in_bs = img; P.out_cplx = B; P.out_es = half; P.out_ls = 1; P.out_bs = img;
+        P.lines_per_img = half; P.nlines = nwin * half; P.mul = op_half;
+    } else if (pass == 2) {     // half columns inverse
+        P.in_cplx = B; P.in_es = half; P.in_ls = 1; P.in_bs = img; P.out_cplx = A; P.out_es = half; P.out_ls = 1; P.out_bs = img;
+        P.lines_per_img = half; P.nlines = nwin * half; P.inverse = 1; P.scale = 1.0 / (double)n;
+    } else {                    // row pairs inverse -> two real rows each
+        P.pair = 2; P.in_cplx = A; P.in_es = 1; P.in_ls = half; P.in_bs = img; P.out_real = out; P.out_es = 1; P.out_ls = n;
+        P.out_bs = (int64_t)n * n; P.lines_per_img = npairs; P.nlines = nwin * npairs; P.inverse = 1; P.scale = 1.0 / (double)n;
+    }
+}
+
+// Hermitian part of an [n][n] operator on the half plane: op_half[u][v] = (op[u][v] + conj op[-u][-v]) / 2, v < half.
+CB_HD double2 op_half_entry(const double2 *op, int n, int64_t i) {
+    const int half = n / 2 + 1;
+    const int u = (int)(i / half), v = (int)(i - (int64_t)u * half);
+    const double2 a = op[(int64_t)u * n + v], b = op[(int64_t)((n - u) % n) * n + (n - v) % n];
+    return cplx(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+}
+template <class Ctx>
+CB_BODY void op_half_body(const Ctx &cx, const double2 *op, int n, double2 *op_half) {
+    const int64_t total = (int64_t)n * (n / 2 + 1);
+    for (int64_t i = (int64_t)cx.bid() * cx.nthreads() + cx.tid(); i < total; i += (int64_t)cx.nblocks() * cx.nthreads())
+        op_half[i] = op_half_entry(op, n, i);
 }

@@ -267,7 +267,7 @@ class CurieOptimise(CurieGrid):
         nwin = int(iy0.numel())
         phi = torch.empty((nwin, plan.nbins), dtype=torch.float64, device="cuda")
         sig = torch.empty_like(phi)
-        step = max(1, int(self.FILTER_CHUNK_BYTES // (n * n * 40)))      # 2 complex scratch planes + the real stack
+        step = max(1, int(self.FILTER_CHUNK_BYTES // (n * n * 26)))      # 2 complex half planes + the real stack
         for a in range(0, nwin, step):
             b = min(a + step, nwin)
             stack = self._filter_windows_device(filt, g, iy0[a:b].contiguous(), ix0[a:b].contiguous(), n)

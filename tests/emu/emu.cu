@@ -365,30 +365,16 @@ int emu_fft2_filter_windows(const double *grid, int64_t ny, int64_t nx, const in
     }
     const int line_slots = (fft_line_slots(fft.n) + 1) & ~1;
     if (bl) filt.resize(line_slots, cplx(0.0, 0.0));
-    const int64_t nn = (int64_t)n * n;
-    std::vector<double2> A(nwin * nn), B(nwin * nn);
-    auto run = [&](LineFftParams P) {
-        P.n = n; P.bluestein = bl; P.fft = fft; P.tw = tw.data(); P.chirp = chirp.data(); P.filt = filt.data();
-        P.slot = slot.data(); P.line_slots = line_slots; P.lines_per_img = n; P.nlines = nwin * n;
+    const int64_t half = n / 2 + 1;
+    std::vector<double2> A(nwin * n * half), B(nwin * n * half), oph(n * half);
+    for (int64_t i = 0; i < (int64_t)oph.size(); ++i) oph[i] = op_half_entry(reinterpret_cast<const double2 *>(filter_re_im), n, i);
+    for (int pass = 0; pass < 4; ++pass) {
+        LineFftParams P;
+        fft2_windows_pass(pass, n, nwin, grid, nx, iy0, ix0, A.data(), B.data(), oph.data(), out, P);
+        P.bluestein = bl; P.fft = fft; P.tw = tw.data(); P.chirp = chirp.data(); P.filt = filt.data();
+        P.slot = slot.data(); P.line_slots = line_slots;
         emu_launch(3, 64, (size_t)2 * line_slots * 16, [&](const HostCtx &cx) { line_fft_body(cx, P); });
-    };
-    LineFftParams P;
-    memset(&P, 0, sizeof(P));
-    P.in_real = grid; P.in_es = 1; P.in_ls = nx; P.in_ld = nx; P.iy0 = iy0; P.ix0 = ix0;
-    P.out_cplx = A.data(); P.out_es = 1; P.out_ls = n; P.out_bs = nn; P.scale = 1.0;
-    run(P);
-    memset(&P, 0, sizeof(P));
-    P.in_cplx = A.data(); P.in_es = n; P.in_ls = 1; P.in_bs = nn; P.out_cplx = B.data(); P.out_es = n; P.out_ls = 1; P.out_bs = nn;
-    P.scale = 1.0; P.mul = reinterpret_cast<const double2 *>(filter_re_im);
-    run(P);
-    memset(&P, 0, sizeof(P));
-    P.in_cplx = B.data(); P.in_es = n; P.in_ls = 1; P.in_bs = nn; P.out_cplx = A.data(); P.out_es = n; P.out_ls = 1; P.out_bs = nn;
-    P.inverse = 1; P.scale = 1.0 / (double)n;
-    run(P);
-    memset(&P, 0, sizeof(P));
-    P.in_cplx = A.data(); P.in_es = 1; P.in_ls = n; P.in_bs = nn; P.out_real = out; P.out_es = 1; P.out_ls = n; P.out_bs = nn;
-    P.inverse = 1; P.scale = 1.0 / (double)n;
-    run(P);
+    }
     return 0;
 }
 

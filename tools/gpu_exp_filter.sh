@@ -22,7 +22,7 @@ for window in (200e3, 100e3):
     sel = np.linspace(0, xc.size - 1, 20000).astype(int)
     iy0, ix0, nw = G._origins_device(window, xc[sel], yc[sel])
     filt = G._window_filter(functools.partial(G.upward_continuation, height=1000.0), nw)
-    tf, stack = timed(lambda: G._filter_windows_device(filt, iy0, ix0, nw))
+    tf, stack = timed(lambda: G._filter_windows_device(filt, g, iy0, ix0, nw))
     plan = _plans.spectrum_plan(nw, G.dx, _plans.taper_vector(np.hanning, nw))
     sy = torch.arange(20000, dtype=torch.int32, device="cuda") * nw
     sx = torch.zeros(20000, dtype=torch.int32, device="cuda")
