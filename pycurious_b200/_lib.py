@@ -150,3 +150,15 @@ def device_info():
     a, b, c, d = _I(), _I(), _I(), _I64()
     check(lib.cb_device_info(C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
     return dict(sm_count=a.value, cc=(b.value, c.value), smem_optin=d.value)
+
+
+def to_device_async(arr):
+    """Host array -> device tensor without blocking the host behind the stream's earlier work: the bytes are staged
+    in page-locked memory from torch's caching host allocator (which keeps the block until the copy has run) and
+    copied asynchronously.  A plain `.cuda()` of a pageable array waits for everything queued before it -- e.g. the
+    135 MB grid upload a batch call has just started -- and with it every bit of host-side planning that follows."""
+    torch = require_cuda()
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.numel() == 0:
+        return t.cuda()
+    return t.pin_memory().cuda(non_blocking=True)

@@ -158,7 +158,7 @@ class CurieGrid(object):
             iy0 = iy0 - np.int32(r0)
         if c0:
             ix0 = ix0 - np.int32(c0)
-        iy0_t, ix0_t = torch.from_numpy(iy0).cuda(), torch.from_numpy(ix0).cuda()
+        iy0_t, ix0_t = _lib.to_device_async(iy0), _lib.to_device_async(ix0)     # (not behind the grid upload)
         iy0_t._cb_host, ix0_t._cb_host = iy0, ix0      # the spectrum plan groups windows by ix0 on the host
         return iy0_t, ix0_t
 
@@ -197,8 +197,8 @@ class CurieGrid(object):
         g, r0, c0 = self._device_region(iyu, ixu, n)
         iyu, ixu = iyu - np.int32(r0), ixu - np.int32(c0)
         rows, cols = iyu.size, ixu.size
-        iy0_t = torch.from_numpy(iyu).cuda().repeat_interleave(cols)
-        ix0_t = torch.from_numpy(ixu).cuda().repeat(rows)
+        iy0_t = _lib.to_device_async(iyu).repeat_interleave(cols)
+        ix0_t = _lib.to_device_async(ixu).repeat(rows)
         iy0_t._cb_host, ix0_t._cb_host = np.repeat(iyu, cols), np.tile(ixu, rows)
         return g, iy0_t, ix0_t, n
 

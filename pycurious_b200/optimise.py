@@ -291,7 +291,7 @@ class CurieOptimise(CurieGrid):
             opt.x0[j], opt.lb[j], opt.ub[j] = float(x0[j]), lb[j], ub[j]
             opt.prior_mu[j], opt.prior_sigma[j] = mu[j], sg[j]
         opt.max_iter, opt.gtol, opt.ftol = int(max_iter), float(gtol), float(ftol)
-        k_t = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float64)).cuda()
+        k_t = _lib.to_device_async(np.ascontiguousarray(k, dtype=np.float64))
         x_t = torch.empty((n, 4), dtype=torch.float64, device="cuda")
         f_t = torch.empty(n, dtype=torch.float64, device="cuda") if diagnostics else None
         it_t = torch.empty(n, dtype=torch.int32, device="cuda") if diagnostics else None
