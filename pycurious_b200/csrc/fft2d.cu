@@ -3,10 +3,13 @@
 // Kernel body: fft2d_body.cuh.
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 #include "fft_plan.h"
 #include "fft2d_body.cuh"
+
+typedef void (*line_fft_fn)(const LineFftParams);
 
 struct cb_fft_plan {
     int n = 0, bluestein = 0, line_slots = 0;
@@ -15,14 +18,21 @@ struct cb_fft_plan {
     int32_t *d_slot = nullptr;
     int teams = 1, sm_count = 0;
     int64_t smem_bytes = 0;
+    line_fft_fn kernel = nullptr;      // generic, or the static engine whose pass list matches (Bluestein lengths 256 / 320 / 512 / 640)
+    int stage_slots = 0;               // twiddles + filter staged in shared memory in front of the lines (static engines)
 };
 
 extern __shared__ double2 cb_fft2d_smem[];
 
+template <class Engine>
 __global__ void __launch_bounds__(512, 1) line_fft_kernel(const __grid_constant__ LineFftParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_fft2d_smem)};
-    line_fft_body(cx, P);
+    line_fft_body<Engine>(cx, P);
 }
+typedef StaticFft<8, 8, 8> LFft512;
+typedef StaticFft<8, 8, 4> LFft256;
+typedef StaticFft<8, 8, 5> LFft320;
+typedef StaticFft<8, 8, 10> LFft640;
 
 __global__ void __launch_bounds__(256) op_half_kernel(const double2 *op, int n, double2 *op_half) {
     DevCtx cx{nullptr};
@@ -73,13 +83,21 @@ int cb_fft_plan_create(int n, cb_fft_plan **out) {
     }
     p->line_slots = (fft_line_slots(p->fft.n) + 1) & ~1;
     if (p->bluestein) filt.resize(p->line_slots, cplx(0.0, 0.0));
+    p->kernel = line_fft_kernel<GenericFft>;
+    if (p->bluestein && !getenv("CB_SPEC_GENERIC")) {
+        if (LFft512::matches(p->fft)) p->kernel = line_fft_kernel<LFft512>;
+        else if (LFft256::matches(p->fft)) p->kernel = line_fft_kernel<LFft256>;
+        else if (LFft320::matches(p->fft)) p->kernel = line_fft_kernel<LFft320>;
+        else if (LFft640::matches(p->fft)) p->kernel = line_fft_kernel<LFft640>;
+        if (p->kernel != line_fft_kernel<GenericFft>) p->stage_slots = (p->fft.tw_count + p->line_slots + 1) & ~1;
+    }
     int dev = 0;
     cudaDeviceProp prop;
     CB_CUDA_TRY_OR(cudaGetDevice(&dev), delete p);
     CB_CUDA_TRY_OR(cudaGetDeviceProperties(&prop, dev), delete p);
     p->sm_count = prop.multiProcessorCount;
     const int64_t line_bytes = (int64_t)p->line_slots * 16;
-    const int teams = (int)std::min<int64_t>(16, (int64_t)prop.sharedMemPerBlockOptin / line_bytes);
+    const int teams = (int)std::min<int64_t>(16, ((int64_t)prop.sharedMemPerBlockOptin - (int64_t)p->stage_slots * 16) / line_bytes);
     if (teams < 1) {
         cb_set_error("length %d needs a %lld-byte shared-memory line (limit %lld)", n, (long long)line_bytes,
                      (long long)prop.sharedMemPerBlockOptin);
@@ -87,13 +105,13 @@ int cb_fft_plan_create(int n, cb_fft_plan **out) {
         return CB_ERR_UNSUPPORTED;
     }
     p->teams = teams;
-    p->smem_bytes = (int64_t)teams * line_bytes;
+    p->smem_bytes = (int64_t)p->stage_slots * 16 + (int64_t)teams * line_bytes;
     if ((rc = upload_vec(&p->d_tw, tw)) || (rc = upload_vec(&p->d_chirp, chirp)) || (rc = upload_vec(&p->d_filt, filt)) ||
         (rc = upload_vec(&p->d_slot, slot))) {
         cb_fft_plan_destroy(p);
         return rc;
     }
-    CB_CUDA_TRY_OR(cudaFuncSetAttribute(line_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB_CUDA_TRY_OR(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)prop.sharedMemPerBlockOptin), cb_fft_plan_destroy(p));
     *out = p;
     return CB_OK;
@@ -102,9 +120,10 @@ int cb_fft_plan_create(int n, cb_fft_plan **out) {
 static int launch_lines(const cb_fft_plan *p, LineFftParams &P, cudaStream_t st) {
     P.n = p->n; P.bluestein = p->bluestein; P.fft = p->fft;
     P.tw = p->d_tw; P.chirp = p->d_chirp; P.filt = p->d_filt; P.slot = p->d_slot; P.line_slots = p->line_slots;
+    P.stage_slots = p->stage_slots;
     const int64_t ctas = (P.nlines + p->teams - 1) / p->teams;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)p->sm_count * 2));
-    line_fft_kernel<<<grid, p->teams * CB_WARP, (size_t)p->smem_bytes, st>>>(P);
+    p->kernel<<<grid, p->teams * CB_WARP, (size_t)p->smem_bytes, st>>>(P);
     CB_CUDA_TRY(cudaGetLastError());
     return CB_OK;
 }

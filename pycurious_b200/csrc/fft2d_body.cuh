@@ -48,14 +48,27 @@ struct LineFftParams {
     const double2 *tw, *chirp, *filt;   // global tables (filt padded like a line)
     const int32_t *slot;                // direct mode: slot of X[k]
     int32_t line_slots;
+    int32_t stage_slots;                // shared-memory slots holding tw + filt in front of the lines (0: read from global)
 };
 
-template <class Ctx>
+// Engine = GenericFft (any length, tables read from global memory) or a StaticFft whose pass list matches the plan
+// (the Bluestein lengths of the BASELINE window sizes): twiddles and Bluestein filter are then staged in shared
+// memory in front of the lines (P.stage_slots double2 slots) and the passes run with compile-time strides.
+template <class Engine, class Ctx>
 CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
     const int tid = cx.tid(), nthr = cx.nthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
     const int n = P.n, M = P.fft.n;
-    double2 *buf = reinterpret_cast<double2 *>(cx.smem()) + (int64_t)warp * P.line_slots;
+    double2 *sm = reinterpret_cast<double2 *>(cx.smem());
+    const double2 *tw = P.tw, *filt = P.filt;
+    if (P.stage_slots > 0) {
+        for (int i = tid; i < P.fft.tw_count; i += nthr) sm[i] = P.tw[i];
+        for (int i = tid; i < P.line_slots; i += nthr) sm[P.fft.tw_count + i] = P.filt[i];
+        cx.sync_block();
+        tw = sm;
+        filt = sm + P.fft.tw_count;
+    }
+    double2 *buf = sm + P.stage_slots + (int64_t)warp * P.line_slots;
     for (int64_t line = (int64_t)cx.bid() * nwarps + warp; line < P.nlines; line += (int64_t)cx.nblocks() * nwarps) {
         cx.sync_warp();
         int64_t img = 0, l = line;
@@ -84,8 +97,8 @@ CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
             }
             buf[CB_PAD(x)] = z;
         }
-        if (P.bluestein) GenericFft::convolve(cx, buf, P.tw, P.filt, P.fft, lane);
-        else GenericFft::forward(cx, buf, P.tw, P.fft, lane);
+        if (P.bluestein) Engine::convolve(cx, buf, tw, filt, P.fft, lane);
+        else Engine::forward(cx, buf, tw, P.fft, lane);
         auto X = [&](int k) -> double2 {
             return P.bluestein ? cmul(Ctx::ldg(P.chirp + k), cconj(buf[CB_PAD(k)])) : buf[CB_PAD(Ctx::ldg(P.slot + k))];
         };

@@ -330,7 +330,7 @@ int emu_fft2_filter(const double *data, int64_t ny, int64_t nx, const double *fi
     auto run = [&](const Plan &pl, LineFftParams P) {
         P.bluestein = pl.bl; P.fft = pl.fft; P.tw = pl.tw.data(); P.chirp = pl.chirp.data(); P.filt = pl.filt.data();
         P.slot = pl.slot.data(); P.line_slots = pl.line_slots;
-        emu_launch(2, 64, (size_t)2 * pl.line_slots * 16, [&](const HostCtx &cx) { line_fft_body(cx, P); });
+        emu_launch(2, 64, (size_t)2 * pl.line_slots * 16, [&](const HostCtx &cx) { line_fft_body<GenericFft>(cx, P); });
     };
     LineFftParams P;
     memset(&P, 0, sizeof(P));
@@ -373,7 +373,7 @@ int emu_fft2_filter_windows(const double *grid, int64_t ny, int64_t nx, const in
         fft2_windows_pass(pass, n, nwin, grid, nx, iy0, ix0, A.data(), B.data(), oph.data(), out, P);
         P.bluestein = bl; P.fft = fft; P.tw = tw.data(); P.chirp = chirp.data(); P.filt = filt.data();
         P.slot = slot.data(); P.line_slots = line_slots;
-        emu_launch(3, 64, (size_t)2 * line_slots * 16, [&](const HostCtx &cx) { line_fft_body(cx, P); });
+        emu_launch(3, 64, (size_t)2 * line_slots * 16, [&](const HostCtx &cx) { line_fft_body<GenericFft>(cx, P); });
     }
     return 0;
 }
