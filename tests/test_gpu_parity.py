@@ -426,6 +426,39 @@ def test_fit_paths_agree(grid, monkeypatch):
     assert np.array_equal(x.cpu().numpy(), base)
 
 
+def test_fit_terminates_on_hostile_spectra(grid):
+    """Rows of NaN / inf / huge / constant values, mixed with good ones, in one batch: every row finishes (status
+    code set, iteration and evaluation counts within the solver's bounds), the good rows are unaffected by their
+    neighbours, and a non-finite start gives the reference's 1e99 behaviour (FIT_BAD_START, optimise.py:226-227)."""
+    import torch
+    g = load_golden("fit.npz")
+    k, good = g["w200_k"], g["w200_phi"]
+    rng = np.random.default_rng(11)
+    rows = [good[i % good.shape[0]].copy() for i in range(64)]
+    rows[3][:] = np.nan
+    rows[7][10] = np.inf
+    rows[11][:] = 1e300
+    rows[13][:] = -1e300
+    rows[17][:] = 5.0
+    rows[19][::2] = -np.inf
+    rows[23] = rng.standard_normal(k.size) * 1e6
+    rows[29] = rng.standard_normal(k.size) * 1e-300
+    phi = np.ascontiguousarray(np.stack(rows))
+    x, d = grid._fit_device(k, torch.from_numpy(phi).cuda(), (3.0, 1.0, 10.0, 5.0), diagnostics=True)
+    torch.cuda.synchronize()
+    x, st, it, nf = x.cpu().numpy(), d["status"].cpu().numpy(), d["niter"].cpu().numpy(), d["nfev"].cpu().numpy()
+    assert np.all((st >= 0) & (st <= 4)) and np.all(it <= 200) and np.all(nf <= 3 * 200 * 41 + 3)
+    for bad in (3, 7, 19):                                   # non-finite objective at the start
+        assert st[bad] == 4 and np.allclose(x[bad], (3.0, 1.0, 10.0, 5.0))
+    ref, _ = grid._fit_device(k, torch.from_numpy(np.ascontiguousarray(good)).cuda(), (3.0, 1.0, 10.0, 5.0), diagnostics=True)
+    ref = ref.cpu().numpy()
+    hostile = {3, 7, 11, 13, 17, 19, 23, 29}
+    for i in range(64):
+        if i not in hostile:
+            assert np.array_equal(x[i], ref[i % good.shape[0]]), i
+    assert np.all(np.isfinite(x[[j for j in range(64) if j not in (3, 7, 19)]]))
+
+
 def test_fft_domain_filters_match_reference(grid, oracle, mag):
     """CurieGrid.upward_continuation / reduce_to_pole (grid.py:405-546): FFTs on the device, golden outputs of
     the reference itself; also as a `process_subgrid` callback of optimise (optimise.py:282-294)."""
