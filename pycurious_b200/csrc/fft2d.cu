@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(512, 1) line_fft_kernel(const __grid_constant_
 typedef StaticFft<8, 8, 8> LFft512;
 typedef StaticFft<8, 8, 4> LFft256;
 typedef StaticFft<8, 8, 5> LFft320;
-typedef StaticFft<8, 8, 10> LFft640;
+typedef StaticFft<8, 10, 8> LFft640;
 
 __global__ void __launch_bounds__(256) op_half_kernel(const double2 *op, int n, double2 *op_half) {
     DevCtx cx{nullptr};

@@ -247,7 +247,7 @@ CB_BODY void bluestein_convolve(const Ctx &cx, double2 *buf, const double2 *tw, 
 // runtime strides: IMAD + LEA = 24 % of the spectrum kernel's instructions, ncu r01e) as on FP64
 // work; with the pass list in the template all of it folds into immediates and the butterfly
 // loops unroll.  Selected on the host for the pass lists the BASELINE window sizes produce
-// (201 -> 512 = 8.8.8, 101 -> 256 = 8.8.4, 129 -> 320 = 8.8.5, 301 -> 640 = 8.8.10); anything
+// (201 -> 512 = 8.8.8, 101 -> 256 = 8.8.4, 129 -> 320 = 8.8.5, 301 -> 640 = 8.10.8); anything
 // else runs the generic engine.  Table layouts (twiddles, filter) are identical.
 // =====================================================================================
 // w[s] = w1^s, s = 1..R-1, by at most three dependent complex products (<= 4 ulp): the static
@@ -387,7 +387,10 @@ struct StaticFft {
 
     static constexpr int NIT = (N / R0 + CB_WARP - 1) / CB_WARP;    // first-pass butterflies per lane
     // a second line's inputs are held in registers beside the transform (12 complex values spill a little and still pay)
-    static constexpr bool PREFETCH = FUSED_SPAN > 0 && NIT * HALF <= 12;
+#ifndef CB_PREFETCH_MAX
+#define CB_PREFETCH_MAX 12
+#endif
+    static constexpr bool PREFETCH = FUSED_SPAN > 0 && NIT * HALF <= CB_PREFETCH_MAX;
     // line index of input (it, t) of lane `lane` in the first pass
     CB_HD static int input_index(int it, int t, int lane) { return it * CB_WARP + lane + t * (N / R0); }
 

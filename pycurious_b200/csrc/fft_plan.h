@@ -32,10 +32,13 @@ static inline std::vector<int> smooth_radices(int N) {
     if (c2 == 1) r.push_back(2);
     for (int i = 0; i < c5; ++i) r.push_back(5);
     for (int i = 0; i < c3; ++i) r.push_back(3);
-    // 640 = 8 * 8 * 10: the (2, 5) tail becomes one twiddle-free radix-10 pass (Dft<10>), three passes instead of
-    // four -- the Bluestein length of the 301-node windows of BASELINE config 5.  Only this length, so that every
-    // other size keeps the plan its static engine was built for.
-    if (N == 640) { r.clear(); r.push_back(8); r.push_back(8); r.push_back(10); }
+    // 640 = 8 * 10 * 8: the factors 2 and 5 become one radix-10 pass (Dft<10>, Good-Thomas inside), three passes
+    // instead of four -- the Bluestein length of the 301-node windows of BASELINE config 5.  The radix-10 pass sits
+    // in the MIDDLE: the pruned first / last passes and the fused filter pass then all run the radix-8 butterfly with
+    // its linear padded addressing (8.8.10, radix 10 in the fused pass, measured 55.1 ms against 45.2 ms for the
+    // 36100 windows of a 4096^2 lattice at 20 km stride, gpurun r02v).  Only this length, so that every other size
+    // keeps the plan its static engine was built for.
+    if (N == 640) { r.clear(); r.push_back(8); r.push_back(10); r.push_back(8); }
     return r;
 }
 
@@ -52,7 +55,7 @@ static inline int bluestein_length(int n) {
         std::vector<int> r = smooth_radices(M);
         if (r.empty() || (int)r.size() > CB_MAX_PASS) continue;
         double c = plan_cost(M, r);
-        // lengths served by a compile-time engine (fft_engine.cuh: 8.8.4, 8.8.5, 8.8.8, 8.8.10 with fused, pruned
+        // lengths served by a compile-time engine (fft_engine.cuh: 8.8.4, 8.8.5, 8.8.8, 8.10.8 with fused, pruned
         // first / last passes) run ~1.5x faster per streamed point than the runtime-radix engine
         if (!(M == 256 || M == 320 || M == 512 || M == 640)) c *= 1.5;
         if (!best || c < best_cost) { best = M; best_cost = c; }

@@ -46,7 +46,7 @@ colspec_kernel(const __grid_constant__ SpectrumParams P) {
 typedef StaticFft<8, 8, 8> Fft512;      // nw 201 (and 129..256 that pad to 512)
 typedef StaticFft<8, 8, 4> Fft256;      // nw 101
 typedef StaticFft<8, 8, 5> Fft320;      // nw 129
-typedef StaticFft<8, 8, 10> Fft640;     // nw 301
+typedef StaticFft<8, 10, 8> Fft640;     // nw 301
 
 __global__ void __launch_bounds__(256) detrend_kernel(const __grid_constant__ DetrendParams P) {
     DevCtx cx{reinterpret_cast<char *>(cb_dyn_smem)};
@@ -76,7 +76,7 @@ static void pick_spectrum_kernels(cb_spectrum_plan *pl) {
         if (Fft512::matches(hp.fft) && hp.n <= Fft512::FUSED_SPAN) return set_kernels<Fft512>(pl, "static 8.8.8");
         if (Fft256::matches(hp.fft) && hp.n <= Fft256::FUSED_SPAN) return set_kernels<Fft256>(pl, "static 8.8.4");
         if (Fft320::matches(hp.fft) && hp.n <= Fft320::FUSED_SPAN) return set_kernels<Fft320>(pl, "static 8.8.5");
-        if (Fft640::matches(hp.fft) && hp.n <= Fft640::FUSED_SPAN) return set_kernels<Fft640>(pl, "static 8.8.10");
+        if (Fft640::matches(hp.fft) && hp.n <= Fft640::FUSED_SPAN) return set_kernels<Fft640>(pl, "static 8.10.8");
     }
     set_kernels<GenericFft>(pl, "generic");
 }

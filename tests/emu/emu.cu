@@ -97,7 +97,7 @@ int emu_dft(int n, const double *in_re_im, double *out_re_im) {
         else if (StaticFft<8, 8, 8>::matches(fft)) StaticFft<8, 8, 8>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
         else if (StaticFft<8, 8, 4>::matches(fft)) StaticFft<8, 8, 4>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
         else if (StaticFft<8, 8, 5>::matches(fft)) StaticFft<8, 8, 5>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
-        else if (StaticFft<8, 8, 10>::matches(fft)) StaticFft<8, 8, 10>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
+        else if (StaticFft<8, 10, 8>::matches(fft)) StaticFft<8, 10, 8>::convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
         else bluestein_convolve(cx, line.data(), tw.data(), filt.data(), fft, lane);
         for (int k = lane; k < n; k += 32) {
             double2 z = direct ? line[CB_PAD(slot[k])] : bluestein_out(line.data(), chirp.data(), k);
@@ -140,8 +140,8 @@ int emu_spectrum(int nw, int nbins, const double *taper_r, const double *taper_c
         emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 4>>(cx, P); });
     else if (!generic && StaticFft<8, 8, 5>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 5>::FUSED_SPAN)
         emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 5>>(cx, P); });
-    else if (!generic && StaticFft<8, 8, 10>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 10>::FUSED_SPAN)
-        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 10>>(cx, P); });
+    else if (!generic && StaticFft<8, 10, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 10, 8>::FUSED_SPAN)
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 10, 8>>(cx, P); });
     else
         emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<GenericFft>(cx, P); });
     return 0;
@@ -197,7 +197,7 @@ int emu_spectrum_shared(int nw, int nbins, const double *taper_r, const double *
     if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 8>>(nblocks, hp, P);
     else if (!generic && StaticFft<8, 8, 4>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 4>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 4>>(nblocks, hp, P);
     else if (!generic && StaticFft<8, 8, 5>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 5>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 5>>(nblocks, hp, P);
-    else if (!generic && StaticFft<8, 8, 10>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 10>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 10>>(nblocks, hp, P);
+    else if (!generic && StaticFft<8, 10, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 10, 8>::FUSED_SPAN) emu_run_shared<StaticFft<8, 10, 8>>(nblocks, hp, P);
     else emu_run_shared<GenericFft>(nblocks, hp, P);
     return 0;
 }

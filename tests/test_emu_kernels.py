@@ -62,7 +62,7 @@ def test_fft_engine_matches_numpy(emu, n):
 
 
 def test_plan_choices_for_baseline_windows(emu, oracle):
-    """none of BASELINE's windows is smooth -> Bluestein on 256 / 320 / 512 / 640 (= 8.8.10, three
+    """none of BASELINE's windows is smooth -> Bluestein on 256 / 320 / 512 / 640 (= 8.10.8, three
     passes with the twiddle-free radix-10 butterfly, instead of 625 = 5^4)."""
     want = {101: 256, 129: 320, 201: 512, 301: 640,
             175: 512, 151: 320, 281: 640}      # off-list sizes go to a compile-time engine's length too (not 360 / 576)
@@ -156,7 +156,7 @@ def test_shared_row_spectra_path_matches_oracle(emu, oracle, mag, nw, taper, det
 
 
 def test_spectrum_static_and_generic_engines_agree(emu, oracle, mag):
-    """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 8.8.10) against the runtime-radix engine."""
+    """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 8.10.8) against the runtime-radix engine."""
     d = np.ascontiguousarray(mag[0])
     for nw in (101, 129, 201, 301):
         origins = [(2, 3)]

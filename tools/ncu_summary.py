@@ -62,7 +62,13 @@ for f in os.listdir(tmp):
         dis[f] = run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)])
 
 
-def line_map(func):
+def norm(name):
+    return re.sub(r"\s+", "", name.replace("void ", "")).replace(">>", "> >").replace(" ", "")
+
+
+def line_map(func, full):
+    """PC offset -> (file, line) of ONE kernel: the .text section whose demangled name is `full` (a template has one
+    section per instantiation, all starting at offset 0)."""
     out, cur, active = {}, None, False
     func = "_Z%d%s" % (len(func), func)      # mangled prefix: "fit_kernel" must not match "misfit_kernel"
     for text in dis.values():
@@ -71,7 +77,7 @@ def line_map(func):
         for ln in text.splitlines():
             m = re.match(r"\s*\.text\.(\S+):", ln)
             if m:
-                active = func in m.group(1)
+                active = func in m.group(1) and norm(run(["c++filt", m.group(1)]).strip()) == norm(full)
                 continue
             if not active:
                 continue
@@ -95,7 +101,7 @@ for kn in dict.fromkeys(names):
     sh = src[h]
     stall_cols = [i for i, n in enumerate(sh) if n.startswith("stall_") and "Not Issued" not in n]
     ci = {n: sh.index(n) for n in ("# Samples", "Instructions Executed", "Thread Instructions Executed")}
-    lm = line_map(short)
+    lm = line_map(short, kn)
     base = None
     stalls = defaultdict(int)
     agg = defaultdict(lambda: [0, 0, 0])
