@@ -556,7 +556,10 @@ def run_gpu(args):
             mcmc["fp64_tflops_counted"] = counts["mh_flop_per_step_99"] * mcmc["value"] / 1e12
         # kernels of this repo per step: spectrum (row + column pass, or the one direct kernel), the k tables, and
         # the fit's template / begin / first / (rounds - 1) evaluation / rounds step / finish kernels
-        fit_rounds = int(os.environ.get("CB_FIT_ROUNDS", "20"))
+        import ctypes
+        fit_rounds = ctypes.c_int(0)
+        _lib.check(_lib.load().cb_fit_schedule(int(hi - lo), ctypes.byref(fit_rounds), None))   # this rank's share
+        fit_rounds = fit_rounds.value
         launches_per_step = (2 if shared else 1) + 1 + 3 + (fit_rounds - 1) + fit_rounds + 1
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",

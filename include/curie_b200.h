@@ -209,6 +209,11 @@ int cb_fit_batch(const double *kh_dev, int nk,
                  int32_t *nfev_dev /* [nwin] or NULL: model evaluations of nk points each */,
                  void *stream);
 
+/* The launch schedule cb_fit_batch uses for a pass of `nwin` windows: batched rounds at most, and the number of
+ * unfinished windows below which the straggler kernel takes over (environment CB_FIT_ROUNDS / CB_FIT_HANDOVER
+ * override both; results do not depend on either).  One call launches 3 + 2 * rounds + 1 kernels per pass. */
+int cb_fit_schedule(int64_t nwin, int *rounds, int *handover);
+
 /* Same fit with per-row prior means: prior_mu_dev[w, j] (NaN = keep opt->prior_mu[j]) replaces the
  * mean of the prior on parameter j for row w; a prior exists iff opt->prior_mu[j] is not NaN.  This is
  * the inner loop of CurieOptimise.sensitivity (optimise.py:705-716): each row is one simulation with its

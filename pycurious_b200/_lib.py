@@ -54,6 +54,7 @@ SIGNATURES = {
     "cb_host_register": (_I, [_VP, _I64]),
     "cb_host_unregister": (_I, [_VP]),
     "cb_release_scratch": (_I, []),
+    "cb_fit_schedule": (_I, [_I64, C.POINTER(_I), C.POINTER(_I)]),
     "cb_spectrum_plan_create": (_I, [_I, _I, _VP, _VP, _VP, _VP, C.POINTER(_VP)]),
     "cb_spectrum_plan_destroy": (_I, [_VP]),
     "cb_spectrum_plan_get_info": (_I, [_VP, C.POINTER(SpectrumPlanInfo)]),

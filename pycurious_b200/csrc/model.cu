@@ -299,6 +299,22 @@ int cb_misfit(const double *kh_dev, int nk, const double *phi_dev, int64_t phi_s
     return CB_OK;
 }
 
+// Batched rounds and hand-over threshold for a pass of `nwin` windows.  A late round costs a launch pair whose
+// duration no longer shrinks with the list (the step kernel's ~40 us of dependent solver algebra, ~50 us for an
+// evaluation), so a small pass hands its stragglers over sooner: measured on one B200 (tools/gpu_exp_fit_small.sh),
+// 19,012 windows 2.68 ms at (12 rounds, 1024) against 2.87 at (20, 2048); 38,025 windows 4.15 at (16, 2048) against
+// 4.28; 76,050 and 152,100 windows are fastest at (20, 2048).
+int cb_fit_schedule(int64_t nwin, int *rounds, int *handover) {
+    int r = nwin <= 24576 ? 12 : (nwin <= 49152 ? 16 : 20), h = nwin <= 24576 ? 1024 : 2048;
+    if (const char *e = getenv("CB_FIT_ROUNDS")) r = atoi(e);
+    if (const char *e = getenv("CB_FIT_HANDOVER")) h = atoi(e);
+    if (r < 1) r = 1;
+    if (h < 0) h = 0;
+    if (rounds) *rounds = r;
+    if (handover) *handover = h;
+    return CB_OK;
+}
+
 int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64_t nwin,
                       const cb_fit_options *opt_host, const double *x0_dev, const double *prior_mu_dev,
                       double *x_out_dev, double *f_out_dev, int32_t *niter_dev, int32_t *status_dev,
@@ -316,12 +332,8 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
     // tuning / test knobs, read per call: CB_FIT_HANDOVER = unfinished windows below which the finish kernel takes
     // over (0: never before the last round), CB_FIT_ROUNDS = batched rounds at most, CB_FIT_PASS = windows per pass
     // of the scratch; every setting gives the same results (tests/test_gpu_parity.py::test_fit_paths_agree)
-    int env_handover = 2048, env_rounds = 20;
     int64_t env_pass = CB_FIT_PASS_WINDOWS;
-    if (const char *e = getenv("CB_FIT_HANDOVER")) env_handover = atoi(e);
-    if (const char *e = getenv("CB_FIT_ROUNDS")) env_rounds = atoi(e);
     if (const char *e = getenv("CB_FIT_PASS")) env_pass = atoll(e);
-    if (env_rounds < 1) env_rounds = 1;
     if (env_pass < 1 || env_pass > CB_FIT_PASS_WINDOWS) env_pass = CB_FIT_PASS_WINDOWS;
     int dev_id = 0, sm_count = 0;
     CB_CUDA_TRY(cudaGetDevice(&dev_id));
@@ -359,6 +371,8 @@ int cb_fit_batch_rows(const double *kh_dev, int nk, const double *phi_dev, int64
         P.sums = P.coef + (size_t)pass * 3 * FC_COUNT;
         int32_t *la = reinterpret_cast<int32_t *>(P.sums + (size_t)pass * 16), *lb = la + pass;
         P.list_in = la; P.list_out = lb;
+        int env_rounds = 0, env_handover = 0;
+        cb_fit_schedule(n, &env_rounds, &env_handover);
         P.handover = env_handover;
         fit_template_kernel<<<1, 1, 0, st>>>(P);
         fit_begin_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(P);

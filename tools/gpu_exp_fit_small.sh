@@ -25,7 +25,9 @@ for share in (8, 4, 2):
         for _ in range(reps): out = G._fit_device(plan.k, phi, (3.0, 1.0, 10.0, 5.0))
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
-    for ho, rounds in ((2048, 20), (2048, 12), (2048, 16), (1024, 20), (1024, 16), (512, 20), (512, 16), (256, 16), (4096, 12), (4096, 8), (1024, 12), (512, 12), (0, 20)):
+    os.environ.pop("CB_FIT_HANDOVER", None); os.environ.pop("CB_FIT_ROUNDS", None)
+    print("windows", m, "default schedule", "fit %.3f ms" % timed(), flush=True)
+    for ho, rounds in ((2048, 20), (2048, 16), (1024, 12), (1024, 10), (1024, 14), (2048, 14)):
         os.environ["CB_FIT_HANDOVER"] = str(ho); os.environ["CB_FIT_ROUNDS"] = str(rounds)
         print("windows", m, "handover", ho, "rounds", rounds, "fit %.3f ms" % timed(), flush=True)
 PY
