@@ -228,21 +228,34 @@ def workload_config(args, nwin, world):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled beside the run (the recipe's clocks line, every 20 ms, time-stamped).  It is started BEFORE the
+    warm-up -- nvidia-smi needs ~0.2 s to produce its first line, more than a whole 8-GPU timed region -- and `mark()`
+    / `stop()` bracket the timed region: only samples stamped inside it are summarised.  A region shorter than two
+    polls falls back to every sample since the start (the warm-up runs the same kernels) and says so in `window`."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
+        import datetime
+        self.now = datetime.datetime.now
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.now()
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
+    def mark(self):
+        """The timed region starts now."""
+        self.t0 = self.now()
+
     def stop(self):
+        import datetime
+        t1 = self.now()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -253,25 +266,30 @@ class ClockSampler(object):
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, smax, power, reasons = [], [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f:
             c = [v.strip() for v in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(c[2]), float(c[3]), float(c[4]),
+                             [nm for nm, v in zip(names, c[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
-            hot = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
-            out.update(sm_mhz=float(np.median(hot)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(power)))
+        inside = [r for r in rows if self.t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 2 and len(rows) > len(inside):
+            inside, window = rows, "warm-up + timed region (the timed region is shorter than two 20 ms polls)"
+        if inside:
+            power = [r[3] for r in inside]
+            hot = [r[1] for r in inside if r[3] >= 0.5 * max(power)] or [r[1] for r in inside]
+            out.update(sm_mhz=float(np.median(hot)), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted({nm for r in inside for nm in r[4]}), samples=len(inside),
+                       power_w_max=float(max(power)), window=window)
         return out
 
 
@@ -347,10 +365,12 @@ def run_gpu(args):
             return pdist.gather_blocks(x, nwin, dst=0)
         return x
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     e0, e1 = ev(), ev()
     e0.record()
     for _ in range(args.steps):
@@ -373,6 +393,8 @@ def run_gpu(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         if s >= e2e_warm:
             e2e_times.append(dt)
+        elif s == e2e_warm - 1 and sampler:
+            sampler.mark()
     rows_up = int(g_dev.shape[0]) * int(g_dev.shape[1]) * 8 + 2 * 4 * (hi - lo) + 8 * plan.k.size
     h2d_t = torch.tensor([float(rows_up)], dtype=torch.float64, device="cuda")
     if world > 1:
