@@ -479,10 +479,11 @@ struct StaticFft {
     }
 
     // conj((a (*) b)[k]) -> sk(k, .) for k < FUSED_SPAN, with a[x] = ld(x) (zero beyond FUSED_SPAN).
-    // The caller guarantees that no lane still reads buf (one warp barrier is issued first).
+    // The caller guarantees that no lane still reads buf (one warp barrier is issued first).  (chirp, n: the
+    // Bluestein chirp of the line length n, used by PlusOneFft only.)
     template <class Ctx, class Loader, class Sink>
     CB_BODY static void convolve_io(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, int lane,
-                                    Loader ld, Sink sk) {
+                                    const double2 *, int, Loader ld, Sink sk) {
         cx.sync_warp();
         first_pass(buf, tw, lane, ld);
         cx.sync_warp();
@@ -529,6 +530,44 @@ struct StaticFft {
     template <class Ctx>
     CB_BODY static void forward(const Ctx &cx, double2 *buf, const double2 *tw, const FftPlan &pl, int lane) {
         fft_forward_dif(cx, buf, tw, pl, lane);      // direct (smooth) sizes are not the hot case
+    }
+};
+
+// A static engine serving ONE more node than its pruned passes hold: lines of n = FUSED_SPAN + 1 = N/2 + 1 nodes
+// (129 on 256, 161 on 320, 257 on 512, 321 on 640) with the Bluestein length N = 2n - 2.
+//   * The chirp filter is even, b[m] = b[-m] = exp(i pi m^2 / n), so a circular length of 2n - 2 is enough: the only
+//     taps that alias are m = +-(n-1), and they are equal (build_bluestein_tables writes that slot twice with the
+//     same value; the unpruned engines need nothing more).
+//   * The pruned passes take inputs x < n-1 and give outputs k < n-1.  The convolution is linear, so the last input
+//     goes around the transform as a rank-1 term, y[k] += a[n-1] b[k-(n-1)], and the last output is one dot product,
+//     y[n-1] = sum_j a[j] b[n-1-j], accumulated while the inputs are loaded and summed over the warp.
+// Against the next length the planner would have to take (320 for 129, 640 for 257) every pass fills its lanes
+// exactly once or twice instead of 1.25 / 2.5 times.
+template <class Base>
+struct PlusOneFft : Base {
+    static constexpr int FUSED_SPAN = Base::FUSED_SPAN + 1;
+    static constexpr bool PREFETCH = false;
+    static bool serves(const FftPlan &pl, int n) { return Base::matches(pl) && n == FUSED_SPAN && pl.n == 2 * n - 2; }
+    template <class Ctx, class Loader, class Sink>
+    CB_BODY static void convolve_io(const Ctx &cx, double2 *buf, const double2 *tw, const double2 *filt, int lane,
+                                    const double2 *chirp, int n, Loader ld, Sink sk) {
+        const double2 a_last = ld(n - 1);                       // the same address on every lane: one broadcast
+        const double2 ca = cconj(a_last);
+        double2 acc = cplx(0.0, 0.0);
+        auto ld1 = [&](int x) -> double2 {                      // x < n - 1 by construction of the pruned first pass
+            const double2 z = ld(x);
+            const double2 c = chirp[n - 1 - x];                 // b[n-1-x] = conj(chirp[n-1-x])
+            acc.x += fma(z.x, c.x, z.y * c.y);
+            acc.y += fma(z.y, c.x, -z.x * c.y);
+            return z;
+        };
+        // the sink receives conj(y[k]); conj(a_last b[k-(n-1)]) = conj(a_last) chirp[n-1-k]
+        auto sk1 = [&](int k, double2 zc) { sk(k, cadd(zc, cmul(ca, chirp[n - 1 - k]))); };
+        Base::convolve_io(cx, buf, tw, filt, lane, chirp, n, ld1, sk1);
+        acc.x = cx.warp_sum(acc.x);
+        acc.y = cx.warp_sum(acc.y);
+        cx.sync_warp();
+        if (lane == 0) sk(n - 1, cplx(acc.x + a_last.x, -(acc.y + a_last.y)));      // b[0] = 1
     }
 };
 

@@ -48,7 +48,14 @@ static inline double plan_cost(int N, const std::vector<int> &radices) {
     return (double)N * (2.0 * (double)radices.size() - 1.0);
 }
 
+static inline bool static_engine_length(int M) { return M == 256 || M == 320 || M == 512 || M == 640; }
+
 static inline int bluestein_length(int n) {
+    // The chirp filter is even (b[m] = b[-m]), so the circular length only has to reach 2n - 2: the two taps that
+    // alias there, m = +-(n-1), are equal.  Taken when it lands on a compile-time engine (n = 129, 161, 257, 321:
+    // PlusOneFft in fft_engine.cuh carries the last node around the pruned passes); the next usable length would be
+    // 1.25x longer and fill the lanes of every pass worse.
+    if (n >= 3 && static_engine_length(2 * n - 2)) return 2 * n - 2;
     int lo = 2 * n - 1, best = 0;
     double best_cost = 0;
     for (int M = lo; M <= 2 * lo + 16; ++M) {
@@ -57,7 +64,7 @@ static inline int bluestein_length(int n) {
         double c = plan_cost(M, r);
         // lengths served by a compile-time engine (fft_engine.cuh: 8.8.4, 8.8.5, 8.8.8, 8.10.8 with fused, pruned
         // first / last passes) run ~1.5x faster per streamed point than the runtime-radix engine
-        if (!(M == 256 || M == 320 || M == 512 || M == 640)) c *= 1.5;
+        if (!static_engine_length(M)) c *= 1.5;
         if (!best || c < best_cost) { best = M; best_cost = c; }
     }
     return best;

@@ -43,9 +43,9 @@ colspec_kernel(const __grid_constant__ SpectrumParams P) {
 
 // FFT engines compiled in: static pass lists for the Bluestein lengths of the BASELINE window sizes,
 // the generic runtime-radix engine for everything else.
-typedef StaticFft<8, 8, 8> Fft512;      // nw 201 (and 129..256 that pad to 512)
-typedef StaticFft<8, 8, 4> Fft256;      // nw 101
-typedef StaticFft<8, 8, 5> Fft320;      // nw 129
+typedef StaticFft<8, 8, 8> Fft512;      // nw 201 (and 162..256; 257 through PlusOneFft)
+typedef StaticFft<8, 8, 4> Fft256;      // nw 101 (and 129 through PlusOneFft)
+typedef StaticFft<8, 8, 5> Fft320;      // nw 130..160 (and 161 through PlusOneFft)
 typedef StaticFft<8, 10, 8> Fft640;     // nw 301
 
 __global__ void __launch_bounds__(256) detrend_kernel(const __grid_constant__ DetrendParams P) {
@@ -73,6 +73,11 @@ static void set_kernels(cb_spectrum_plan *pl, const char *name) {
 static void pick_spectrum_kernels(cb_spectrum_plan *pl) {
     const SpectrumHostPlan &hp = pl->hp;
     if (hp.bluestein && !getenv("CB_SPEC_GENERIC")) {
+        // lines of N/2 + 1 nodes on the length-N engine (Bluestein length 2n - 2, see PlusOneFft)
+        if (PlusOneFft<Fft256>::serves(hp.fft, hp.n)) return set_kernels<PlusOneFft<Fft256>>(pl, "static 8.8.4 + 1");
+        if (PlusOneFft<Fft320>::serves(hp.fft, hp.n)) return set_kernels<PlusOneFft<Fft320>>(pl, "static 8.8.5 + 1");
+        if (PlusOneFft<Fft512>::serves(hp.fft, hp.n)) return set_kernels<PlusOneFft<Fft512>>(pl, "static 8.8.8 + 1");
+        if (PlusOneFft<Fft640>::serves(hp.fft, hp.n)) return set_kernels<PlusOneFft<Fft640>>(pl, "static 8.10.8 + 1");
         if (Fft512::matches(hp.fft) && hp.n <= Fft512::FUSED_SPAN) return set_kernels<Fft512>(pl, "static 8.8.8");
         if (Fft256::matches(hp.fft) && hp.n <= Fft256::FUSED_SPAN) return set_kernels<Fft256>(pl, "static 8.8.4");
         if (Fft320::matches(hp.fft) && hp.n <= Fft320::FUSED_SPAN) return set_kernels<Fft320>(pl, "static 8.8.5");

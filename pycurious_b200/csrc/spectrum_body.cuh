@@ -277,7 +277,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                 auto sk = [&](int k, double2 z) {
                     if (k < n) buf[CB_PAD(k)] = z;
                 };
-                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, s_chirp, n, ld, sk);
                 cx.sync_warp();
             }
             if (!fused) {
@@ -349,7 +349,7 @@ CB_BODY void spectrum_body(const Ctx &cx, const SpectrumParams &P) {
                 auto sk = [&](int u, double2 z) {
                     if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, cb_half_log(fma(z.x, z.x, z.y * z.y)));
                 };
-                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, s_chirp, n, ld, sk);
             }
             if (!fused) {
                 for (int yb = 0; yb < n; yb += 4 * CB_WARP) {
@@ -457,7 +457,7 @@ CB_BODY void rowspec_body(const Ctx &cx, const SpectrumParams &P) {
             auto sk = [&](int k, double2 z) {
                 if (k < n) buf[CB_PAD(k)] = z;
             };
-            Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+            Engine::convolve_io(cx, buf, s_tw, s_filt, lane, s_chirp, n, ld, sk);
             cx.sync_warp();
         }
         if (!fused) {
@@ -598,7 +598,7 @@ CB_BODY void colspec_body(const Ctx &cx, const SpectrumParams &P) {
                 auto sk = [&](int u, double2 z) {
                     if ((u <= lo_end || u >= hi_start) && u < n) Ctx::stcg(out + u, cb_half_log(fma(z.x, z.x, z.y * z.y)));
                 };
-                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, ld, sk);
+                Engine::convolve_io(cx, buf, s_tw, s_filt, lane, s_chirp, n, ld, sk);
             }
             if (!fused) {
                 cx.sync_warp();

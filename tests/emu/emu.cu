@@ -134,7 +134,15 @@ int emu_spectrum(int nw, int nbins, const double *taper_r, const double *taper_c
     P.gt = gt.data(); P.lh = lh.data();
     // same engine selection as the product (spectrum.cu:pick_spectrum_kernel); max_teams < 0 forces the generic engine
     const bool generic = max_teams < 0 || !hp.bluestein;
-    if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN)
+    if (!generic && PlusOneFft<StaticFft<8, 8, 4>>::serves(hp.fft, hp.n))
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<PlusOneFft<StaticFft<8, 8, 4>>>(cx, P); });
+    else if (!generic && PlusOneFft<StaticFft<8, 8, 5>>::serves(hp.fft, hp.n))
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<PlusOneFft<StaticFft<8, 8, 5>>>(cx, P); });
+    else if (!generic && PlusOneFft<StaticFft<8, 8, 8>>::serves(hp.fft, hp.n))
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<PlusOneFft<StaticFft<8, 8, 8>>>(cx, P); });
+    else if (!generic && PlusOneFft<StaticFft<8, 10, 8>>::serves(hp.fft, hp.n))
+        emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<PlusOneFft<StaticFft<8, 10, 8>>>(cx, P); });
+    else if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN)
         emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 8>>(cx, P); });
     else if (!generic && StaticFft<8, 8, 4>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 4>::FUSED_SPAN)
         emu_launch(nblocks, hp.threads, (size_t)hp.smem_bytes, [&](const HostCtx &cx) { spectrum_body<StaticFft<8, 8, 4>>(cx, P); });
@@ -194,7 +202,11 @@ int emu_spectrum_shared(int nw, int nbins, const double *taper_r, const double *
     if (detrend) P.rowsum = rowsum.data();
     (void)ny;
     const bool generic = max_teams < 0 || !hp.bluestein;
-    if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 8>>(nblocks, hp, P);
+    if (!generic && PlusOneFft<StaticFft<8, 8, 4>>::serves(hp.fft, hp.n)) emu_run_shared<PlusOneFft<StaticFft<8, 8, 4>>>(nblocks, hp, P);
+    else if (!generic && PlusOneFft<StaticFft<8, 8, 5>>::serves(hp.fft, hp.n)) emu_run_shared<PlusOneFft<StaticFft<8, 8, 5>>>(nblocks, hp, P);
+    else if (!generic && PlusOneFft<StaticFft<8, 8, 8>>::serves(hp.fft, hp.n)) emu_run_shared<PlusOneFft<StaticFft<8, 8, 8>>>(nblocks, hp, P);
+    else if (!generic && PlusOneFft<StaticFft<8, 10, 8>>::serves(hp.fft, hp.n)) emu_run_shared<PlusOneFft<StaticFft<8, 10, 8>>>(nblocks, hp, P);
+    else if (!generic && StaticFft<8, 8, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 8>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 8>>(nblocks, hp, P);
     else if (!generic && StaticFft<8, 8, 4>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 4>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 4>>(nblocks, hp, P);
     else if (!generic && StaticFft<8, 8, 5>::matches(hp.fft) && hp.n <= StaticFft<8, 8, 5>::FUSED_SPAN) emu_run_shared<StaticFft<8, 8, 5>>(nblocks, hp, P);
     else if (!generic && StaticFft<8, 10, 8>::matches(hp.fft) && hp.n <= StaticFft<8, 10, 8>::FUSED_SPAN) emu_run_shared<StaticFft<8, 10, 8>>(nblocks, hp, P);

@@ -40,8 +40,8 @@ class MhOpt(C.Structure):
 
 
 # ------------------------------------------------------------------------------------ FFT engine
-@pytest.mark.parametrize("n", [4, 5, 6, 8, 9, 10, 15, 16, 25, 27, 30, 64, 100, 101, 125, 128, 129, 151, 201, 240,
-                               256, 301, 305, 320, 401, 625, 640, 1000])
+@pytest.mark.parametrize("n", [4, 5, 6, 8, 9, 10, 15, 16, 25, 27, 30, 64, 100, 101, 125, 128, 129, 151, 161, 201, 240,
+                               256, 257, 301, 305, 320, 321, 401, 625, 640, 1000])
 def test_fft_engine_matches_numpy(emu, n):
     rng = np.random.default_rng(n)
     x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
@@ -58,14 +58,16 @@ def test_fft_engine_matches_numpy(emu, n):
             smooth //= p
     assert (M == 0) == (smooth == 1)          # direct mixed radix iff 2/3/5-smooth, else Bluestein
     if M:
-        assert M >= 2 * n - 1
+        assert M >= 2 * n - 2          # the chirp is even: 2n - 2 is enough (fft_plan.h:bluestein_length)
+        assert (M == 2 * n - 2) == (n in (129, 161, 257, 321))
 
 
 def test_plan_choices_for_baseline_windows(emu, oracle):
     """none of BASELINE's windows is smooth -> Bluestein on 256 / 320 / 512 / 640 (= 8.10.8, three
     passes with the twiddle-free radix-10 butterfly, instead of 625 = 5^4)."""
-    want = {101: 256, 129: 320, 201: 512, 301: 640,
-            175: 512, 151: 320, 281: 640}      # off-list sizes go to a compile-time engine's length too (not 360 / 576)
+    want = {101: 256, 201: 512, 301: 640,
+            175: 512, 151: 320, 281: 640,      # off-list sizes go to a compile-time engine's length too (not 360 / 576)
+            129: 256, 161: 320, 257: 512, 131: 320}      # N/2 + 1 nodes ride on the length-N engine (PlusOneFft)
     for nw, M in want.items():
         _, dk, edges = oracle.taper_and_bins(nw, nw, 1000.0, None)
         _, masks = oracle.radial_bin_masks(nw, dk, edges)
@@ -156,9 +158,10 @@ def test_shared_row_spectra_path_matches_oracle(emu, oracle, mag, nw, taper, det
 
 
 def test_spectrum_static_and_generic_engines_agree(emu, oracle, mag):
-    """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 8.10.8) against the runtime-radix engine."""
+    """The compile-time pass lists (8.8.8, 8.8.4, 8.8.5, 8.10.8, and their N/2 + 1-node forms for 129 / 161 / 257)
+    against the runtime-radix engine."""
     d = np.ascontiguousarray(mag[0])
-    for nw in (101, 129, 201, 301):
+    for nw in (101, 129, 161, 201, 257, 301):
         origins = [(2, 3)]
         a = _emu_spectrum(emu, oracle, d, origins, nw, np.hanning, 0, 2.0, max_teams=4)
         b = _emu_spectrum(emu, oracle, d, origins, nw, np.hanning, 0, 2.0, max_teams=-4)

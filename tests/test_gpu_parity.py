@@ -135,10 +135,10 @@ def test_shared_row_spectra_path_equals_direct_path(pc, grid, oracle, mag, detre
         np.testing.assert_allclose(ph[i], p0, rtol=1e-10)
 
 
-@pytest.mark.parametrize("nw", [20, 21, 30, 51, 64, 75, 128, 151, 256, 305])
+@pytest.mark.parametrize("nw", [20, 21, 30, 51, 64, 75, 128, 129, 151, 161, 256, 257, 305, 321])
 def test_window_size_sweep_both_paths(pc, oracle, nw):
     """Odd / even / prime / 2-3-5-smooth window edges (Bluestein on static and generic engines, direct
-    mixed radix), each through cb_spectrum_batch and cb_spectrum_batch_shared_rows, with taper + detrend,
+    mixed radix; 129 / 161 / 257 / 321 = N/2 + 1 nodes on the length-N static engines, PlusOneFft), each through cb_spectrum_batch and cb_spectrum_batch_shared_rows, with taper + detrend,
     against the oracle."""
     import torch
     from pycurious_b200 import _plans
