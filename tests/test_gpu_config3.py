@@ -148,5 +148,8 @@ def test_config3_size_independent_properties_all_windows(cfg3):
     expect = full.copy()
     expect[:, 3] += 2.0 * np.log(a)
     d = _rel(scaled, expect)
-    assert np.mean(d < 1e-4) >= 0.99, (np.mean(d < 1e-4), np.mean(d < 1e-6))
-    assert np.median(d) < 1e-7, np.median(d)
+    # measured (profiles/r02x_scale_property_config3.json): all 152,100 windows within 1e-4 (max 1.1e-5), 99.99 %
+    # within 1e-6, median 2e-10
+    assert np.mean(d < 1e-4) >= 0.999, (np.mean(d < 1e-4), np.mean(d < 1e-6))
+    assert np.mean(d < 1e-6) >= 0.995, np.mean(d < 1e-6)
+    assert np.median(d) < 1e-8, np.median(d)
