@@ -170,7 +170,9 @@ int cb_fft2_filter(const cb_fft_plan *plan_x, const cb_fft_plan *plan_y, const d
 int64_t cb_fft2_filter_windows_workspace_bytes(int n, int64_t nwin) {
     if (n <= 0 || nwin <= 0) return 0;
     const int64_t half = n / 2 + 1;
-    return (2 * nwin + 1) * (int64_t)n * half * 16 + 512;        // A, B [nwin][n][half] + the operator's Hermitian half
+    // A (and B, when the column passes are not fused: 2/3/5-smooth edges) [nwin][n][half] + the operator's Hermitian half
+    const int64_t stacks = cbplan::smooth_radices(n).empty() ? 1 : 2;
+    return (stacks * nwin + 1) * (int64_t)n * half * 16 + 512;
 }
 
 int cb_fft2_filter_windows(const cb_fft_plan *plan, const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
@@ -196,9 +198,11 @@ int cb_fft2_filter_windows(const cb_fft_plan *plan, const double *grid_dev, int6
     op_half_kernel<<<(int)std::min<int64_t>((n * half + 255) / 256, 1024), 256, 0, st>>>(
         reinterpret_cast<const double2 *>(filter_dev), (int)n, op_half);
     CB_CUDA_TRY(cudaGetLastError());
+    const bool fused = plan->bluestein != 0;      // column forward x operator x column inverse in one visit of the line
     for (int pass = 0; pass < 4; ++pass) {
+        if (fused && pass == 2) continue;
         LineFftParams P;
-        fft2_windows_pass(pass, (int)n, nwin, grid_dev, ld, iy0_dev, ix0_dev, A, B, op_half, out_dev, P);
+        fft2_windows_pass(pass, (int)n, nwin, grid_dev, ld, iy0_dev, ix0_dev, A, fused ? nullptr : B, op_half, out_dev, P, fused);
         const int rc = launch_lines(plan, P, st);
         if (rc) return rc;
     }

@@ -41,6 +41,10 @@ struct LineFftParams {
     //             symmetry) to two real lines
     //   pair = 0  plain complex lines (the column passes then run over the half columns only)
     int32_t pair, half;
+    // twice = 1 (Bluestein lines, pair = 0): the two column passes of a filter in one visit -- forward transform,
+    // times `mul`, inverse transform (scale applies to it), all in the warp's line; in and out may be the same array.
+    // Bit for bit what the two separate passes give (the value that would travel through global memory is the same).
+    int32_t twice;
     int32_t inverse;           // 1: conj in, conj out, scale
     double scale;
     int32_t bluestein;
@@ -112,6 +116,23 @@ CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
             }
             continue;
         }
+        if (P.twice) {
+            // forward output X[k] -> Y[k] = X[k] mul[k] -> input of the inverse transform, conj(Y[k]) chirp[k], written
+            // back to slot k (each lane rewrites the slots it read); the zero padding is restored
+            for (int k = lane; k < M; k += CB_WARP) {
+                double2 z = cplx(0.0, 0.0);
+                if (k < n) {
+                    const int64_t oi = l0 * P.out_ls + (int64_t)k * P.out_es;
+                    const double2 c = Ctx::ldg(P.chirp + k);
+                    z = cmul(cconj(cmul(cmul(c, cconj(buf[CB_PAD(k)])), Ctx::ldg(P.mul + oi))), c);
+                }
+                buf[CB_PAD(k)] = z;
+            }
+            Engine::convolve(cx, buf, tw, filt, P.fft, lane);
+            for (int k = lane; k < n; k += CB_WARP)
+                P.out_cplx[img * P.out_bs + l0 * P.out_ls + (int64_t)k * P.out_es] = cscale(cconj(X(k)), P.scale);
+            continue;
+        }
         for (int k = lane; k < n; k += CB_WARP) {
             double2 z = X(k);
             if (P.inverse) z = cscale(cconj(z), P.scale);
@@ -127,21 +148,23 @@ CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
     }
 }
 
-// The four passes of the window batch (cb_fft2_filter_windows and its emulation): windows gathered from the grid
+// The passes of the window batch (cb_fft2_filter_windows and its emulation): windows gathered from the grid
 // -> A[img][y][v] (v < half) -> B[img][u][v] = op_sym * column transform -> A (column inverse) -> real stack.
-// op_half = the Hermitian part of the operator on the half plane, [n][half].
+// op_half = the Hermitian part of the operator on the half plane, [n][half].  Bluestein lines (every odd BASELINE
+// window) take the two column passes in one visit, A -> A (pass 1 with fused = true, pass 2 skipped, no B).
 static inline void fft2_windows_pass(int pass, int n, int64_t nwin, const double *grid, int64_t ld, const int32_t *iy0,
                                      const int32_t *ix0, double2 *A, double2 *B, const double2 *op_half, double *out,
-                                     LineFftParams &P) {
+                                     LineFftParams &P, bool fused = false) {
     const int64_t half = n / 2 + 1, npairs = (n + 1) / 2, img = (int64_t)n * half;
     memset(&P, 0, sizeof(P));
     P.n = n; P.half = (int32_t)half; P.scale = 1.0;
     if (pass == 0) {            // row pairs forward, gathered from the grid
         P.pair = 1; P.in_real = grid; P.in_es = 1; P.in_ls = ld; P.in_ld = ld; P.iy0 = iy0; P.ix0 = ix0;
         P.out_cplx = A; P.out_es = 1; P.out_ls = half; P.out_bs = img; P.lines_per_img = npairs; P.nlines = nwin * npairs;
-    } else if (pass == 1) {     // half columns forward, times the operator
-        P.in_cplx = A; P.in_es = half; P.in_ls = 1; P.in_bs = img; P.out_cplx = B; P.out_es = half; P.out_ls = 1; P.out_bs = img;
+    } else if (pass == 1) {     // half columns forward, times the operator (fused: and back, in place)
+        P.in_cplx = A; P.in_es = half; P.in_ls = 1; P.in_bs = img; P.out_cplx = fused ? A : B; P.out_es = half; P.out_ls = 1; P.out_bs = img;
         P.lines_per_img = half; P.nlines = nwin * half; P.mul = op_half;
+        if (fused) { P.twice = 1; P.scale = 1.0 / (double)n; }
     } else if (pass == 2) {     // half columns inverse
         P.in_cplx = B; P.in_es = half; P.in_ls = 1; P.in_bs = img; P.out_cplx = A; P.out_es = half; P.out_ls = 1; P.out_bs = img;
         P.lines_per_img = half; P.nlines = nwin * half; P.inverse = 1; P.scale = 1.0 / (double)n;

@@ -381,8 +381,9 @@ int emu_fft2_filter_windows(const double *grid, int64_t ny, int64_t nx, const in
     std::vector<double2> A(nwin * n * half), B(nwin * n * half), oph(n * half);
     for (int64_t i = 0; i < (int64_t)oph.size(); ++i) oph[i] = op_half_entry(reinterpret_cast<const double2 *>(filter_re_im), n, i);
     for (int pass = 0; pass < 4; ++pass) {
+        if (bl && pass == 2) continue;                  // Bluestein lines: pass 1 does both column transforms
         LineFftParams P;
-        fft2_windows_pass(pass, n, nwin, grid, nx, iy0, ix0, A.data(), B.data(), oph.data(), out, P);
+        fft2_windows_pass(pass, n, nwin, grid, nx, iy0, ix0, A.data(), bl ? nullptr : B.data(), oph.data(), out, P, bl != 0);
         P.bluestein = bl; P.fft = fft; P.tw = tw.data(); P.chirp = chirp.data(); P.filt = filt.data();
         P.slot = slot.data(); P.line_slots = line_slots;
         emu_launch(3, 64, (size_t)2 * line_slots * 16, [&](const HostCtx &cx) { line_fft_body<GenericFft>(cx, P); });
