@@ -277,7 +277,8 @@ int cb_fft2_filter(const cb_fft_plan *plan_x /* length nx */, const cb_fft_plan 
  * complex128 [n, n] operator, `out_dev` a dense [nwin, n, n] stack that cb_spectrum_batch can read as a grid of
  * nwin*n rows.  The caller validates the origins (0 <= iy0 <= ny-n, 0 <= ix0 <= nx-n).  Real windows have Hermitian
  * spectra and real(ifft2(op * .)) acts through the Hermitian part of `op` only: the library forms that part on the
- * half plane and runs row pairs / half the columns (4 * ceil(n/2) line transforms per window instead of 4 n). */
+ * half plane and runs row pairs / half the columns (4 * ceil(n/2) line transforms per window instead of 4 n); on
+ * Bluestein lines (n not 2/3/5-smooth) the forward and inverse column transforms share one visit of the line. */
 int64_t cb_fft2_filter_windows_workspace_bytes(int n, int64_t nwin);
 int cb_fft2_filter_windows(const cb_fft_plan *plan, const double *grid_dev, int64_t ny, int64_t nx, int64_t ld,
                            const int32_t *iy0_dev, const int32_t *ix0_dev, int64_t nwin, const void *filter_dev,
