@@ -81,28 +81,43 @@ CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
         const bool has1 = P.pair && l0 + 1 < P.n;                     // (pair modes: square images, n lines of n elements)
         int64_t in0 = img * P.in_bs + l0 * P.in_ls;
         if (P.iy0) in0 += (int64_t)Ctx::ldg(P.iy0 + img) * P.in_ld + Ctx::ldg(P.ix0 + img);
-        for (int x = lane; x < M; x += CB_WARP) {
-            double2 z = cplx(0.0, 0.0);
-            if (x < n) {
-                if (P.pair == 1) {
-                    z = cplx(P.in_real[in0 + (int64_t)x * P.in_es], has1 ? P.in_real[in0 + P.in_ls + (int64_t)x * P.in_es] : 0.0);
-                } else if (P.pair == 2) {
-                    // Z[x] = A0[x] + i A1[x], the half lines extended by A[n - x] = conj A[x]
-                    const bool up = x >= P.half;
-                    const int64_t xi = up ? n - x : x;
-                    double2 a = P.in_cplx[in0 + xi * P.in_es];
-                    double2 b = has1 ? P.in_cplx[in0 + P.in_ls + xi * P.in_es] : cplx(0.0, 0.0);
-                    if (up) { a = cconj(a); b = cconj(b); }
-                    z = cplx(a.x - b.y, a.y + b.x);
-                } else if (P.in_real) z = cplx(P.in_real[in0 + (int64_t)x * P.in_es], 0.0);
-                else z = P.in_cplx[in0 + (int64_t)x * P.in_es];
-                if (P.inverse) z = cconj(z);
-                if (P.bluestein) z = cmul(z, Ctx::ldg(P.chirp + x));
+        // element x < n of the line as the transform takes it (pair packing, conjugation for the inverse, chirp)
+        auto element = [&](int x) -> double2 {
+            double2 z;
+            if (P.pair == 1) {
+                z = cplx(P.in_real[in0 + (int64_t)x * P.in_es], has1 ? P.in_real[in0 + P.in_ls + (int64_t)x * P.in_es] : 0.0);
+            } else if (P.pair == 2) {
+                // Z[x] = A0[x] + i A1[x], the half lines extended by A[n - x] = conj A[x]
+                const bool up = x >= P.half;
+                const int64_t xi = up ? n - x : x;
+                double2 a = P.in_cplx[in0 + xi * P.in_es];
+                double2 b = has1 ? P.in_cplx[in0 + P.in_ls + xi * P.in_es] : cplx(0.0, 0.0);
+                if (up) { a = cconj(a); b = cconj(b); }
+                z = cplx(a.x - b.y, a.y + b.x);
+            } else if (P.in_real) z = cplx(P.in_real[in0 + (int64_t)x * P.in_es], 0.0);
+            else z = P.in_cplx[in0 + (int64_t)x * P.in_es];
+            if (P.inverse) z = cconj(z);
+            if (P.bluestein) z = cmul(z, Ctx::ldg(P.chirp + x));
+            return z;
+        };
+        // Static engines on lines that fit their pruned passes: the first pass pulls its inputs straight from
+        // `element`, the last one leaves the n live outputs in the line (no fill pass, no zero padding in memory).
+        bool pruned = false;
+        if constexpr (Engine::FUSED_SPAN > 0) pruned = P.bluestein && n <= Engine::FUSED_SPAN;
+        auto keep = [&](int k, double2 z) {
+            if (k < n) buf[CB_PAD(k)] = z;
+        };
+        if (pruned) {
+            if constexpr (Engine::FUSED_SPAN > 0) {
+                auto ld = [&](int x) -> double2 { return x < n ? element(x) : cplx(0.0, 0.0); };
+                Engine::convolve_io(cx, buf, tw, filt, lane, P.chirp, n, ld, keep);
+                cx.sync_warp();
             }
-            buf[CB_PAD(x)] = z;
+        } else {
+            for (int x = lane; x < M; x += CB_WARP) buf[CB_PAD(x)] = x < n ? element(x) : cplx(0.0, 0.0);
+            if (P.bluestein) Engine::convolve(cx, buf, tw, filt, P.fft, lane);
+            else Engine::forward(cx, buf, tw, P.fft, lane);
         }
-        if (P.bluestein) Engine::convolve(cx, buf, tw, filt, P.fft, lane);
-        else Engine::forward(cx, buf, tw, P.fft, lane);
         auto X = [&](int k) -> double2 {
             return P.bluestein ? cmul(Ctx::ldg(P.chirp + k), cconj(buf[CB_PAD(k)])) : buf[CB_PAD(Ctx::ldg(P.slot + k))];
         };
@@ -117,18 +132,24 @@ CB_BODY void line_fft_body(const Ctx &cx, const LineFftParams &P) {
             continue;
         }
         if (P.twice) {
-            // forward output X[k] -> Y[k] = X[k] mul[k] -> input of the inverse transform, conj(Y[k]) chirp[k], written
-            // back to slot k (each lane rewrites the slots it read); the zero padding is restored
-            for (int k = lane; k < M; k += CB_WARP) {
-                double2 z = cplx(0.0, 0.0);
-                if (k < n) {
-                    const int64_t oi = l0 * P.out_ls + (int64_t)k * P.out_es;
-                    const double2 c = Ctx::ldg(P.chirp + k);
-                    z = cmul(cconj(cmul(cmul(c, cconj(buf[CB_PAD(k)])), Ctx::ldg(P.mul + oi))), c);
+            // forward output X[k] -> Y[k] = X[k] mul[k] -> input of the inverse transform, conj(Y[k]) chirp[k]
+            auto again = [&](int k) -> double2 {
+                const int64_t oi = l0 * P.out_ls + (int64_t)k * P.out_es;
+                const double2 c = Ctx::ldg(P.chirp + k);
+                return cmul(cconj(cmul(cmul(c, cconj(buf[CB_PAD(k)])), Ctx::ldg(P.mul + oi))), c);
+            };
+            if (pruned) {
+                // a first-pass butterfly reads the slots it writes, and they were filled by this lane's own sink
+                if constexpr (Engine::FUSED_SPAN > 0) {
+                    auto ld = [&](int x) -> double2 { return x < n ? again(x) : cplx(0.0, 0.0); };
+                    Engine::convolve_io(cx, buf, tw, filt, lane, P.chirp, n, ld, keep);
+                    cx.sync_warp();
                 }
-                buf[CB_PAD(k)] = z;
+            } else {
+                // written back to slot k (each lane rewrites the slots it read); the zero padding is restored
+                for (int k = lane; k < M; k += CB_WARP) buf[CB_PAD(k)] = k < n ? again(k) : cplx(0.0, 0.0);
+                Engine::convolve(cx, buf, tw, filt, P.fft, lane);
             }
-            Engine::convolve(cx, buf, tw, filt, P.fft, lane);
             for (int k = lane; k < n; k += CB_WARP)
                 P.out_cplx[img * P.out_bs + l0 * P.out_ls + (int64_t)k * P.out_es] = cscale(cconj(X(k)), P.scale);
             continue;

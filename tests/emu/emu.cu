@@ -386,7 +386,19 @@ int emu_fft2_filter_windows(const double *grid, int64_t ny, int64_t nx, const in
         fft2_windows_pass(pass, n, nwin, grid, nx, iy0, ix0, A.data(), bl ? nullptr : B.data(), oph.data(), out, P, bl != 0);
         P.bluestein = bl; P.fft = fft; P.tw = tw.data(); P.chirp = chirp.data(); P.filt = filt.data();
         P.slot = slot.data(); P.line_slots = line_slots;
-        emu_launch(3, 64, (size_t)2 * line_slots * 16, [&](const HostCtx &cx) { line_fft_body<GenericFft>(cx, P); });
+        // same engine selection as cb_fft_plan_create: the static engines stage twiddles + filter in front of the lines
+        // and run their pruned passes on lines that fit
+        const int stage = (fft.tw_count + line_slots + 1) & ~1;
+        auto run_static = [&](auto engine_tag) {
+            typedef decltype(engine_tag) E;
+            P.stage_slots = stage;
+            emu_launch(3, 64, (size_t)(stage + 2 * line_slots) * 16, [&](const HostCtx &cx) { line_fft_body<E>(cx, P); });
+        };
+        if (bl && StaticFft<8, 8, 8>::matches(fft)) run_static(StaticFft<8, 8, 8>());
+        else if (bl && StaticFft<8, 8, 4>::matches(fft)) run_static(StaticFft<8, 8, 4>());
+        else if (bl && StaticFft<8, 8, 5>::matches(fft)) run_static(StaticFft<8, 8, 5>());
+        else if (bl && StaticFft<8, 10, 8>::matches(fft)) run_static(StaticFft<8, 10, 8>());
+        else emu_launch(3, 64, (size_t)2 * line_slots * 16, [&](const HostCtx &cx) { line_fft_body<GenericFft>(cx, P); });
     }
     return 0;
 }
