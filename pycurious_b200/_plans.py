@@ -33,6 +33,27 @@ def nearest_node(coords, q):
     return np.where(pick_lo, lo, hi).astype(np.int64)
 
 
+def nearest_nodes_of_list(coords, q):
+    """nearest_node for one axis of a centroid LIST.  Lists come from create_centroid_list (a raveled meshgrid,
+    grid.py:196-197) or are contiguous blocks of one (a rank's share): along x the values repeat with the lattice's
+    column count, along y they come in runs.  Either structure is detected with O(n) comparisons and only the distinct
+    values are searched (two binary searches per centroid are the largest host cost of a block otherwise);
+    anything else takes the plain path.  The result is nearest_node(coords, q) in every case."""
+    n = q.size
+    if n < 4096:
+        return nearest_node(coords, q)
+    change = np.flatnonzero(q[1:] != q[:-1])
+    if change.size * 16 <= n:                                   # runs of equal values (the slow axis)
+        starts = np.concatenate(([0], change + 1))
+        return np.repeat(nearest_node(coords, q[starts]), np.diff(np.append(starts, n)))
+    rep = np.flatnonzero(q[1:] == q[0])
+    if rep.size:                                                # period p (the fast axis)
+        p = int(rep[0]) + 1
+        if 2 * p <= n and (q[p:] == q[:-p]).all():
+            return np.resize(nearest_node(coords, q[:p]), n)
+    return nearest_node(coords, q)
+
+
 def _lattice_shape(xc, yc):
     """(rows, cols) when (xc, yc) is a raveled meshgrid with x fastest (what create_centroid_list returns,
     grid.py:196-197), else None.  O(n) comparisons instead of two searches per centroid."""
@@ -71,9 +92,9 @@ def window_origins(g, window, xc, yc):
         rows, cols = lat
         ix = np.tile(nearest_node(g.xcoords, xc[:cols]), rows)
         iy = np.repeat(nearest_node(g.ycoords, yc[::cols]), cols)
-    else:
-        ix = nearest_node(g.xcoords, xc)
-        iy = nearest_node(g.ycoords, yc)
+    else:                                # blocks of a lattice (a rank's share) keep its structure per axis
+        ix = nearest_nodes_of_list(g.xcoords, xc)
+        iy = nearest_nodes_of_list(g.ycoords, yc)
     bad = (ix - half < 0) | (ix + half + 1 > g.nx) | (iy - half < 0) | (iy + half + 1 > g.ny)
     if bad.any():
         i = int(np.flatnonzero(bad)[0])

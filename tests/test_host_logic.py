@@ -263,6 +263,13 @@ def test_lattice_fast_path_equals_generic_rule(pc):
     assert _plans._lattice_shape(xc[perm], yc[perm]) is None
     iy2, ix2, _ = _plans.window_origins(G, 100e3, xc[perm], yc[perm])
     assert np.array_equal(ix2, ix0[perm]) and np.array_equal(iy2, iy0[perm])
+    # contiguous blocks of the list (one rank's share): they start and end in the middle of a lattice row
+    for lo, hi in ((0, xc.size // 3 + 5), (xc.size // 3 + 5, 2 * xc.size // 3 - 11), (17, xc.size - 3), (40, 40 + 4096)):
+        iy3, ix3, _ = _plans.window_origins(G, 100e3, xc[lo:hi], yc[lo:hi])
+        assert np.array_equal(ix3, ix0[lo:hi]) and np.array_equal(iy3, iy0[lo:hi])
+    # per axis: periodic, runs, one broken element, short lists, constant lists
+    for q in (xc, yc, xs, xc[5:5000], yc[5:5000], np.full(5000, xc[3]), np.r_[xc[:4000], xc[:4000][::-1]]):
+        assert np.array_equal(_plans.nearest_nodes_of_list(G.xcoords, q), _plans.nearest_node(G.xcoords, q))
 
 
 def test_lattice_origins_match_centroid_lists(pc):
