@@ -85,7 +85,12 @@ int cb_fft_plan_create(int n, cb_fft_plan **out) {
     if (p->bluestein) filt.resize(p->line_slots, cplx(0.0, 0.0));
     p->kernel = line_fft_kernel<GenericFft>;
     if (p->bluestein && !getenv("CB_SPEC_GENERIC")) {
-        if (LFft512::matches(p->fft)) p->kernel = line_fft_kernel<LFft512>;
+        // lines of N/2 + 1 nodes on the length-N engine (Bluestein length 2n - 2): the last node goes around the pruned passes
+        if (PlusOneFft<LFft256>::serves(p->fft, n)) p->kernel = line_fft_kernel<PlusOneFft<LFft256>>;
+        else if (PlusOneFft<LFft320>::serves(p->fft, n)) p->kernel = line_fft_kernel<PlusOneFft<LFft320>>;
+        else if (PlusOneFft<LFft512>::serves(p->fft, n)) p->kernel = line_fft_kernel<PlusOneFft<LFft512>>;
+        else if (PlusOneFft<LFft640>::serves(p->fft, n)) p->kernel = line_fft_kernel<PlusOneFft<LFft640>>;
+        else if (LFft512::matches(p->fft)) p->kernel = line_fft_kernel<LFft512>;
         else if (LFft256::matches(p->fft)) p->kernel = line_fft_kernel<LFft256>;
         else if (LFft320::matches(p->fft)) p->kernel = line_fft_kernel<LFft320>;
         else if (LFft640::matches(p->fft)) p->kernel = line_fft_kernel<LFft640>;

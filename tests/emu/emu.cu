@@ -394,7 +394,10 @@ int emu_fft2_filter_windows(const double *grid, int64_t ny, int64_t nx, const in
             P.stage_slots = stage;
             emu_launch(3, 64, (size_t)(stage + 2 * line_slots) * 16, [&](const HostCtx &cx) { line_fft_body<E>(cx, P); });
         };
-        if (bl && StaticFft<8, 8, 8>::matches(fft)) run_static(StaticFft<8, 8, 8>());
+        if (bl && PlusOneFft<StaticFft<8, 8, 4>>::serves(fft, n)) run_static(PlusOneFft<StaticFft<8, 8, 4>>());
+        else if (bl && PlusOneFft<StaticFft<8, 8, 5>>::serves(fft, n)) run_static(PlusOneFft<StaticFft<8, 8, 5>>());
+        else if (bl && PlusOneFft<StaticFft<8, 8, 8>>::serves(fft, n)) run_static(PlusOneFft<StaticFft<8, 8, 8>>());
+        else if (bl && StaticFft<8, 8, 8>::matches(fft)) run_static(StaticFft<8, 8, 8>());
         else if (bl && StaticFft<8, 8, 4>::matches(fft)) run_static(StaticFft<8, 8, 4>());
         else if (bl && StaticFft<8, 8, 5>::matches(fft)) run_static(StaticFft<8, 8, 5>());
         else if (bl && StaticFft<8, 10, 8>::matches(fft)) run_static(StaticFft<8, 10, 8>());

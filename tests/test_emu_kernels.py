@@ -455,12 +455,12 @@ def test_fft2_filter_body_matches_reference_filters(emu, oracle, mag, ny, nx):
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
 
 
-@pytest.mark.parametrize("n", [32, 51, 101, 129, 151])
+@pytest.mark.parametrize("n", [32, 51, 101, 129, 151, 161])
 def test_fft2_filter_window_batch_equals_per_window_reference(emu, oracle, mag, n):
     """The batched form (image index folded into the line index, first pass gathering from the grid): every
     window of the stack equals the reference filter applied to that window alone.  32: direct mixed radix, four
     passes; 51: generic Bluestein, fused column pass; 101 / 151: static engines with pruned passes fed straight from
-    the line's elements; 129: the 2n - 2 Bluestein length on the unpruned static engine."""
+    the line's elements; 129 / 161: the 2n - 2 Bluestein length, last node carried around the pruned passes."""
     d = np.ascontiguousarray(mag[0])
     iy0 = np.array([0, 7, min(100, d.shape[0] - n), d.shape[0] - n, 33], dtype=np.int32)
     ix0 = np.array([0, min(200, d.shape[1] - n), 3, d.shape[1] - n, 33], dtype=np.int32)

@@ -528,6 +528,29 @@ def test_filter_stage_recognised_in_batches(grid, oracle, mag, monkeypatch):
     assert grid._window_filter(lambda w: w, 101) is None
 
 
+@pytest.mark.parametrize("wkm", [50e3, 128e3, 150e3, 160e3])
+def test_filter_stage_window_sizes(grid, oracle, mag, wkm):
+    """The device filter stage on every line-engine path: 51 nodes (generic Bluestein), 129 and 161 (N/2 + 1 nodes on
+    the 256- and 320-point static engines, PlusOneFft), 151 (static engine, pruned passes) -- spectra of the filtered
+    windows against the reference sequence subgrid -> upward_continuation -> radial_spectrum."""
+    import functools
+    d, ext = mag
+    spec = oracle.GridSpec(d, *ext)
+    xc, yc = grid.create_centroid_list(wkm, 31e3, 37e3)
+    n = int(round(wkm / grid.dx)) + 1
+    stage = functools.partial(grid.upward_continuation, height=1200.0)
+    assert grid._window_filter(stage, n) is not None
+    k, phi, sig = grid._batch_spectra(wkm, xc, yc, np.hanning, stage, {})
+    phi, sig = phi.cpu().numpy(), sig.cpu().numpy()
+    filt = oracle.upward_continuation_filter((n, n), grid.dx, grid.dy, 1200.0)
+    for i in (0, xc.size // 2, xc.size - 1):
+        win = oracle.fft_filter(oracle.cut_window(spec, wkm, xc[i], yc[i]), filt)
+        k_o, phi_o, sig_o = oracle.radial_spectrum(win, spec.dx)
+        assert np.array_equal(k, k_o)
+        np.testing.assert_allclose(phi[i], phi_o, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(sig[i], sig_o, rtol=1e-8, atol=1e-9)
+
+
 def test_tanaka_batch_matches_reference(pc, grid, oracle, mag):
     """CurieGrid.tanaka_batch = radial_spectrum(power=0.5) -> tanaka1999 -> ComputeTanaka per centroid."""
     d, ext = mag
